@@ -1,0 +1,94 @@
+/* yacht_b200.h -- C ABI of the B200-native Yacht-Auction engine (libyacht_b200.so).
+ *
+ * This is the drop-in boundary for the reference's hot path.  The reference
+ * (iyioon/NYPC-Yacht-Auction) is pure Python and has no FFI of its own; each entry point
+ * below replaces the Python method cited next to it and is what a maintainer would bind
+ * with ctypes from yacht/YachtGame.py / MCTS.py (see INTEGRATION.md for the stub).
+ *
+ * Conventions
+ *   - Plain pointers and sizes only.  All `states`, `players`, ... pointers are DEVICE
+ *     pointers unless the function name contains `_host_`.  The caller owns every buffer.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream).  Calls are
+ *     asynchronous, never allocate and never synchronise (except the `_host_` variants).
+ *   - Return value: 0 on success, otherwise a cudaError_t value.
+ *   - Packed state: 8 x uint32 per game in two uint4 planes: words 0..3 of game g live at
+ *     states[4*g .. 4*g+3], words 4..7 at states[4*(stride+g) ..].  `stride` is the number
+ *     of games the buffer was allocated for (>= n).  Bit layout: csrc/ya_common.cuh and
+ *     DESIGN.md "Packed state".
+ *   - players are int8 +1 / -1 (Game.py:40-52).  Actions are int32 in [0, 3226)
+ *     (YachtGame.py:27-42): 202 bids then 12 x 252 (category, 5-of-10 subset) scores.
+ *   - Per-game status codes (int32): 0 ok; 1 ValueError "Invalid action in BID phase"
+ *     (YachtGame.py:268-269); 2 ValueError "Invalid action in SCORE phase" (:306-307);
+ *     3 RuntimeError "Invalid phase/state" (:372); 4 AssertionError in bid resolution (:508);
+ *     5 carry would exceed 10 dice (outside legal play; engine limit); 0x100 / 0x200: the
+ *     transition needs a tie-break / two dice rolls that were not injected (draw_mode 1).
+ */
+#ifndef YACHT_B200_H
+#define YACHT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define YA_ABI_VERSION 1
+#define YA_ACTION_SIZE 3226
+#define YA_FEATURE_SIZE 59
+#define YA_SCORE_TABLE_SIZE 3024
+
+int ya_abi_version(void);
+int ya_set_device(int device);
+
+/* getInitBoard (YachtGame.py:232-237) for n games: round 1, bid phase, rollA then rollB drawn
+ * from Philox(seed; game_base+g, episode[g], ply 0, tag INIT).  players/ply/episode may be NULL. */
+int ya_init_states(uint32_t* states, int64_t stride, int8_t* players, int32_t* ply, const uint32_t* episode,
+                   int64_t n, uint64_t seed, uint64_t game_base, void* stream);
+
+/* getNextState (YachtGame.py:260-372) incl. _resolve_bids_and_assign (:502-542).
+ * draw_mode 0: dice/tie-breaks from Philox(seed; game_base+g, episode[g], ply[g], tag, depth_sim[g]).
+ * draw_mode 1: draws injected by the host through the reference's own hooks roll_five /
+ *   tiebreak_uniform (:154-159): injected[g*12] = {tie, rollA[5], rollB[5], valid bits (1 tie, 2 rolls)}.
+ * in/out may alias.  status[g] as documented above; on error the state is copied unchanged. */
+int ya_next_state(const uint32_t* states_in, int64_t in_stride, const int8_t* players, const int32_t* actions,
+                  uint32_t* states_out, int64_t out_stride, int8_t* next_players, int32_t* status, int64_t n,
+                  int draw_mode, const uint8_t* injected, uint64_t seed, uint64_t game_base,
+                  const uint32_t* episode, const int32_t* ply, uint32_t tag, const uint32_t* depth_sim, void* stream);
+
+/* getValidMoves (YachtGame.py:374-406): masks is uint8[n][3226], 16-byte aligned. */
+int ya_valid_moves(const uint32_t* states, int64_t stride, const int8_t* players, uint8_t* masks, int64_t n, void* stream);
+
+/* getGameEnded (YachtGame.py:408-428): 0, +1, -1 or 1e-4 per game, from players[g]'s view. */
+int ya_game_ended(const uint32_t* states, int64_t stride, const int8_t* players, float* out, int64_t n, void* stream);
+
+/* getCanonicalForm (YachtGame.py:430-442): p1<->p2 and their pending bids swapped where players[g] == -1. */
+int ya_canonical_form(const uint32_t* states_in, int64_t in_stride, const int8_t* players,
+                      uint32_t* states_out, int64_t out_stride, int64_t n, void* stream);
+
+/* state_to_vec (yacht/NNet.py:50-86) of canonical states: features is float32[n][59]. */
+int ya_features(const uint32_t* states, int64_t stride, float* features, int64_t n, void* stream);
+
+/* RandomYachtPlayer.play (yacht/YachtPlayers.py:174-183): uniform over the legal set (0 if empty),
+ * index = (Philox word * count) >> 32 with tag ACTION. */
+int ya_random_action(const uint32_t* states, int64_t stride, const int8_t* players, int32_t* actions, int64_t n,
+                     uint64_t seed, uint64_t game_base, const uint32_t* episode, const int32_t* ply, void* stream);
+
+/* Scoring-move enumeration (the 12 x 252 loop of yacht/YachtPlayers.py:134-169 and
+ * score_category, YachtGame.py:57-108): scores is uint8[n][12][252] = points / 1000 of every
+ * (category, 5-of-10 subset) for the player to move, 0 where the subset does not fit. */
+int ya_enumerate_scores(const uint32_t* states, int64_t stride, const int8_t* players, uint8_t* scores, int64_t n,
+                        void* stream);
+
+/* One ply of Arena.playGame (Arena.py:49-71) with RandomYachtPlayer on both sides, for n games at
+ * once: legal mask written to masks (uint8[n][3226], may be NULL), action sampled, transition
+ * applied in place, outcome[g] = getGameEnded(board, 1) after the move (0 while running).  With
+ * auto_reset, a finished game is re-dealt (episode[g]++, ply 0).  err_flag (may be NULL) receives
+ * OR(1 << status) of any non-zero status. */
+int ya_play_ply(uint32_t* states, int64_t stride, int8_t* players, int32_t* ply, uint32_t* episode,
+                int32_t* actions, float* outcome, uint8_t* masks, int32_t* err_flag,
+                int64_t n, uint64_t seed, uint64_t game_base, int auto_reset, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* YACHT_B200_H */

@@ -1,0 +1,73 @@
+"""ctypes binding of libyacht_b200.so (the C ABI declared in include/yacht_b200.h).
+
+There is deliberately no fallback: if the CUDA library has not been built, importing a symbol
+raises; if it is called without a CUDA device the CUDA runtime error is raised.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libyacht_b200.so")
+
+_vp = ctypes.c_void_p
+_i64 = ctypes.c_int64
+_u64 = ctypes.c_uint64
+_u32 = ctypes.c_uint32
+_int = ctypes.c_int
+
+# name -> argtypes; every function returns int (0 / cudaError_t).  Must list every symbol of
+# include/yacht_b200.h (tests/test_abi.py parses the header and checks both directions).
+SIGNATURES = {
+    "ya_abi_version": [],
+    "ya_set_device": [_int],
+    "ya_init_states": [_vp, _i64, _vp, _vp, _vp, _i64, _u64, _u64, _vp],
+    "ya_next_state": [_vp, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _i64, _int, _vp, _u64, _u64, _vp, _vp, _u32, _vp, _vp],
+    "ya_valid_moves": [_vp, _i64, _vp, _vp, _i64, _vp],
+    "ya_game_ended": [_vp, _i64, _vp, _vp, _i64, _vp],
+    "ya_canonical_form": [_vp, _i64, _vp, _vp, _i64, _i64, _vp],
+    "ya_features": [_vp, _i64, _vp, _i64, _vp],
+    "ya_random_action": [_vp, _i64, _vp, _vp, _i64, _u64, _u64, _vp, _vp, _vp],
+    "ya_enumerate_scores": [_vp, _i64, _vp, _vp, _i64, _vp],
+    "ya_play_ply": [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _u64, _u64, _int, _vp],
+}
+
+_lib = None
+
+
+class YachtB200Error(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise YachtB200Error(
+            "%s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a).  There is no CPU fallback." % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = ctypes.c_int
+    _lib = lib
+    return lib
+
+
+def check(code, what):
+    if code != 0:
+        raise YachtB200Error("%s failed with CUDA error %d" % (what, code))
+
+
+def ptr(t):
+    """Device (or pinned-host) pointer of a torch tensor, or NULL."""
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def current_stream():
+    import torch
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)

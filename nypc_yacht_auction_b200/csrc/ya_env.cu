@@ -1,0 +1,402 @@
+// Yacht-Auction B200 engine -- environment kernels (init / transition / legal masks /
+// random-legal policy / outcomes / canonical form / features / scoring-move enumeration and
+// the fused "play one ply" kernel) and their C-ABI entry points (include/yacht_b200.h).
+//
+// Every entry point takes raw device pointers (torch owns the buffers), launches on the
+// stream it is given and returns a cudaError_t as int.  No allocation, no host sync.
+#include "ya_common.cuh"
+#include "../../include/yacht_b200.h"
+
+namespace {
+
+constexpr int kThreads = 256;
+
+__device__ __forceinline__ YaState ya_fresh_state(uint64_t seed, uint32_t gid, uint32_t episode) {
+    // getInitBoard: YachtGame.py:232-237 (rollA then rollB)
+    YaDraw d = ya_draw(seed, gid, episode, 0, YA_TAG_INIT, 0, 0);
+    YaState s;
+    s.w[0] = 1u;
+    s.w[1] = d.roll_a | (d.roll_b << 15);
+#pragma unroll
+    for (int i = 2; i < 8; ++i) s.w[i] = 0u;
+    return s;
+}
+
+// ------------------------------------------------------------------ init
+__global__ void ya_k_init(uint4* __restrict__ states, int64_t stride, int8_t* __restrict__ players,
+                          int32_t* __restrict__ ply, const uint32_t* __restrict__ episode,
+                          int64_t n, uint64_t seed, uint64_t game_base) {
+    int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n) return;
+    uint32_t ep = episode ? episode[g] : 0u;
+    YaState s = ya_fresh_state(seed, (uint32_t)(game_base + g), ep);
+    ya_store(states, stride, g, s);
+    if (players) players[g] = 1;
+    if (ply) ply[g] = 0;
+}
+
+// ------------------------------------------------------------------ getNextState
+// draw_mode 0: Philox on device, counter (game, episode, ply, tag, depth, sim).
+// draw_mode 1: draws injected by the host: inj[g*12 + 0] = tie, [1..5] rollA, [6..10] rollB,
+//              [11] = bitset of what is valid (1 = tie, 2 = rolls).  If a needed draw is not
+//              valid the state is left untouched and status = YA_NEED_* tells the host what to draw.
+__global__ void ya_k_next_state(const uint4* __restrict__ in, int64_t in_stride,
+                                const int8_t* __restrict__ players, const int32_t* __restrict__ actions,
+                                uint4* __restrict__ out, int64_t out_stride, int8_t* __restrict__ next_players,
+                                int32_t* __restrict__ status, int64_t n,
+                                int draw_mode, const uint8_t* __restrict__ inj,
+                                uint64_t seed, uint64_t game_base, const uint32_t* __restrict__ episode,
+                                const int32_t* __restrict__ ply, uint32_t tag, const uint32_t* __restrict__ depth_sim) {
+    int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n) return;
+    YaState s = ya_load(in, in_stride, g);
+    int pl = players[g];
+    int a = actions[g];
+    int needs = ya_draw_needs(s, pl, a);
+    YaDraw d;
+    d.roll_a = d.roll_b = d.tie = d.pick = 0;
+    int st = YA_OK;
+    int np = pl;
+    bool run = true;
+    if (needs) {
+        if (draw_mode == 0) {
+            uint32_t ds = depth_sim ? depth_sim[g] : 0u;
+            d = ya_draw(seed, (uint32_t)(game_base + g), episode ? episode[g] : 0u, ply ? (uint32_t)ply[g] : 0u,
+                        tag, ds & 0xFF, ds >> 8);
+        } else {
+            const uint8_t* t = inj + g * 12;
+            int have = t[11];
+            int missing = 0;
+            if ((needs & YA_NEED_TIE) && !(have & 1)) missing |= YA_NEED_TIE;
+            if ((needs & YA_NEED_ROLLS) && !(have & 2)) missing |= YA_NEED_ROLLS;
+            if (missing) { st = missing; run = false; }
+            d.tie = t[0];
+            for (int i = 0; i < 5; ++i) {
+                d.roll_a |= (uint32_t)t[1 + i] << (3 * i);
+                d.roll_b |= (uint32_t)t[6 + i] << (3 * i);
+            }
+        }
+    }
+    if (run) np = ya_transition(s, pl, a, d, &st);
+    ya_store(out, out_stride, g, s);
+    next_players[g] = (int8_t)np;
+    status[g] = st;
+}
+
+// ------------------------------------------------------------------ legal-mask writer
+// A game's mask row (uint8[3226], the reference's dtype: YachtGame.py:375) is 13 runs: 202
+// bid bytes then 12 x 252 category bytes.  Per game we keep H (13 head bits) and F (13 fill
+// bits): run r is F[r] everywhere except its first byte, which is H[r].  Ten-dice and bid
+// rows have F == H; five-dice rows have F = 0 for the category runs (only subset 0 fits).
+// Rows are 3226 B apart (only 2-byte aligned), so the buffer is written as one flat byte
+// stream with 16-byte vector stores; a vector spans at most two runs.
+__device__ __forceinline__ uint32_t ya_hf_from_desc(uint32_t desc) {
+    uint32_t h = desc & 0x1FFFu;
+    uint32_t f = (desc >> 13) ? h : (h & 1u);
+    return h | (f << 16);
+}
+
+__device__ __forceinline__ uint32_t ya_low_bytes_mask(int nbytes) {   // nbytes may be <0 or >4
+    int sh = min(max(nbytes, 0), 4) * 8;
+    return __funnelshift_lc(0xFFFFFFFFu, 0u, sh);
+}
+
+__device__ __forceinline__ uint4 ya_mask_vector(uint32_t cur, uint32_t nxt, int p) {
+    int s = ((p + 50) * 4162) >> 20;            // run index: 0 = bids, 1..12 = categories
+    int e = 202 + 252 * s;                      // end of run s
+    int k = e - p;                              // bytes of run s inside this vector (>= 1)
+    int st = s ? e - 252 : 0;
+    uint32_t fa = (cur >> (16 + s)) & 1u;
+    uint32_t ha = (cur >> s) & 1u;
+    uint32_t src2 = s < 12 ? (cur >> (s + 1)) : nxt;
+    uint32_t fb = (src2 >> 16) & 1u;
+    uint32_t hb = src2 & 1u;
+    uint32_t A = fa * 0x01010101u, B = fb * 0x01010101u;
+    uint32_t w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        uint32_t m = ya_low_bytes_mask(k - 4 * j);
+        w[j] = (A & m) | (B & ~m);
+    }
+    if (p == st) w[0] = (w[0] & ~0xFFu) | ha;
+    if (k < 16) {
+        uint32_t sh = (k & 3) * 8;
+        uint32_t clr = ~(0xFFu << sh), setv = hb << sh;
+        int j = k >> 2;
+        if (j == 0) w[0] = (w[0] & clr) | setv;
+        else if (j == 1) w[1] = (w[1] & clr) | setv;
+        else if (j == 2) w[2] = (w[2] & clr) | setv;
+        else w[3] = (w[3] & clr) | setv;
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// Writes rows of `ng` consecutive games starting at a 16-byte aligned address.
+// hf[i] (shared memory) is the H/F word of local game i.
+__device__ __forceinline__ void ya_write_mask_chunk(uint8_t* __restrict__ out, int ng, const uint32_t* hf,
+                                                    int tid, int nthr) {
+    const int total = ng * YA_N_ACTION;
+    const int nvec = total >> 4;
+    const int step = nthr * 16;
+    const int dg = step / YA_N_ACTION, dp = step - dg * YA_N_ACTION;
+    int b = tid * 16;
+    int g = b / YA_N_ACTION, p = b - g * YA_N_ACTION;
+    uint4* vout = reinterpret_cast<uint4*>(out);
+    for (int v = tid; v < nvec; v += nthr) {
+        uint32_t cur = hf[g];
+        uint32_t nxt = (g + 1 < ng) ? hf[g + 1] : 0u;
+        __stcs(vout + v, ya_mask_vector(cur, nxt, p));
+        p += dp; g += dg;
+        if (p >= YA_N_ACTION) { p -= YA_N_ACTION; ++g; }
+    }
+    // ragged tail (only when ng is not a multiple of 8): plain byte stores
+    for (int i = (nvec << 4) + tid; i < total; i += nthr) {
+        int gg = i / YA_N_ACTION, pp = i - gg * YA_N_ACTION;
+        int s = ((pp + 50) * 4162) >> 20;
+        int st = s ? 202 + 252 * (s - 1) : 0;
+        uint32_t c = hf[gg];
+        out[i] = (uint8_t)((pp == st ? (c >> s) : (c >> (16 + s))) & 1u);
+    }
+}
+
+constexpr int kMaskGames = 64;      // games per CTA in the mask kernels (multiple of 8)
+
+__global__ void __launch_bounds__(kThreads)
+ya_k_valid_moves(const uint4* __restrict__ states, int64_t stride, const int8_t* __restrict__ players,
+                 uint8_t* __restrict__ masks, int64_t n) {
+    __shared__ uint32_t hf[kMaskGames];
+    int64_t g0 = (int64_t)blockIdx.x * kMaskGames;
+    int ng = (int)min((int64_t)kMaskGames, n - g0);
+    if (threadIdx.x < ng) {
+        YaState s = ya_load(states, stride, g0 + threadIdx.x);
+        hf[threadIdx.x] = ya_hf_from_desc(ya_mask_desc(s, players[g0 + threadIdx.x]));
+    }
+    __syncthreads();
+    ya_write_mask_chunk(masks + g0 * YA_N_ACTION, ng, hf, threadIdx.x, blockDim.x);
+}
+
+// ------------------------------------------------------------------ small per-game kernels
+__global__ void ya_k_game_ended(const uint4* __restrict__ states, int64_t stride, const int8_t* __restrict__ players,
+                                float* __restrict__ out, int64_t n) {
+    int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n) return;
+    out[g] = ya_game_ended(ya_load(states, stride, g), players[g]);
+}
+
+__global__ void ya_k_canonical(const uint4* __restrict__ in, int64_t in_stride, const int8_t* __restrict__ players,
+                               uint4* __restrict__ out, int64_t out_stride, int64_t n) {
+    int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n) return;
+    YaState s = ya_load(in, in_stride, g);
+    ya_store(out, out_stride, g, players[g] == 1 ? s : ya_flip(s));
+}
+
+__global__ void ya_k_features(const uint4* __restrict__ states, int64_t stride, float* __restrict__ feat, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * YA_N_FEATURE) return;
+    int64_t g = i / YA_N_FEATURE;
+    int f = (int)(i - g * YA_N_FEATURE);
+    feat[i] = ya_feature(ya_load(states, stride, g), f);
+}
+
+__global__ void ya_k_random_action(const uint4* __restrict__ states, int64_t stride, const int8_t* __restrict__ players,
+                                   int32_t* __restrict__ actions, int64_t n, uint64_t seed, uint64_t game_base,
+                                   const uint32_t* __restrict__ episode, const int32_t* __restrict__ ply) {
+    int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n) return;
+    YaState s = ya_load(states, stride, g);
+    uint32_t desc = ya_mask_desc(s, players[g]);
+    int count = ya_legal_count(desc);
+    int a = 0;                                             // YachtPlayers.py:183: 0 when nothing is legal
+    if (count) {
+        YaDraw d = ya_draw(seed, (uint32_t)(game_base + g), episode ? episode[g] : 0u, ply ? (uint32_t)ply[g] : 0u,
+                           YA_TAG_ACTION, 0, 0);
+        a = ya_nth_legal(desc, (int)__umulhi(d.pick, (uint32_t)count));
+    }
+    actions[g] = a;
+}
+
+// ------------------------------------------------------------------ scoring-move enumeration
+// out[g][cat][subset] = score_category(cat, dice at subset) / 1000 for the player to move, 0
+// where the subset does not fit (YachtPlayers.py:134-169 enumerates exactly this 12 x 252 table).
+// One warp per game: lanes stride over the 252 subsets, the 3024-byte tile is staged in shared
+// memory and leaves as 189 coalesced 16-byte stores.
+constexpr int kEnumWarps = 8;
+
+__global__ void __launch_bounds__(kEnumWarps * 32)
+ya_k_enumerate_scores(const uint4* __restrict__ states, int64_t stride, const int8_t* __restrict__ players,
+                      uint8_t* __restrict__ out, int64_t n) {
+    __shared__ __align__(16) uint8_t tile[kEnumWarps][YA_N_CAT * YA_N_SUBSET];
+    __shared__ uint16_t smask[YA_N_SUBSET];
+    for (int i = threadIdx.x; i < YA_N_SUBSET; i += blockDim.x) smask[i] = ya_subset_mask[i];
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t nwarps = (int64_t)gridDim.x * kEnumWarps;
+    for (int64_t g = (int64_t)blockIdx.x * kEnumWarps + warp; g < n; g += nwarps) {
+        YaState s = ya_load(states, stride, g);
+        uint32_t carry = s.w[2 + (players[g] == 1 ? 0 : 1)];
+        int nd = ya_dice_count(carry);
+        uint8_t* t = tile[warp];
+        for (int sub = lane; sub < YA_N_SUBSET; sub += 32) {
+            uint32_t m = smask[sub];
+            bool fits = (31 - __clz(m)) < nd;
+            uint32_t hist = 0, pips = 0;
+            if (fits) ya_gather(carry, m, hist, pips);
+#pragma unroll
+            for (int cat = 0; cat < YA_N_CAT; ++cat)
+                t[cat * YA_N_SUBSET + sub] = fits ? (uint8_t)ya_category_points_k(cat, hist, pips) : (uint8_t)0;
+        }
+        __syncwarp();
+        const uint4* src = reinterpret_cast<const uint4*>(t);
+        uint4* dst = reinterpret_cast<uint4*>(out + g * (YA_N_CAT * YA_N_SUBSET));
+        for (int i = lane; i < (YA_N_CAT * YA_N_SUBSET) / 16; i += 32) __stcs(dst + i, src[i]);
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------ fused ply
+// One launch = one ply of every game under the uniform random-legal policy
+// (YachtPlayers.py:174-183 + Arena.py:49-71): legal mask materialised (optional), action
+// sampled with Philox, transition applied, outcome reported, finished games re-dealt.
+template <int GAMES>
+__global__ void __launch_bounds__(kThreads)
+ya_k_play_ply(uint4* __restrict__ states, int64_t stride, int8_t* __restrict__ players, int32_t* __restrict__ ply,
+              uint32_t* __restrict__ episode, int32_t* __restrict__ actions, float* __restrict__ outcome,
+              uint8_t* __restrict__ masks, int32_t* __restrict__ err_flag,
+              int64_t n, uint64_t seed, uint64_t game_base, int auto_reset) {
+    __shared__ uint32_t hf[GAMES];
+    const int64_t g0 = (int64_t)blockIdx.x * GAMES;
+    const int ng = (int)min((int64_t)GAMES, n - g0);
+    for (int t = threadIdx.x; t < ng; t += blockDim.x) {
+        const int64_t g = g0 + t;
+        YaState s = ya_load(states, stride, g);
+        int pl = players[g];
+        uint32_t p = (uint32_t)ply[g], ep = episode[g];
+        uint32_t gid = (uint32_t)(game_base + g);
+        uint32_t desc = ya_mask_desc(s, pl);
+        hf[t] = ya_hf_from_desc(desc);
+        int count = ya_legal_count(desc);
+        int a = 0;
+        if (count) {
+            YaDraw da = ya_draw(seed, gid, ep, p, YA_TAG_ACTION, 0, 0);
+            a = ya_nth_legal(desc, (int)__umulhi(da.pick, (uint32_t)count));
+        }
+        YaDraw d;
+        d.roll_a = d.roll_b = d.tie = d.pick = 0;
+        if (ya_draw_needs(s, pl, a)) d = ya_draw(seed, gid, ep, p, YA_TAG_REAL, 0, 0);
+        int st;
+        int np = ya_transition(s, pl, a, d, &st);
+        if (st != YA_OK && err_flag) atomicOr(err_flag, 1 << st);
+        float res = ya_game_ended(s, 1);
+        p += 1;
+        if (res != 0.0f && auto_reset) {
+            ep += 1;
+            p = 0;
+            np = 1;
+            s = ya_fresh_state(seed, gid, ep);
+        }
+        ya_store(states, stride, g, s);
+        players[g] = (int8_t)np;
+        ply[g] = (int32_t)p;
+        episode[g] = ep;
+        actions[g] = a;
+        outcome[g] = res;
+    }
+    if (masks) {
+        __syncthreads();
+        ya_write_mask_chunk(masks + g0 * YA_N_ACTION, ng, hf, threadIdx.x, blockDim.x);
+    }
+}
+
+inline int blocks_for(int64_t n, int per) { return (int)((n + per - 1) / per); }
+
+}  // namespace
+
+// =================================================================== C ABI
+extern "C" {
+
+int ya_abi_version(void) { return YA_ABI_VERSION; }
+
+int ya_set_device(int device) { return (int)cudaSetDevice(device); }
+
+int ya_init_states(uint32_t* states, int64_t stride, int8_t* players, int32_t* ply, const uint32_t* episode,
+                   int64_t n, uint64_t seed, uint64_t game_base, void* stream) {
+    if (n <= 0) return 0;
+    ya_k_init<<<blocks_for(n, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<uint4*>(states), stride, players, ply, episode, n, seed, game_base);
+    return (int)cudaGetLastError();
+}
+
+int ya_next_state(const uint32_t* states_in, int64_t in_stride, const int8_t* players, const int32_t* actions,
+                  uint32_t* states_out, int64_t out_stride, int8_t* next_players, int32_t* status, int64_t n,
+                  int draw_mode, const uint8_t* injected, uint64_t seed, uint64_t game_base,
+                  const uint32_t* episode, const int32_t* ply, uint32_t tag, const uint32_t* depth_sim, void* stream) {
+    if (n <= 0) return 0;
+    ya_k_next_state<<<blocks_for(n, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const uint4*>(states_in), in_stride, players, actions,
+        reinterpret_cast<uint4*>(states_out), out_stride, next_players, status, n,
+        draw_mode, injected, seed, game_base, episode, ply, tag, depth_sim);
+    return (int)cudaGetLastError();
+}
+
+int ya_valid_moves(const uint32_t* states, int64_t stride, const int8_t* players, uint8_t* masks, int64_t n, void* stream) {
+    if (n <= 0) return 0;
+    if ((reinterpret_cast<uintptr_t>(masks) & 15u) != 0) return (int)cudaErrorMisalignedAddress;
+    ya_k_valid_moves<<<blocks_for(n, kMaskGames), kThreads, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const uint4*>(states), stride, players, masks, n);
+    return (int)cudaGetLastError();
+}
+
+int ya_game_ended(const uint32_t* states, int64_t stride, const int8_t* players, float* out, int64_t n, void* stream) {
+    if (n <= 0) return 0;
+    ya_k_game_ended<<<blocks_for(n, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const uint4*>(states), stride, players, out, n);
+    return (int)cudaGetLastError();
+}
+
+int ya_canonical_form(const uint32_t* states_in, int64_t in_stride, const int8_t* players,
+                      uint32_t* states_out, int64_t out_stride, int64_t n, void* stream) {
+    if (n <= 0) return 0;
+    ya_k_canonical<<<blocks_for(n, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const uint4*>(states_in), in_stride, players, reinterpret_cast<uint4*>(states_out), out_stride, n);
+    return (int)cudaGetLastError();
+}
+
+int ya_features(const uint32_t* states, int64_t stride, float* features, int64_t n, void* stream) {
+    if (n <= 0) return 0;
+    ya_k_features<<<blocks_for(n * YA_N_FEATURE, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const uint4*>(states), stride, features, n);
+    return (int)cudaGetLastError();
+}
+
+int ya_random_action(const uint32_t* states, int64_t stride, const int8_t* players, int32_t* actions, int64_t n,
+                     uint64_t seed, uint64_t game_base, const uint32_t* episode, const int32_t* ply, void* stream) {
+    if (n <= 0) return 0;
+    ya_k_random_action<<<blocks_for(n, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const uint4*>(states), stride, players, actions, n, seed, game_base, episode, ply);
+    return (int)cudaGetLastError();
+}
+
+int ya_enumerate_scores(const uint32_t* states, int64_t stride, const int8_t* players, uint8_t* scores, int64_t n,
+                        void* stream) {
+    if (n <= 0) return 0;
+    if ((reinterpret_cast<uintptr_t>(scores) & 15u) != 0) return (int)cudaErrorMisalignedAddress;
+    int blocks = (int)min((int64_t)148 * 8, (n + kEnumWarps - 1) / kEnumWarps);
+    ya_k_enumerate_scores<<<blocks, kEnumWarps * 32, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const uint4*>(states), stride, players, scores, n);
+    return (int)cudaGetLastError();
+}
+
+int ya_play_ply(uint32_t* states, int64_t stride, int8_t* players, int32_t* ply, uint32_t* episode,
+                int32_t* actions, float* outcome, uint8_t* masks, int32_t* err_flag,
+                int64_t n, uint64_t seed, uint64_t game_base, int auto_reset, void* stream) {
+    if (n <= 0) return 0;
+    if (masks && (reinterpret_cast<uintptr_t>(masks) & 15u) != 0) return (int)cudaErrorMisalignedAddress;
+    constexpr int G = 64;
+    ya_k_play_ply<G><<<blocks_for(n, G), kThreads, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<uint4*>(states), stride, players, ply, episode, actions, outcome, masks, err_flag,
+        n, seed, game_base, auto_reset);
+    return (int)cudaGetLastError();
+}
+
+}  // extern "C"
