@@ -168,7 +168,7 @@ __device__ __forceinline__ uint32_t ya_category_points_k(int cat, uint32_t hist,
     if (cat == 11) return e5 ? 50u : 0u;
     // presence bits, face f -> bit f-1
     uint32_t nz = (hist | (hist >> 1) | (hist >> 2) | (hist >> 3)) & 0x111111u;
-    uint32_t seen = (nz | (nz >> 3) | (nz >> 6) | (nz >> 9) | (nz >> 12) | (nz >> 15)) & 0x3Fu;
+    uint32_t seen = (nz & 1u) | ((nz >> 3) & 2u) | ((nz >> 6) & 4u) | ((nz >> 9) & 8u) | ((nz >> 12) & 16u) | ((nz >> 15) & 32u);
     if (cat == 9) {
         bool ok = ((seen & 0x0Fu) == 0x0Fu) || ((seen & 0x1Eu) == 0x1Eu) || ((seen & 0x3Cu) == 0x3Cu);
         return ok ? 15u : 0u;
