@@ -88,6 +88,18 @@ int ya_play_ply(uint32_t* states, int64_t stride, int8_t* players, int32_t* ply,
                 int32_t* actions, float* outcome, uint8_t* masks, int32_t* err_flag,
                 int64_t n, uint64_t seed, uint64_t game_base, int auto_reset, void* stream);
 
+/* ---- host-buffer variants (end-to-end path for callers that keep boards in host memory) ----
+ * ya_host_create allocates the device mirror for n games once (no allocation per call);
+ * ya_host_play_ply copies the packed states and side arrays host->device, runs ya_play_ply,
+ * copies states / players / ply / episode / actions / outcome (and masks if requested and the
+ * context was created with_masks) back and synchronises.  All pointers are HOST pointers; the
+ * state buffer uses stride = n. */
+int ya_host_create(int64_t n, int with_masks, void** handle);
+int ya_host_destroy(void* handle);
+int ya_host_play_ply(void* handle, uint32_t* states, int8_t* players, int32_t* ply, uint32_t* episode,
+                     int32_t* actions, float* outcome, uint8_t* masks, int32_t* err_flag,
+                     uint64_t seed, uint64_t game_base, int auto_reset);
+
 #ifdef __cplusplus
 }
 #endif

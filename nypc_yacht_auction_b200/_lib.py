@@ -31,6 +31,9 @@ SIGNATURES = {
     "ya_random_action": [_vp, _i64, _vp, _vp, _i64, _u64, _u64, _vp, _vp, _vp],
     "ya_enumerate_scores": [_vp, _i64, _vp, _vp, _i64, _vp],
     "ya_play_ply": [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _u64, _u64, _int, _vp],
+    "ya_host_create": [_i64, _int, ctypes.POINTER(ctypes.c_void_p)],
+    "ya_host_destroy": [_vp],
+    "ya_host_play_ply": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _u64, _u64, _int],
 }
 
 _lib = None

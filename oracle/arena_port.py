@@ -1,0 +1,67 @@
+"""TEST INFRASTRUCTURE ONLY (see oracle/__init__.py) -- CPU baseline driver.
+
+Restates the reference's config-1 workload, ``Arena.playGame`` with ``RandomYachtPlayer`` on both
+sides (Arena.py:30-93, yacht/YachtPlayers.py:174-183), on top of oracle/yacht_rules.py, keeping
+the reference's call structure (two legal-mask evaluations per ply: one by the player, one by
+the arena's legality assert) so its cost profile is that of the reference's Python path.  Dice and
+picks come from the Philox protocol, so a game is the same game the GPU plays.
+"""
+from __future__ import annotations
+
+import multiprocessing as mp
+import os
+import time
+
+import numpy as np
+
+from . import philox
+from . import yacht_rules as yr
+
+
+def play_game(seed, game_id, episode=0):
+    """One full game; returns (plies, outcome for player 1)."""
+    board = yr.new_game(philox.Draw(seed, game_id, episode, 0, philox.TAG_INIT))
+    cur, ply = 1, 0
+    while yr.outcome(board, cur) == 0:                               # Arena.py:49
+        canon = yr.canonical(board, cur)                             # Arena.py:55-56
+        legal = np.nonzero(yr.legal_mask(canon, 1))[0]               # YachtPlayers.py:181-182
+        pick = philox.Draw(seed, game_id, episode, ply, philox.TAG_ACTION).pick(len(legal)) if len(legal) else 0
+        action = int(legal[pick]) if len(legal) else 0
+        valids = yr.legal_mask(yr.canonical(board, cur), 1)          # Arena.py:58-64
+        assert valids[action] > 0
+        board, cur = yr.next_state(board, cur, action, philox.Draw(seed, game_id, episode, ply, philox.TAG_REAL))
+        ply += 1
+    return ply, yr.outcome(board, 1)
+
+
+def _worker(args):
+    seed, first, count, budget_s = args
+    t0 = time.perf_counter()
+    steps = games = 0
+    for g in range(first, first + count):
+        p, _ = play_game(seed, g)
+        steps += p
+        games += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
+    return steps, games, time.perf_counter() - t0
+
+
+def timed_sample(seed=0, budget_s=10.0, procs=None, games_per_proc=100000):
+    """Plays games on `procs` processes (default: all host cores) for about budget_s seconds.
+    Returns dict(steps_per_s, games, steps, cores, seconds)."""
+    procs = procs or os.cpu_count() or 1
+    jobs = [(seed, i * games_per_proc, games_per_proc, budget_s) for i in range(procs)]
+    t0 = time.perf_counter()
+    if procs == 1:
+        res = [_worker(jobs[0])]
+    else:
+        ctx = mp.get_context("fork")
+        with ctx.Pool(procs) as pool:
+            res = pool.map(_worker, jobs)
+    wall = time.perf_counter() - t0
+    steps = sum(r[0] for r in res)
+    games = sum(r[1] for r in res)
+    # aggregate throughput: every worker ran for its own measured time
+    rate = sum(r[0] / r[2] for r in res)
+    return {"steps_per_s": rate, "games": games, "steps": steps, "cores": procs, "seconds": wall}
