@@ -85,77 +85,95 @@ __global__ void ya_k_next_state(const uint4* __restrict__ in, int64_t in_stride,
 
 // ------------------------------------------------------------------ legal-mask writer
 // A game's mask row (uint8[3226], the reference's dtype: YachtGame.py:375) is 13 runs: 202
-// bid bytes then 12 x 252 category bytes.  Per game we keep H (13 head bits) and F (13 fill
-// bits): run r is F[r] everywhere except its first byte, which is H[r].  Ten-dice and bid
-// rows have F == H; five-dice rows have F = 0 for the category runs (only subset 0 fits).
-// Rows are 3226 B apart (only 2-byte aligned), so the buffer is written as one flat byte
-// stream with 16-byte vector stores; a vector spans at most two runs.
-__device__ __forceinline__ uint32_t ya_hf_from_desc(uint32_t desc) {
+// bid bytes then 12 x 252 category bytes.  Per game we keep F (13 fill bits): run r is F[r]
+// everywhere.  Bid rows and ten-dice rows are exactly that; five-dice rows (round 13 only) have
+// F = 0 for the category runs and get their <= 12 single "subset 0" bytes patched afterwards.
+//
+// Rows are 3226 B apart (only 2-byte aligned), so the buffer is written as one flat byte stream
+// with 16-byte vector stores.  8 rows = 25,808 B = 1613 vectors is the alignment period: which
+// run(s) a vector covers and where the run boundary falls inside it depends only on the vector's
+// index j in its 8-row superblock, never on game data.  That static part lives in a shared-memory
+// table (built once per CTA); the per-vector work is: 1 table load, 1 descriptor load, 1 LUT load,
+// a handful of logic ops and one 16-byte streaming store.
+constexpr int kSuperGames = 8;
+constexpr int kSuperVec = kSuperGames * YA_N_ACTION / 16;          // 1613
+
+struct YaMaskSmem {
+    uint4 tail_lut[16];              // [k-1]: 0xFF in bytes >= k (k = bytes of the first run in the vector)
+    uint32_t fext[72];               // per local game: F[0..12] | F_next_game[0] << 13
+    uint16_t tab[kSuperVec + 3];     // per vector of a superblock: local game | run << 3 | (k-1) << 7
+};
+
+__device__ __forceinline__ uint32_t ya_fill_bits(uint32_t desc) {
     uint32_t h = desc & 0x1FFFu;
-    uint32_t f = (desc >> 13) ? h : (h & 1u);
-    return h | (f << 16);
+    return (desc >> 13) ? h : (h & 1u);
 }
 
-__device__ __forceinline__ uint32_t ya_low_bytes_mask(int nbytes) {   // nbytes may be <0 or >4
-    int sh = min(max(nbytes, 0), 4) * 8;
-    return __funnelshift_lc(0xFFFFFFFFu, 0u, sh);
-}
-
-__device__ __forceinline__ uint4 ya_mask_vector(uint32_t cur, uint32_t nxt, int p) {
-    int s = ((p + 50) * 4162) >> 20;            // run index: 0 = bids, 1..12 = categories
-    int e = 202 + 252 * s;                      // end of run s
-    int k = e - p;                              // bytes of run s inside this vector (>= 1)
-    int st = s ? e - 252 : 0;
-    uint32_t fa = (cur >> (16 + s)) & 1u;
-    uint32_t ha = (cur >> s) & 1u;
-    uint32_t src2 = s < 12 ? (cur >> (s + 1)) : nxt;
-    uint32_t fb = (src2 >> 16) & 1u;
-    uint32_t hb = src2 & 1u;
-    uint32_t A = fa * 0x01010101u, B = fb * 0x01010101u;
-    uint32_t w[4];
+__device__ __forceinline__ void ya_mask_smem_init(YaMaskSmem& sm, int tid, int nthr) {
+    for (int j = tid; j < kSuperVec; j += nthr) {
+        int b = j * 16;
+        int lg = b / YA_N_ACTION, p = b - lg * YA_N_ACTION;
+        int s = ((p + 50) * 4162) >> 20;            // run index: 0 = bids, 1..12 = categories
+        int k = min(202 + 252 * s - p, 16);         // bytes of run s inside this vector
+        sm.tab[j] = (uint16_t)(lg | (s << 3) | ((k - 1) << 7));
+    }
+    if (tid < 16) {
+        uint32_t w[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        uint32_t m = ya_low_bytes_mask(k - 4 * j);
-        w[j] = (A & m) | (B & ~m);
+        for (int q = 0; q < 4; ++q) {
+            uint32_t m = 0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) if (4 * q + i >= tid + 1) m |= 0xFFu << (8 * i);
+            w[q] = m;
+        }
+        sm.tail_lut[tid] = make_uint4(w[0], w[1], w[2], w[3]);
     }
-    if (p == st) w[0] = (w[0] & ~0xFFu) | ha;
-    if (k < 16) {
-        uint32_t sh = (k & 3) * 8;
-        uint32_t clr = ~(0xFFu << sh), setv = hb << sh;
-        int j = k >> 2;
-        if (j == 0) w[0] = (w[0] & clr) | setv;
-        else if (j == 1) w[1] = (w[1] & clr) | setv;
-        else if (j == 2) w[2] = (w[2] & clr) | setv;
-        else w[3] = (w[3] & clr) | setv;
-    }
-    return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
-// Writes rows of `ng` consecutive games starting at a 16-byte aligned address.
-// hf[i] (shared memory) is the H/F word of local game i.
-__device__ __forceinline__ void ya_write_mask_chunk(uint8_t* __restrict__ out, int ng, const uint32_t* hf,
+// fill[] (shared, ng entries valid) -> fext[]; call between two __syncthreads().
+__device__ __forceinline__ void ya_mask_smem_link(YaMaskSmem& sm, const uint32_t* fill, int ng, int cap, int tid, int nthr) {
+    for (int t = tid; t < cap; t += nthr) {
+        uint32_t f = t < ng ? fill[t] : 0u;
+        uint32_t nx = (t + 1 < ng) ? fill[t + 1] : 0u;
+        sm.fext[t] = f | ((nx & 1u) << 13);
+    }
+}
+
+// Writes rows of `ng` consecutive games starting at a 16-byte aligned address (ng <= 64).
+__device__ __forceinline__ void ya_write_mask_chunk(uint8_t* __restrict__ out, int ng, const YaMaskSmem& sm,
                                                     int tid, int nthr) {
     const int total = ng * YA_N_ACTION;
     const int nvec = total >> 4;
-    const int step = nthr * 16;
-    const int dg = step / YA_N_ACTION, dp = step - dg * YA_N_ACTION;
-    int b = tid * 16;
-    int g = b / YA_N_ACTION, p = b - g * YA_N_ACTION;
     uint4* vout = reinterpret_cast<uint4*>(out);
+    int j = tid, sb8 = 0;                           // nthr <= kSuperVec
     for (int v = tid; v < nvec; v += nthr) {
-        uint32_t cur = hf[g];
-        uint32_t nxt = (g + 1 < ng) ? hf[g + 1] : 0u;
-        __stcs(vout + v, ya_mask_vector(cur, nxt, p));
-        p += dp; g += dg;
-        if (p >= YA_N_ACTION) { p -= YA_N_ACTION; ++g; }
+        uint32_t t = sm.tab[j];
+        uint32_t two = sm.fext[sb8 + (t & 7u)] >> ((t >> 3) & 15u);
+        uint32_t A = (two & 1u) * 0x01010101u;
+        uint32_t X = ((two ^ (two >> 1)) & 1u) * 0x01010101u;
+        uint4 nm = sm.tail_lut[t >> 7];
+        __stcs(vout + v, make_uint4(A ^ (X & nm.x), A ^ (X & nm.y), A ^ (X & nm.z), A ^ (X & nm.w)));
+        j += nthr;
+        if (j >= kSuperVec) { j -= kSuperVec; sb8 += kSuperGames; }
     }
     // ragged tail (only when ng is not a multiple of 8): plain byte stores
     for (int i = (nvec << 4) + tid; i < total; i += nthr) {
         int gg = i / YA_N_ACTION, pp = i - gg * YA_N_ACTION;
         int s = ((pp + 50) * 4162) >> 20;
-        int st = s ? 202 + 252 * (s - 1) : 0;
-        uint32_t c = hf[gg];
-        out[i] = (uint8_t)((pp == st ? (c >> s) : (c >> (16 + s))) & 1u);
+        out[i] = (uint8_t)((sm.fext[gg] >> s) & 1u);
+    }
+}
+
+// Five-dice rows: set the "subset 0" byte of every open category (call after a __syncthreads()
+// that follows ya_write_mask_chunk).  desc[] holds the ya_mask_desc words of the chunk.
+__device__ __forceinline__ void ya_patch_five_dice_rows(uint8_t* __restrict__ out, int ng, const uint32_t* desc,
+                                                        int tid, int nthr) {
+    for (int t = tid; t < ng; t += nthr) {
+        uint32_t d = desc[t];
+        if ((d >> 13) || !(d & 0x1FFEu)) continue;
+        uint8_t* row = out + (size_t)t * YA_N_ACTION + YA_N_BID;
+        for (uint32_t open = (d >> 1) & 0xFFFu; open; open &= open - 1)
+            row[(__ffs(open) - 1) * YA_N_SUBSET] = 1;
     }
 }
 
@@ -164,15 +182,25 @@ constexpr int kMaskGames = 64;      // games per CTA in the mask kernels (multip
 __global__ void __launch_bounds__(kThreads)
 ya_k_valid_moves(const uint4* __restrict__ states, int64_t stride, const int8_t* __restrict__ players,
                  uint8_t* __restrict__ masks, int64_t n) {
-    __shared__ uint32_t hf[kMaskGames];
+    __shared__ YaMaskSmem sm;
+    __shared__ uint32_t desc[kMaskGames];
+    __shared__ uint32_t fill[kMaskGames];
     int64_t g0 = (int64_t)blockIdx.x * kMaskGames;
     int ng = (int)min((int64_t)kMaskGames, n - g0);
+    ya_mask_smem_init(sm, threadIdx.x, blockDim.x);
     if (threadIdx.x < ng) {
         YaState s = ya_load(states, stride, g0 + threadIdx.x);
-        hf[threadIdx.x] = ya_hf_from_desc(ya_mask_desc(s, players[g0 + threadIdx.x]));
+        uint32_t d = ya_mask_desc(s, players[g0 + threadIdx.x]);
+        desc[threadIdx.x] = d;
+        fill[threadIdx.x] = ya_fill_bits(d);
     }
     __syncthreads();
-    ya_write_mask_chunk(masks + g0 * YA_N_ACTION, ng, hf, threadIdx.x, blockDim.x);
+    ya_mask_smem_link(sm, fill, ng, kMaskGames, threadIdx.x, blockDim.x);
+    __syncthreads();
+    uint8_t* out = masks + g0 * YA_N_ACTION;
+    ya_write_mask_chunk(out, ng, sm, threadIdx.x, blockDim.x);
+    __syncthreads();
+    ya_patch_five_dice_rows(out, ng, desc, threadIdx.x, blockDim.x);
 }
 
 // ------------------------------------------------------------------ small per-game kernels
@@ -259,14 +287,18 @@ ya_k_enumerate_scores(const uint4* __restrict__ states, int64_t stride, const in
 // (YachtPlayers.py:174-183 + Arena.py:49-71): legal mask materialised (optional), action
 // sampled with Philox, transition applied, outcome reported, finished games re-dealt.
 template <int GAMES>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 4)
 ya_k_play_ply(uint4* __restrict__ states, int64_t stride, int8_t* __restrict__ players, int32_t* __restrict__ ply,
               uint32_t* __restrict__ episode, int32_t* __restrict__ actions, float* __restrict__ outcome,
               uint8_t* __restrict__ masks, int32_t* __restrict__ err_flag,
               int64_t n, uint64_t seed, uint64_t game_base, int auto_reset) {
-    __shared__ uint32_t hf[GAMES];
+    static_assert(GAMES % kSuperGames == 0 && GAMES <= 64, "chunk must be whole superblocks");
+    __shared__ YaMaskSmem sm;
+    __shared__ uint32_t desc_s[GAMES];
+    __shared__ uint32_t fill_s[GAMES];
     const int64_t g0 = (int64_t)blockIdx.x * GAMES;
     const int ng = (int)min((int64_t)GAMES, n - g0);
+    if (masks) ya_mask_smem_init(sm, threadIdx.x, blockDim.x);
     for (int t = threadIdx.x; t < ng; t += blockDim.x) {
         const int64_t g = g0 + t;
         YaState s = ya_load(states, stride, g);
@@ -274,7 +306,8 @@ ya_k_play_ply(uint4* __restrict__ states, int64_t stride, int8_t* __restrict__ p
         uint32_t p = (uint32_t)ply[g], ep = episode[g];
         uint32_t gid = (uint32_t)(game_base + g);
         uint32_t desc = ya_mask_desc(s, pl);
-        hf[t] = ya_hf_from_desc(desc);
+        desc_s[t] = desc;
+        fill_s[t] = ya_fill_bits(desc);
         int count = ya_legal_count(desc);
         int a = 0;
         if (count) {
@@ -304,7 +337,12 @@ ya_k_play_ply(uint4* __restrict__ states, int64_t stride, int8_t* __restrict__ p
     }
     if (masks) {
         __syncthreads();
-        ya_write_mask_chunk(masks + g0 * YA_N_ACTION, ng, hf, threadIdx.x, blockDim.x);
+        ya_mask_smem_link(sm, fill_s, ng, GAMES, threadIdx.x, blockDim.x);
+        __syncthreads();
+        uint8_t* out = masks + g0 * YA_N_ACTION;
+        ya_write_mask_chunk(out, ng, sm, threadIdx.x, blockDim.x);
+        __syncthreads();
+        ya_patch_five_dice_rows(out, ng, desc_s, threadIdx.x, blockDim.x);
     }
 }
 
