@@ -88,6 +88,61 @@ int ya_play_ply(uint32_t* states, int64_t stride, int8_t* players, int32_t* ply,
                 int32_t* actions, float* outcome, uint8_t* masks, int32_t* err_flag,
                 int64_t n, uint64_t seed, uint64_t game_base, int auto_reset, void* stream);
 
+/* ---- MCTS (MCTS.py:16-164) over a flat per-game node pool ------------------------------------
+ * The caller (torch) allocates the pool once and passes it as a ya_mcts_tree:
+ *   nodes   uint32[n][max_nodes][16]   64-byte node records (key = packed canonical state)
+ *   ht      uint16[n][ht_size]         open-addressing table, ht_size = power of two >= 2*max_nodes
+ *   arena   uint32[n][arena_words]     legal-only float32 prior rows + visited-edge chunks (Nsa, Qsa)
+ *   meta    uint32[n][4]               node count, arena top, round of the last root
+ *   cursor  uint32[n][32]              path / leaf of the simulation in flight
+ * One simulation of every game = ya_mcts_select -> evaluator -> ya_mcts_expand.  The tree persists
+ * across moves (Coach.py:93 resets it per episode: call ya_mcts_reset) and is pruned at round
+ * boundaries, which is exact because the reference's search never leaves a round >= 2.          */
+typedef struct {
+    uint32_t* nodes;
+    uint16_t* ht;
+    uint32_t* arena;
+    uint32_t* meta;
+    uint32_t* cursor;
+    int64_t n;
+    int32_t max_nodes;
+    int32_t ht_size;
+    int64_t arena_words;
+} ya_mcts_tree;
+
+int ya_mcts_cursor_words(void);
+int ya_mcts_node_words(void);
+
+/* MCTS.__init__ (MCTS.py:16-26): empty tables for the games flagged in `which` (NULL = all). */
+int ya_mcts_reset(const ya_mcts_tree* tree, const uint8_t* which, void* stream);
+
+/* The descent of MCTS.search (MCTS.py:56-150) for simulation `sim` of every active game, from the
+ * canonical form of states[g].  Leaves that need the evaluator get need_eval[g] = 1, their
+ * state_to_vec row in features[g][59] and (optionally) their packed state in leaf_states; all other
+ * paths (terminal, dead end) are backed up inside this call.  err_flag bits: 0x100 node pool full,
+ * 0x200 arena full, 0x400 path deeper than 16, 0x800 | (1 << status) rule error. */
+int ya_mcts_select(const ya_mcts_tree* tree, const uint32_t* states, int64_t stride, const int8_t* players,
+                   const int32_t* ply, const uint32_t* episode, uint64_t seed, uint64_t game_base, uint32_t sim,
+                   float cpuct, const uint8_t* active, float* features, uint8_t* need_eval, uint32_t* leaf_states,
+                   int32_t* err_flag, void* stream);
+
+/* Leaf expansion + backup (MCTS.py:86-115,152-164): pi is float32[n][3226] over ALL actions and
+ * value float32[n], as NeuralNet.predict returns them (NeuralNet.py:27-37); with uniform != 0 every
+ * leaf gets pi = uniform_p, v = uniform_v without reading memory (BASELINE.json configs[2]). */
+int ya_mcts_expand(const ya_mcts_tree* tree, const float* pi, const float* value, int uniform, float uniform_p,
+                   float uniform_v, int32_t* err_flag, void* stream);
+
+/* counts[g][a] = Nsa[(root, a)] (MCTS.py:40-42), visits[g] = Ns[root] (-1 if the root is unknown);
+ * optional qvals (float64) / qkind (1 = numpy float32, 2 = Python float) expose Qsa for tests. */
+int ya_mcts_root_counts(const ya_mcts_tree* tree, const uint32_t* states, int64_t stride, const int8_t* players,
+                        int32_t* counts, int32_t* visits, double* qvals, uint8_t* qkind, void* stream);
+
+/* Move selection from visit counts (Coach.py:56-65, MCTS.py:44-54): temp = (ply+1 < temp_threshold);
+ * temp 1 samples proportionally to the counts, temp 0 picks uniformly among the arg-max actions;
+ * randomness = Philox word of tag ACTION. */
+int ya_mcts_pick_action(const int32_t* counts, const int32_t* ply, const uint32_t* episode, int64_t n, uint64_t seed,
+                        uint64_t game_base, int temp_threshold, int32_t* actions, void* stream);
+
 /* ---- host-buffer variants (end-to-end path for callers that keep boards in host memory) ----
  * ya_host_create allocates the device mirror for n games once (no allocation per call);
  * ya_host_play_ply copies the packed states and side arrays host->device, runs ya_play_ply,

@@ -31,10 +31,25 @@ SIGNATURES = {
     "ya_random_action": [_vp, _i64, _vp, _vp, _i64, _u64, _u64, _vp, _vp, _vp],
     "ya_enumerate_scores": [_vp, _i64, _vp, _vp, _i64, _vp],
     "ya_play_ply": [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _u64, _u64, _int, _vp],
+    "ya_mcts_cursor_words": [],
+    "ya_mcts_node_words": [],
+    "ya_mcts_reset": [_vp, _vp, _vp],
+    "ya_mcts_select": [_vp, _vp, _i64, _vp, _vp, _vp, _u64, _u64, _u32, ctypes.c_float, _vp, _vp, _vp, _vp, _vp, _vp],
+    "ya_mcts_expand": [_vp, _vp, _vp, _int, ctypes.c_float, ctypes.c_float, _vp, _vp],
+    "ya_mcts_root_counts": [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp],
+    "ya_mcts_pick_action": [_vp, _vp, _vp, _i64, _u64, _u64, _int, _vp, _vp],
     "ya_host_create": [_i64, _int, ctypes.POINTER(ctypes.c_void_p)],
     "ya_host_destroy": [_vp],
     "ya_host_play_ply": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _u64, _u64, _int],
 }
+
+
+
+class MctsTreeStruct(ctypes.Structure):
+    """ya_mcts_tree of include/yacht_b200.h."""
+    _fields_ = [("nodes", _vp), ("ht", _vp), ("arena", _vp), ("meta", _vp), ("cursor", _vp),
+                ("n", _i64), ("max_nodes", ctypes.c_int32), ("ht_size", ctypes.c_int32), ("arena_words", _i64)]
+
 
 _lib = None
 

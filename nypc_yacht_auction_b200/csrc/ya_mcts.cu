@@ -1,0 +1,577 @@
+// Yacht-Auction B200 engine -- batched MCTS (select / expand / backup) over a flat per-game node
+// pool in HBM.  One warp per game; thousands of games advance one simulation per launch pair:
+//
+//   ya_mcts_select   walks root -> leaf with the reference's UCB rule, applies the (stochastic)
+//                    transitions, allocates the leaf node, writes its feature row for the batched
+//                    evaluator; paths that end in a terminal / dead-end node are backed up at once
+//   [evaluator]      ONE batched forward for all leaves (PyTorch), or the uniform prior
+//   ya_mcts_expand   masks + renormalises the policy into the leaf's legal-only prior row (numpy's
+//                    pairwise float32 summation order), then backs the value up the recorded path
+//
+// Behavioural source of truth: /root/reference/MCTS.py (cited per function) with the quirks listed
+// in SURVEY.md section 8a (Q1-Q9): state-keyed nodes (transpositions merge, tree persists across moves),
+// in-search dice, lowest-index tie-break, three leaf fallbacks, un-negated 0 from dead-end revisits,
+// and step-wise float32 / Python-double arithmetic decided per value exactly as numpy (NEP 50) does.
+#include "ya_common.cuh"
+#include "../../include/yacht_b200.h"
+#include <math_constants.h>
+
+namespace {
+
+constexpr int kNodeWords = 16;        // 64-byte node record
+constexpr int kCursorWords = 32;      // 128-byte per-game search cursor
+constexpr int kMaxDepth = 16;
+constexpr int kChunkEdges = 32;
+constexpr int kChunkWords = 114;      // [0] next, [1] pad, [2..17] idx u16 x32, [18..49] nsa u32 x32, [50..113] q f64 x32
+constexpr int kWarpsPerBlock = 4;
+
+// node words
+enum { N_KEY = 0, N_DESC = 8, N_VISITS = 9, N_PRIOR = 10, N_EDGES = 11, N_NEDGE = 12 };
+// cursor words
+enum { C_LEAF = 0, C_DEPTH = 8, C_KIND = 9, C_NODE = 10, C_PATH = 12 };
+enum { KIND_DONE = 0, KIND_NEED_EVAL = 1, KIND_ERROR = 2 };
+// meta words
+enum { M_NODES = 0, M_TOP = 1, M_ROUND = 2 };
+// error bits (OR-ed into err_flag)
+enum { E_NODES_FULL = 1 << 8, E_ARENA_FULL = 1 << 9, E_DEPTH = 1 << 10, E_RULE = 1 << 11 };
+
+struct View {
+    uint32_t* nodes;
+    uint16_t* ht;
+    uint32_t* arena;
+    uint32_t* meta;
+    uint32_t* cur;
+    int max_nodes, ht_size;
+    uint32_t arena_words;
+};
+
+__device__ __forceinline__ View make_view(const ya_mcts_tree& t, int64_t g) {
+    View v;
+    v.nodes = t.nodes + g * (int64_t)t.max_nodes * kNodeWords;
+    v.ht = t.ht + g * (int64_t)t.ht_size;
+    v.arena = t.arena + g * t.arena_words;
+    v.meta = t.meta + g * 4;
+    v.cur = t.cursor + g * kCursorWords;
+    v.max_nodes = t.max_nodes;
+    v.ht_size = t.ht_size;
+    v.arena_words = (uint32_t)t.arena_words;
+    return v;
+}
+
+// A value travelling up the tree with the numeric type Python would give it.
+struct Val {
+    double d;        // value (exact float32 value when is_f32)
+    bool is_f32;
+};
+
+__device__ __forceinline__ uint32_t state_hash(const YaState& s) {
+    uint32_t h = 0x811C9DC5u;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) h = (h ^ s.w[i]) * 0x01000193u;
+    h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12;
+    return h;
+}
+
+// open-addressing lookup (all lanes run it redundantly: uniform addresses broadcast)
+__device__ __forceinline__ int ht_find(const View& v, const YaState& s, int* free_slot) {
+    int mask = v.ht_size - 1;
+    int slot = (int)(state_hash(s) & (uint32_t)mask);
+    for (;;) {
+        uint32_t e = v.ht[slot];
+        if (e == 0) { *free_slot = slot; return -1; }
+        const uint4* k = reinterpret_cast<const uint4*>(v.nodes + (int64_t)(e - 1) * kNodeWords);
+        uint4 a = k[0], b = k[1];
+        if (a.x == s.w[0] && a.y == s.w[1] && a.z == s.w[2] && a.w == s.w[3] &&
+            b.x == s.w[4] && b.y == s.w[5] && b.z == s.w[6] && b.w == s.w[7]) return (int)(e - 1);
+        slot = (slot + 1) & mask;
+    }
+}
+
+__device__ __forceinline__ double es_as_double(float es) {       // getGameEnded returns Python floats
+    if (es == 1.0f) return 1.0;
+    if (es == -1.0f) return -1.0;
+    return 1e-4;
+}
+
+// ---------------------------------------------------------------- UCB argmax (MCTS.py:117-133)
+__device__ __forceinline__ int ucb_select(const View& v, const uint32_t* node, int L, float cpuct, int lane) {
+    const uint32_t visits = node[N_VISITS];
+    const uint32_t* row = v.arena + node[N_PRIOR];
+    const float sq_new = (float)sqrt((double)visits + 1e-8);       // math.sqrt(Ns + EPS), rounded when it meets float32
+    const float sq_old = (float)sqrt((double)visits);
+    float best = -CUDART_INF_F;
+    int besti = 0x7FFFFFFF;
+    // visited edges: u = Q + cpuct * P * sqrt(Ns) / (1 + Nsa)
+    uint32_t off = node[N_EDGES];
+    int remaining = (int)node[N_NEDGE];
+    while (remaining > 0) {
+        int cnt = min(remaining, kChunkEdges);
+        const uint32_t* ch = v.arena + off;
+        if (lane < cnt) {
+            int ai = reinterpret_cast<const uint16_t*>(ch + 2)[lane];
+            uint32_t nsa = ch[18 + lane] & 0x7FFFFFFFu;
+            double q = reinterpret_cast<const double*>(ch + 50)[lane];
+            float p = __uint_as_float(row[ai] & 0x7FFFFFFFu);
+            float t = __fmul_rn(__fmul_rn(cpuct, p), sq_old);
+            t = __fdiv_rn(t, (float)(1u + nsa));
+            float u = __fadd_rn((float)q, t);
+            if (u > best || (u == best && ai < besti)) { best = u; besti = ai; }
+        }
+        off = ch[0];
+        remaining -= cnt;
+    }
+    // unvisited edges: u = cpuct * P * sqrt(Ns + EPS)
+    for (int i = lane; i < L; i += 32) {
+        uint32_t bits = row[i];
+        if (bits >> 31) continue;
+        float u = __fmul_rn(__fmul_rn(cpuct, __uint_as_float(bits)), sq_new);
+        if (u > best || (u == best && i < besti)) { best = u; besti = i; }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        float ou = __shfl_xor_sync(0xFFFFFFFFu, best, o);
+        int oi = __shfl_xor_sync(0xFFFFFFFFu, besti, o);
+        if (ou > best || (ou == best && oi < besti)) { best = ou; besti = oi; }
+    }
+    return besti;
+}
+
+// ---------------------------------------------------------------- backup (MCTS.py:152-164)
+// Returns false if the arena overflowed.
+__device__ __forceinline__ bool backup_edge(const View& v, uint32_t* node, int ai, const Val& val, uint32_t& arena_top, int lane) {
+    // locate the edge
+    uint32_t off = node[N_EDGES];
+    int n_edges = (int)node[N_NEDGE];
+    int remaining = n_edges;
+    uint32_t last = 0, found_off = 0;
+    int found_slot = -1;
+    while (remaining > 0) {
+        int cnt = min(remaining, kChunkEdges);
+        const uint32_t* ch = v.arena + off;
+        bool hit = lane < cnt && reinterpret_cast<const uint16_t*>(ch + 2)[lane] == ai;
+        uint32_t m = __ballot_sync(0xFFFFFFFFu, hit);
+        if (m) { found_off = off; found_slot = __ffs(m) - 1; break; }
+        last = off;
+        off = ch[0];
+        remaining -= cnt;
+    }
+    if (lane == 0) {
+        if (found_slot >= 0) {
+            uint32_t* ch = v.arena + found_off;
+            uint32_t raw = ch[18 + found_slot];
+            uint32_t nsa = raw & 0x7FFFFFFFu;
+            bool q_f32 = (raw >> 31) == 0;
+            double* qp = reinterpret_cast<double*>(ch + 50) + found_slot;
+            double q = *qp;
+            if (!q_f32 && !val.is_f32) {
+                // Python floats all the way: (Nsa * Q + v) / (Nsa + 1) in double
+                q = __ddiv_rn(__dadd_rn(__dmul_rn((double)nsa, q), val.d), (double)(nsa + 1u));
+            } else {
+                // numpy float32 arithmetic; a Python-float operand is rounded to float32 first
+                float prod = q_f32 ? __fmul_rn((float)nsa, (float)q) : (float)__dmul_rn((double)nsa, q);
+                float sum = __fadd_rn(prod, (float)val.d);
+                q = (double)__fdiv_rn(sum, (float)(nsa + 1u));
+                q_f32 = true;
+            }
+            *qp = q;
+            ch[18 + found_slot] = (nsa + 1u) | (q_f32 ? 0u : 0x80000000u);
+        } else {
+            int slot = n_edges % kChunkEdges;
+            uint32_t choff;
+            bool ok = true;
+            if (slot == 0) {                                         // need a new chunk
+                uint32_t top = (arena_top + 1u) & ~1u;
+                if (top + kChunkWords > v.arena_words) ok = false;
+                else {
+                    choff = top;
+                    arena_top = top + kChunkWords;
+                    v.arena[choff] = 0;
+                    if (n_edges == 0) node[N_EDGES] = choff; else v.arena[last] = choff;
+                }
+            } else {
+                choff = last;                                        // the tail chunk still has room
+            }
+            if (ok) {
+                uint32_t* ch = v.arena + choff;
+                reinterpret_cast<uint16_t*>(ch + 2)[slot] = (uint16_t)ai;
+                ch[18 + slot] = 1u | (val.is_f32 ? 0u : 0x80000000u);       // Qsa = v, Nsa = 1
+                reinterpret_cast<double*>(ch + 50)[slot] = val.d;
+                node[N_NEDGE] = (uint32_t)(n_edges + 1);
+                v.arena[node[N_PRIOR] + ai] |= 0x80000000u;                 // mark the prior entry as visited
+            } else {
+                arena_top = 0xFFFFFFFFu;
+            }
+        }
+        node[N_VISITS] += 1;                                         // Ns[s] += 1
+    }
+    arena_top = __shfl_sync(0xFFFFFFFFu, arena_top, 0);
+    __syncwarp();
+    return arena_top != 0xFFFFFFFFu;
+}
+
+__device__ __forceinline__ bool backup_path(const View& v, int depth, Val ret, uint32_t& arena_top, int lane) {
+    for (int d = depth - 1; d >= 0; --d) {
+        uint32_t pe = v.cur[C_PATH + d];
+        uint32_t* node = v.nodes + (int64_t)(pe & 0xFFFFu) * kNodeWords;
+        if (!backup_edge(v, node, (int)(pe >> 16), ret, arena_top, lane)) return false;
+        ret.d = -ret.d;                                              // return -v
+    }
+    return true;
+}
+
+// ---------------------------------------------------------------- select (MCTS.py:56-150)
+template <bool WRITE_LEAF_STATE>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+ya_k_mcts_select(ya_mcts_tree tree, const uint4* __restrict__ states, int64_t stride, const int8_t* __restrict__ players,
+                 const int32_t* __restrict__ ply, const uint32_t* __restrict__ episode, uint64_t seed, uint64_t game_base,
+                 uint32_t sim, float cpuct, const uint8_t* __restrict__ active, float* __restrict__ features,
+                 uint8_t* __restrict__ need_eval, uint32_t* __restrict__ leaf_states, int32_t* __restrict__ err_flag) {
+    const int lane = threadIdx.x & 31;
+    const int64_t g = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    if (g >= tree.n) return;
+    if (active && !active[g]) { if (lane == 0) need_eval[g] = 0; return; }
+    View v = make_view(tree, g);
+    YaState cur = ya_load(states, stride, g);
+    if (players[g] != 1) cur = ya_flip(cur);                         // getCanonicalForm of the root
+    const uint32_t gid = (uint32_t)(game_base + g);
+    const uint32_t ep = episode ? episode[g] : 0u, pl = ply ? (uint32_t)ply[g] : 0u;
+
+    uint32_t node_count = v.meta[M_NODES], arena_top = v.meta[M_TOP];
+    // Lazy pruning at round boundaries: inside rounds >= 2 the search never leaves the root's round
+    // (quirk Q3), so nothing stored for an earlier round >= 2 can be reached again.
+    if (sim == 0) {
+        uint32_t old_round = v.meta[M_ROUND], new_round = (uint32_t)ya_round(cur);
+        if (old_round != new_round) {
+            if (old_round >= 2 || new_round < old_round) {
+                for (int i = lane; i < v.ht_size / 2; i += 32) reinterpret_cast<uint32_t*>(v.ht)[i] = 0u;
+                node_count = 0;
+                arena_top = 2;
+            }
+            if (lane == 0) v.meta[M_ROUND] = new_round;
+            __syncwarp();
+        }
+    }
+
+    int depth = 0, kind = KIND_DONE, err = 0, leaf_node = -1;
+    Val ret;
+    ret.d = 0.0; ret.is_f32 = false;
+    for (;;) {
+        float es = ya_game_ended(cur, 1);                           // Es[s], MCTS.py:79-83
+        if (es != 0.0f) { ret.d = -es_as_double(es); ret.is_f32 = false; break; }
+        int free_slot;
+        int idx = ht_find(v, cur, &free_slot);
+        if (idx < 0) {                                               // leaf: MCTS.py:84-115 (evaluation happens outside)
+            uint32_t desc = ya_mask_desc(cur, 1);
+            int L = ya_legal_count(desc);
+            if ((int)node_count >= v.max_nodes) { err = E_NODES_FULL; kind = KIND_ERROR; break; }
+            if (arena_top + (uint32_t)L > v.arena_words) { err = E_ARENA_FULL; kind = KIND_ERROR; break; }
+            idx = (int)node_count;
+            if (lane == 0) {
+                uint32_t* nd = v.nodes + (int64_t)idx * kNodeWords;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) nd[N_KEY + i] = cur.w[i];
+                nd[N_DESC] = desc; nd[N_VISITS] = 0; nd[N_PRIOR] = arena_top; nd[N_EDGES] = 0; nd[N_NEDGE] = 0;
+                v.ht[free_slot] = (uint16_t)(idx + 1);
+            }
+            node_count += 1;
+            arena_top += (uint32_t)L;
+            for (int f = lane; f < YA_N_FEATURE; f += 32) features[g * YA_N_FEATURE + f] = ya_feature(cur, f);
+            leaf_node = idx;
+            kind = KIND_NEED_EVAL;
+            __syncwarp();
+            break;
+        }
+        uint32_t* node = v.nodes + (int64_t)idx * kNodeWords;
+        uint32_t desc = node[N_DESC];
+        int L = ya_legal_count(desc);
+        if (L == 0) { ret.d = 0.0; ret.is_f32 = false; break; }    // MCTS.py:138-147: `return 0`, not negated
+        if (depth >= kMaxDepth) { err = E_DEPTH; kind = KIND_ERROR; break; }
+        int ai = ucb_select(v, node, L, cpuct, lane);
+        int a = ya_nth_legal(desc, ai);
+        if (lane == 0) v.cur[C_PATH + depth] = (uint32_t)idx | ((uint32_t)ai << 16);
+        YaDraw d;
+        d.roll_a = d.roll_b = d.tie = d.pick = 0;
+        if (ya_draw_needs(cur, 1, a)) d = ya_draw(seed, gid, ep, pl, YA_TAG_SEARCH, (uint32_t)depth, sim);
+        int st;
+        int np = ya_transition(cur, 1, a, d, &st);                   // getNextState(canonicalBoard, 1, a), MCTS.py:149
+        if (st != YA_OK) { err = E_RULE | (1 << st); kind = KIND_ERROR; break; }
+        if (np != 1) cur = ya_flip(cur);                             // getCanonicalForm(next_s, next_player), MCTS.py:150
+        ++depth;
+    }
+    __syncwarp();
+    if (kind == KIND_DONE) {
+        if (!backup_path(v, depth, ret, arena_top, lane)) { err = E_ARENA_FULL; kind = KIND_ERROR; }
+    }
+    if (lane == 0) {
+        v.meta[M_NODES] = node_count;
+        v.meta[M_TOP] = arena_top;
+        v.cur[C_DEPTH] = (uint32_t)depth;
+        v.cur[C_KIND] = (uint32_t)kind;
+        v.cur[C_NODE] = (uint32_t)leaf_node;
+        need_eval[g] = kind == KIND_NEED_EVAL ? 1 : 0;
+        if (err && err_flag) atomicOr(err_flag, err);
+        if (WRITE_LEAF_STATE && leaf_states && kind == KIND_NEED_EVAL) {
+            uint4* o = reinterpret_cast<uint4*>(leaf_states);
+            o[g] = make_uint4(cur.w[0], cur.w[1], cur.w[2], cur.w[3]);
+            o[tree.n + g] = make_uint4(cur.w[4], cur.w[5], cur.w[6], cur.w[7]);
+        }
+    }
+}
+
+// ---------------------------------------------------------------- expand (MCTS.py:86-115) + backup
+// validity of action i for a mask descriptor
+__device__ __forceinline__ bool desc_valid(uint32_t desc, int i) {
+    int r = ((i + 50) * 4162) >> 20;
+    if (!((desc >> r) & 1u)) return false;
+    if (r == 0 || (desc >> 13)) return true;
+    return i == YA_N_BID + YA_N_SUBSET * (r - 1);
+}
+
+// sum of x[i] = valid(i) ? pi[i] : 0 over i < 3226 in numpy's float32 pairwise order
+// (numpy/_core/src/umath/loops_utils.h.src: blocks of <= 128 with 8 accumulators, halves rounded
+// down to a multiple of 8).  For n = 3226 that is a perfect binary tree over 32 blocks of 96 / 104 /
+// 106 elements: 8 lanes run a block's accumulators, four blocks per pass.
+template <bool UNIFORM>
+__device__ __forceinline__ float masked_pairwise_sum(const float* __restrict__ pi, float uniform_p, uint32_t desc, int lane) {
+    const int sub = lane & 7, grp = lane >> 3;
+    float my_leaf = 0.0f;
+#pragma unroll 1
+    for (int pass = 0; pass < 8; ++pass) {
+        int leaf = pass * 4 + grp;
+        int start = 0, n = YA_N_ACTION;
+#pragma unroll
+        for (int lvl = 4; lvl >= 0; --lvl) {
+            int n2 = n / 2;
+            n2 -= n2 % 8;
+            if ((leaf >> lvl) & 1) { start += n2; n -= n2; } else { n = n2; }
+        }
+        int body = n - (n % 8);
+        int i = start + sub;
+        float r = desc_valid(desc, i) ? (UNIFORM ? uniform_p : pi[i]) : 0.0f;
+        for (int t = 8; t < body; t += 8) {
+            int k = start + t + sub;
+            float x = desc_valid(desc, k) ? (UNIFORM ? uniform_p : pi[k]) : 0.0f;
+            r = __fadd_rn(r, x);
+        }
+        // ((r0+r1)+(r2+r3)) + ((r4+r5)+(r6+r7))
+        r = __fadd_rn(r, __shfl_xor_sync(0xFFFFFFFFu, r, 1));
+        r = __fadd_rn(r, __shfl_xor_sync(0xFFFFFFFFu, r, 2));
+        r = __fadd_rn(r, __shfl_xor_sync(0xFFFFFFFFu, r, 4));
+        for (int k = start + body; k < start + n; ++k) {              // the n % 8 leftovers, in order
+            float x = desc_valid(desc, k) ? (UNIFORM ? uniform_p : pi[k]) : 0.0f;
+            r = __fadd_rn(r, x);
+        }
+        float leaf_sum = __shfl_sync(0xFFFFFFFFu, r, (lane & 24));   // sub-lane 0 of my group
+        // lane `leaf` keeps block `leaf`
+        float from = __shfl_sync(0xFFFFFFFFu, leaf_sum, ((lane & 3) << 3));
+        if ((lane >> 2) == pass) my_leaf = from;
+    }
+    // perfect binary tree over the 32 block sums
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) my_leaf = __fadd_rn(my_leaf, __shfl_xor_sync(0xFFFFFFFFu, my_leaf, o));
+    return my_leaf;
+}
+
+template <bool UNIFORM>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+ya_k_mcts_expand(ya_mcts_tree tree, const float* __restrict__ pi_all, const float* __restrict__ value,
+                 float uniform_p, float uniform_v, int32_t* __restrict__ err_flag) {
+    const int lane = threadIdx.x & 31;
+    const int64_t g = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    if (g >= tree.n) return;
+    View v = make_view(tree, g);
+    if (v.cur[C_KIND] != KIND_NEED_EVAL) return;
+    uint32_t* node = v.nodes + (int64_t)v.cur[C_NODE] * kNodeWords;
+    const uint32_t desc = node[N_DESC];
+    const int L = ya_legal_count(desc);
+    const float* pi = UNIFORM ? nullptr : pi_all + g * YA_N_ACTION;
+    if (L > 0) {
+        float total = masked_pairwise_sum<UNIFORM>(pi, uniform_p, desc, lane);
+        float* row = reinterpret_cast<float*>(v.arena + node[N_PRIOR]);
+        if (total > 0.0f) {                                          // Ps /= sum, MCTS.py:90-91
+            for (int k = lane; k < L; k += 32) {
+                float p = UNIFORM ? uniform_p : pi[ya_nth_legal(desc, k)];
+                row[k] = __fdiv_rn(p, total);
+            }
+        } else {                                                     // all legal moves masked: uniform over legal, :97-101
+            float u = __fdiv_rn(1.0f, (float)L);
+            for (int k = lane; k < L; k += 32) row[k] = u;
+        }
+    }
+    __syncwarp();
+    Val ret;
+    ret.d = -(double)(UNIFORM ? uniform_v : value[g]);               // return -v (numpy float32)
+    ret.is_f32 = true;
+    uint32_t arena_top = v.meta[M_TOP];
+    bool ok = backup_path(v, (int)v.cur[C_DEPTH], ret, arena_top, lane);
+    if (lane == 0) {
+        v.meta[M_TOP] = arena_top;
+        v.cur[C_KIND] = KIND_DONE;
+        if (!ok && err_flag) atomicOr(err_flag, E_ARENA_FULL);
+    }
+}
+
+// ---------------------------------------------------------------- root statistics (MCTS.py:40-42)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+ya_k_mcts_root_counts(ya_mcts_tree tree, const uint4* __restrict__ states, int64_t stride, const int8_t* __restrict__ players,
+                      int32_t* __restrict__ counts, int32_t* __restrict__ visits, double* __restrict__ qvals,
+                      uint8_t* __restrict__ qkind) {
+    const int lane = threadIdx.x & 31;
+    const int64_t g = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    if (g >= tree.n) return;
+    View v = make_view(tree, g);
+    YaState cur = ya_load(states, stride, g);
+    if (players[g] != 1) cur = ya_flip(cur);
+    int32_t* row = counts + g * YA_N_ACTION;
+    for (int i = lane; i < YA_N_ACTION; i += 32) {
+        row[i] = 0;
+        if (qvals) qvals[g * YA_N_ACTION + i] = 0.0;
+        if (qkind) qkind[g * YA_N_ACTION + i] = 0;
+    }
+    __syncwarp();
+    int free_slot;
+    int idx = ht_find(v, cur, &free_slot);
+    if (idx < 0) { if (lane == 0 && visits) visits[g] = -1; return; }
+    const uint32_t* node = v.nodes + (int64_t)idx * kNodeWords;
+    if (lane == 0 && visits) visits[g] = (int32_t)node[N_VISITS];
+    uint32_t desc = node[N_DESC];
+    uint32_t off = node[N_EDGES];
+    int remaining = (int)node[N_NEDGE];
+    while (remaining > 0) {
+        int cnt = min(remaining, kChunkEdges);
+        const uint32_t* ch = v.arena + off;
+        if (lane < cnt) {
+            int a = ya_nth_legal(desc, reinterpret_cast<const uint16_t*>(ch + 2)[lane]);
+            uint32_t raw = ch[18 + lane];
+            row[a] = (int32_t)(raw & 0x7FFFFFFFu);
+            if (qvals) qvals[g * YA_N_ACTION + a] = reinterpret_cast<const double*>(ch + 50)[lane];
+            if (qkind) qkind[g * YA_N_ACTION + a] = (raw >> 31) ? 2 : 1;       // 1 = float32, 2 = Python float
+        }
+        off = ch[0];
+        remaining -= cnt;
+    }
+}
+
+// ---------------------------------------------------------------- action from visit counts
+// temp = 1 (Coach.py:56-65): inverse CDF over the integer counts, r = (word * total) >> 32.
+// temp = 0 (MCTS.py:44-49): uniformly among the arg-max actions, k = (word * ties) >> 32.
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+ya_k_mcts_pick(const int32_t* __restrict__ counts, const int32_t* __restrict__ ply, const uint32_t* __restrict__ episode,
+               int64_t n, uint64_t seed, uint64_t game_base, int temp_threshold, int32_t* __restrict__ actions) {
+    const int lane = threadIdx.x & 31;
+    const int64_t g = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    if (g >= n) return;
+    const int32_t* row = counts + g * YA_N_ACTION;
+    uint32_t p = ply ? (uint32_t)ply[g] : 0u;
+    YaDraw d = ya_draw(seed, (uint32_t)(game_base + g), episode ? episode[g] : 0u, p, YA_TAG_ACTION, 0, 0);
+    const bool greedy = !((int)(p + 1) < temp_threshold);
+    // each lane owns a contiguous slice of 101 actions
+    const int per = (YA_N_ACTION + 31) / 32;
+    const int lo = lane * per, hi = min(lo + per, YA_N_ACTION);
+    long long sum = 0;
+    int mx = 0;
+    for (int i = lo; i < hi; ++i) { int c = row[i]; sum += c; mx = max(mx, c); }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) mx = max(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, o));
+    long long weight = 0;                                            // what this lane contributes to the CDF
+    if (greedy) { for (int i = lo; i < hi; ++i) weight += row[i] == mx; } else weight = sum;
+    long long incl = weight;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        long long t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    long long total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+    long long r = (long long)(((unsigned long long)d.pick * (unsigned long long)total) >> 32);
+    long long before = incl - weight;
+    int found = -1;
+    if (total > 0 && r >= before && r < incl) {
+        long long acc = before;
+        for (int i = lo; i < hi; ++i) {
+            acc += greedy ? (row[i] == mx) : row[i];
+            if (acc > r) { found = i; break; }
+        }
+    }
+    uint32_t m = __ballot_sync(0xFFFFFFFFu, found >= 0);
+    int src = m ? __ffs(m) - 1 : 0;
+    int a = __shfl_sync(0xFFFFFFFFu, found, src);
+    if (lane == 0) actions[g] = m ? a : -1;
+}
+
+__global__ void ya_k_mcts_reset(ya_mcts_tree tree, const uint8_t* __restrict__ which) {
+    const int64_t g = blockIdx.x;
+    if (g >= tree.n || (which && !which[g])) return;
+    View v = make_view(tree, g);
+    for (int i = threadIdx.x; i < v.ht_size / 2; i += blockDim.x) reinterpret_cast<uint32_t*>(v.ht)[i] = 0u;
+    if (threadIdx.x == 0) {
+        v.meta[M_NODES] = 0; v.meta[M_TOP] = 2; v.meta[M_ROUND] = 0; v.meta[3] = 0;
+        v.cur[C_KIND] = KIND_DONE; v.cur[C_DEPTH] = 0;
+    }
+}
+
+inline int warp_blocks(int64_t n) { return (int)((n + kWarpsPerBlock - 1) / kWarpsPerBlock); }
+
+bool tree_ok(const ya_mcts_tree* t) {
+    return t && t->n > 0 && t->max_nodes > 0 && t->max_nodes < 65535 && t->ht_size >= 2 * t->max_nodes &&
+           (t->ht_size & (t->ht_size - 1)) == 0 && t->arena_words > 2 && (t->arena_words % 2) == 0 &&
+           t->arena_words < (1ll << 32);
+}
+
+}  // namespace
+
+extern "C" {
+
+int ya_mcts_cursor_words(void) { return kCursorWords; }
+int ya_mcts_node_words(void) { return kNodeWords; }
+
+int ya_mcts_reset(const ya_mcts_tree* tree, const uint8_t* which, void* stream) {
+    if (!tree_ok(tree)) return (int)cudaErrorInvalidValue;
+    ya_k_mcts_reset<<<(unsigned)tree->n, 128, 0, (cudaStream_t)stream>>>(*tree, which);
+    return (int)cudaGetLastError();
+}
+
+int ya_mcts_select(const ya_mcts_tree* tree, const uint32_t* states, int64_t stride, const int8_t* players,
+                   const int32_t* ply, const uint32_t* episode, uint64_t seed, uint64_t game_base, uint32_t sim,
+                   float cpuct, const uint8_t* active, float* features, uint8_t* need_eval, uint32_t* leaf_states,
+                   int32_t* err_flag, void* stream) {
+    if (!tree_ok(tree)) return (int)cudaErrorInvalidValue;
+    if (leaf_states)
+        ya_k_mcts_select<true><<<warp_blocks(tree->n), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
+            *tree, reinterpret_cast<const uint4*>(states), stride, players, ply, episode, seed, game_base, sim, cpuct,
+            active, features, need_eval, leaf_states, err_flag);
+    else
+        ya_k_mcts_select<false><<<warp_blocks(tree->n), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
+            *tree, reinterpret_cast<const uint4*>(states), stride, players, ply, episode, seed, game_base, sim, cpuct,
+            active, features, need_eval, leaf_states, err_flag);
+    return (int)cudaGetLastError();
+}
+
+int ya_mcts_expand(const ya_mcts_tree* tree, const float* pi, const float* value, int uniform, float uniform_p,
+                   float uniform_v, int32_t* err_flag, void* stream) {
+    if (!tree_ok(tree)) return (int)cudaErrorInvalidValue;
+    if (uniform)
+        ya_k_mcts_expand<true><<<warp_blocks(tree->n), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
+            *tree, nullptr, nullptr, uniform_p, uniform_v, err_flag);
+    else
+        ya_k_mcts_expand<false><<<warp_blocks(tree->n), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
+            *tree, pi, value, 0.0f, 0.0f, err_flag);
+    return (int)cudaGetLastError();
+}
+
+int ya_mcts_root_counts(const ya_mcts_tree* tree, const uint32_t* states, int64_t stride, const int8_t* players,
+                        int32_t* counts, int32_t* visits, double* qvals, uint8_t* qkind, void* stream) {
+    if (!tree_ok(tree)) return (int)cudaErrorInvalidValue;
+    ya_k_mcts_root_counts<<<warp_blocks(tree->n), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
+        *tree, reinterpret_cast<const uint4*>(states), stride, players, counts, visits, qvals, qkind);
+    return (int)cudaGetLastError();
+}
+
+int ya_mcts_pick_action(const int32_t* counts, const int32_t* ply, const uint32_t* episode, int64_t n, uint64_t seed,
+                        uint64_t game_base, int temp_threshold, int32_t* actions, void* stream) {
+    if (n <= 0) return 0;
+    ya_k_mcts_pick<<<warp_blocks(n), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
+        counts, ply, episode, n, seed, game_base, temp_threshold, actions);
+    return (int)cudaGetLastError();
+}
+
+}  // extern "C"

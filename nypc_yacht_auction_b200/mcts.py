@@ -1,0 +1,289 @@
+"""MCTS host side: the batched self-play searcher (thousands of lock-step games, one warp per game
+on device) and the drop-in ``MCTS`` class with the reference's constructor / ``getActionProb`` /
+``search`` surface (/root/reference/MCTS.py:16,28,56), both driving the same CUDA kernels
+(csrc/ya_mcts.cu) through the C ABI.  No tree logic runs on the host.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from .engine import ACTION_SIZE, FEATURE_SIZE, BatchedYacht
+from .layout import YachtBoard, boards_to_planes, pack_state, planes_to_boards
+
+ERR_BITS = {0x100: "MCTS node pool full (raise max_nodes)", 0x200: "MCTS arena full (raise arena_mb_per_game)",
+            0x400: "MCTS path deeper than 16", 0x800: "rule error inside search"}
+
+
+def _next_pow2(x):
+    p = 1
+    while p < x:
+        p *= 2
+    return p
+
+
+class TreePool:
+    """Device storage of n per-game trees (include/yacht_b200.h: ya_mcts_tree)."""
+
+    def __init__(self, n, num_sims, device, arena_mb_per_game=None, max_nodes=None):
+        self.n = int(n)
+        self.device = torch.device(device)
+        lib = _lib.load()
+        self.max_nodes = int(max_nodes or (6 * num_sims + 16))
+        assert self.max_nodes < 65535
+        self.ht_size = _next_pow2(2 * self.max_nodes)
+        if arena_mb_per_game is None:
+            # worst case: every node of a round owns a full 3024-entry prior row + an edge chunk
+            arena_mb_per_game = min(4.0 * num_sims * (3024 + 114) * 4 / 2 ** 20, 64.0)
+            arena_mb_per_game = max(arena_mb_per_game, 0.25)
+        words = int(arena_mb_per_game * 2 ** 20) // 4
+        self.arena_words = words - (words % 2)
+        d = self.device
+        self.nodes = torch.zeros((self.n, self.max_nodes, lib.ya_mcts_node_words()), dtype=torch.int32, device=d)
+        self.ht = torch.zeros((self.n, self.ht_size), dtype=torch.int16, device=d)
+        self.arena = torch.empty((self.n, self.arena_words), dtype=torch.int32, device=d)
+        self.meta = torch.zeros((self.n, 4), dtype=torch.int32, device=d)
+        self.cursor = torch.zeros((self.n, lib.ya_mcts_cursor_words()), dtype=torch.int32, device=d)
+        self.struct = _lib.MctsTreeStruct(
+            self.nodes.data_ptr(), self.ht.data_ptr(), self.arena.data_ptr(), self.meta.data_ptr(),
+            self.cursor.data_ptr(), self.n, self.max_nodes, self.ht_size, self.arena_words)
+        self.ref = ctypes.byref(self.struct)
+        self.lib = lib
+        self.reset()
+
+    def bytes(self):
+        return sum(t.numel() * t.element_size() for t in (self.nodes, self.ht, self.arena, self.meta, self.cursor))
+
+    def reset(self, which=None):
+        _lib.check(self.lib.ya_mcts_reset(self.ref, _lib.ptr(which), _lib.current_stream()), "ya_mcts_reset")
+
+    def node_counts(self):
+        return self.meta[:, 0]
+
+
+class UniformEvaluator:
+    """BASELINE.json configs[2]: P = 1/3226 (float32), v = 0; handled inside ya_mcts_expand."""
+    uniform = True
+    p = float(np.float32(1.0) / np.float32(ACTION_SIZE))
+    v = 0.0
+
+
+class TorchEvaluator:
+    """One batched forward of a policy/value net for all leaves (the only dense contraction).
+    predict semantics of yacht/NNet.py:177-195: pi = exp(log_softmax(logits)) over all 3226 actions."""
+    uniform = False
+
+    def __init__(self, net, autocast_dtype=None):
+        self.net = net.eval()
+        self.autocast_dtype = autocast_dtype
+
+    @torch.no_grad()
+    def __call__(self, features, need_eval=None, leaf_states=None):
+        if self.autocast_dtype is not None:
+            with torch.autocast("cuda", dtype=self.autocast_dtype):
+                logits, v = self.net(features)
+        else:
+            logits, v = self.net(features)
+        pi = torch.softmax(logits.float(), dim=1)
+        return pi.contiguous(), v.float().reshape(-1).contiguous()
+
+
+class BatchedMCTS:
+    """numMCTSSims simulations for every game of a BatchedYacht per move, tree kept per episode
+    (Coach.py:93) and pruned at round boundaries."""
+
+    def __init__(self, env: BatchedYacht, num_sims, cpuct=1.5, evaluator=None, temp_threshold=15,
+                 arena_mb_per_game=None, max_nodes=None, want_leaf_states=False):
+        self.env = env
+        self.lib = env.lib
+        self.num_sims = int(num_sims)
+        self.cpuct = float(cpuct)
+        self.temp_threshold = int(temp_threshold)
+        self.evaluator = evaluator or UniformEvaluator()
+        self.pool = TreePool(env.n, self.num_sims, env.device, arena_mb_per_game, max_nodes)
+        d = env.device
+        n = env.n
+        self.features = torch.zeros((n, FEATURE_SIZE), dtype=torch.float32, device=d)
+        self.need_eval = torch.zeros(n, dtype=torch.uint8, device=d)
+        self.leaf_states = torch.zeros((2, n, 4), dtype=torch.int32, device=d) if want_leaf_states else None
+        self.counts = torch.zeros((n, ACTION_SIZE), dtype=torch.int32, device=d)
+        self.visits = torch.zeros(n, dtype=torch.int32, device=d)
+        self.err_flag = torch.zeros(1, dtype=torch.int32, device=d)
+        self.picked = torch.zeros(n, dtype=torch.int32, device=d)
+        self.sims_run = 0
+
+    # ------------------------------------------------------------------ one simulation wave
+    def simulate(self, sim):
+        env, s = self.env, _lib.current_stream()
+        _lib.check(self.lib.ya_mcts_select(
+            self.pool.ref, _lib.ptr(env.states), env.n, _lib.ptr(env.players), _lib.ptr(env.ply), _lib.ptr(env.episode),
+            env.seed, env.game_base, sim, self.cpuct, None, _lib.ptr(self.features), _lib.ptr(self.need_eval),
+            _lib.ptr(self.leaf_states), _lib.ptr(self.err_flag), s), "ya_mcts_select")
+        ev = self.evaluator
+        if getattr(ev, "uniform", False):
+            _lib.check(self.lib.ya_mcts_expand(self.pool.ref, None, None, 1, ev.p, ev.v, _lib.ptr(self.err_flag), s),
+                       "ya_mcts_expand")
+        else:
+            pi, v = ev(self.features, self.need_eval, self.leaf_states)
+            assert pi.dtype == torch.float32 and pi.is_contiguous() and pi.shape == (env.n, ACTION_SIZE)
+            assert v.dtype == torch.float32 and v.is_contiguous() and v.shape == (env.n,)
+            _lib.check(self.lib.ya_mcts_expand(self.pool.ref, _lib.ptr(pi), _lib.ptr(v), 0, 0.0, 0.0,
+                                               _lib.ptr(self.err_flag), s), "ya_mcts_expand")
+        self.sims_run += env.n
+
+    def search(self):
+        """getActionProb's simulation loop (MCTS.py:37-38) for every game."""
+        for sim in range(self.num_sims):
+            self.simulate(sim)
+
+    def check_errors(self):
+        e = int(self.err_flag.item())
+        if e:
+            msgs = [m for b, m in ERR_BITS.items() if e & b]
+            raise _lib.YachtB200Error("MCTS kernel error %#x: %s" % (e, "; ".join(msgs)))
+
+    def root_counts(self, with_q=False):
+        env = self.env
+        q = kind = None
+        if with_q:
+            q = torch.zeros((env.n, ACTION_SIZE), dtype=torch.float64, device=env.device)
+            kind = torch.zeros((env.n, ACTION_SIZE), dtype=torch.uint8, device=env.device)
+        _lib.check(self.lib.ya_mcts_root_counts(
+            self.pool.ref, _lib.ptr(env.states), env.n, _lib.ptr(env.players), _lib.ptr(self.counts), _lib.ptr(self.visits),
+            _lib.ptr(q), _lib.ptr(kind), _lib.current_stream()), "ya_mcts_root_counts")
+        return (self.counts, self.visits, q, kind) if with_q else (self.counts, self.visits)
+
+    def pick_actions(self):
+        env = self.env
+        _lib.check(self.lib.ya_mcts_pick_action(
+            _lib.ptr(self.counts), _lib.ptr(env.ply), _lib.ptr(env.episode), env.n, env.seed, env.game_base,
+            self.temp_threshold, _lib.ptr(self.picked), _lib.current_stream()), "ya_mcts_pick_action")
+        return self.picked
+
+    def play_ply(self):
+        """One move of Coach.executeEpisode (Coach.py:54-66) for every game: search, pick, step."""
+        self.search()
+        self.root_counts()
+        actions = self.pick_actions()
+        self.env.next_state(actions, check=False)
+        return actions
+
+    def new_episode(self):
+        """Coach.py:93: a fresh tree per episode."""
+        self.pool.reset()
+        self.env.episode += 1
+        self.env.reset()
+
+
+# ======================================================================================= drop-in
+class MCTS:
+    """Drop-in for /root/reference/MCTS.py: ``MCTS(game, nnet, args)``, ``getActionProb(board, temp)``.
+
+    The tree lives on the GPU (one game); ``nnet.predict(canonicalBoard)`` is called on the host for
+    every leaf exactly like the reference does (MCTS.py:86), so any evaluator plugs in.  Dice rolled
+    *inside* search come from the engine's Philox stream keyed by (seed, tree id, root index, sim,
+    depth) instead of the global numpy RNG (see DESIGN.md "Randomness")."""
+
+    _next_tree_id = 0
+
+    def __init__(self, game, nnet, args):
+        self.game = game
+        self.nnet = nnet
+        self.args = args
+        self.device = torch.device(getattr(game, "device", "cuda"))
+        if not torch.cuda.is_available():
+            raise _lib.YachtB200Error("no CUDA device: MCTS has no CPU fallback")
+        self.lib = _lib.load()
+        sims = int(args.numMCTSSims)
+        self.pool = TreePool(1, max(sims, 1), self.device,
+                             arena_mb_per_game=_arg(args, "arena_mb_per_game", None), max_nodes=_arg(args, "max_nodes", None))
+        self.seed = int(_arg(args, "search_seed", 0))
+        self.tree_id = int(_arg(args, "tree_id", MCTS._next_tree_id))
+        MCTS._next_tree_id += 1
+        d = self.device
+        self.states = torch.zeros((2, 1, 4), dtype=torch.int32, device=d)
+        self.players = torch.ones(1, dtype=torch.int8, device=d)
+        self.ply = torch.zeros(1, dtype=torch.int32, device=d)
+        self.features = torch.zeros((1, FEATURE_SIZE), dtype=torch.float32, device=d)
+        self.need_eval = torch.zeros(1, dtype=torch.uint8, device=d)
+        self.leaf_states = torch.zeros((2, 1, 4), dtype=torch.int32, device=d)
+        self.err_flag = torch.zeros(1, dtype=torch.int32, device=d)
+        self.counts = torch.zeros((1, ACTION_SIZE), dtype=torch.int32, device=d)
+        self.visits = torch.zeros(1, dtype=torch.int32, device=d)
+        self.pi_dev = torch.zeros((1, ACTION_SIZE), dtype=torch.float32, device=d)
+        self.v_dev = torch.zeros(1, dtype=torch.float32, device=d)
+        self.root_index = -1          # number of getActionProb calls - 1 = the "ply" of the draw counter
+        self.sim_index = 0
+        self._root = None
+
+    def _load_root(self, board):
+        b = pack_state(board)
+        if b != self._root:
+            self.states.copy_(torch.from_numpy(boards_to_planes([b]).view(np.int32)))
+            self._root = b
+
+    def search(self, canonicalBoard):
+        """One simulation from canonicalBoard (MCTS.py:56-164)."""
+        self._load_root(canonicalBoard)
+        if self.root_index < 0:
+            self.root_index = 0
+        self.ply.fill_(self.root_index)
+        s = _lib.current_stream()
+        _lib.check(self.lib.ya_mcts_select(
+            self.pool.ref, _lib.ptr(self.states), 1, _lib.ptr(self.players), _lib.ptr(self.ply), None,
+            self.seed, self.tree_id, self.sim_index, float(self.args.cpuct), None, _lib.ptr(self.features),
+            _lib.ptr(self.need_eval), _lib.ptr(self.leaf_states), _lib.ptr(self.err_flag), s), "ya_mcts_select")
+        self.sim_index += 1
+        if int(self.need_eval.item()):
+            leaf = planes_to_boards(self.leaf_states.cpu().numpy().view(np.uint32))[0]
+            pi, v = self.nnet.predict(leaf)                                   # MCTS.py:86
+            pi = np.ascontiguousarray(np.asarray(pi, dtype=np.float32).reshape(ACTION_SIZE))
+            self.pi_dev.copy_(torch.from_numpy(pi).unsqueeze(0))
+            self.v_dev.fill_(float(np.float32(v)))
+            _lib.check(self.lib.ya_mcts_expand(self.pool.ref, _lib.ptr(self.pi_dev), _lib.ptr(self.v_dev), 0, 0.0, 0.0,
+                                               _lib.ptr(self.err_flag), s), "ya_mcts_expand")
+
+    def getActionProb(self, canonicalBoard, temp=1):
+        """MCTS.py:28-54."""
+        self.root_index += 1
+        self.sim_index = 0
+        for _ in range(int(self.args.numMCTSSims)):
+            self.search(canonicalBoard)
+        e = int(self.err_flag.item())
+        if e:
+            raise _lib.YachtB200Error("MCTS kernel error %#x: %s" % (e, "; ".join(m for b, m in ERR_BITS.items() if e & b)))
+        _lib.check(self.lib.ya_mcts_root_counts(
+            self.pool.ref, _lib.ptr(self.states), 1, _lib.ptr(self.players), _lib.ptr(self.counts), _lib.ptr(self.visits),
+            None, None, _lib.current_stream()), "ya_mcts_root_counts")
+        counts = [int(x) for x in self.counts[0].cpu().numpy()]
+        if temp == 0:
+            bestAs = np.array(np.argwhere(counts == np.max(counts))).flatten()    # MCTS.py:45-49
+            bestA = np.random.choice(bestAs)
+            probs = [0] * len(counts)
+            probs[bestA] = 1
+            return probs
+        counts = [x ** (1. / temp) for x in counts]                               # MCTS.py:51-54
+        counts_sum = float(sum(counts))
+        return [x / counts_sum for x in counts]
+
+    def root_statistics(self):
+        """(counts int32[3226], Ns, Q float64[3226], kind uint8[3226]) of the last searched root."""
+        q = torch.zeros((1, ACTION_SIZE), dtype=torch.float64, device=self.device)
+        kind = torch.zeros((1, ACTION_SIZE), dtype=torch.uint8, device=self.device)
+        _lib.check(self.lib.ya_mcts_root_counts(
+            self.pool.ref, _lib.ptr(self.states), 1, _lib.ptr(self.players), _lib.ptr(self.counts), _lib.ptr(self.visits),
+            _lib.ptr(q), _lib.ptr(kind), _lib.current_stream()), "ya_mcts_root_counts")
+        return self.counts[0].cpu().numpy(), int(self.visits.item()), q[0].cpu().numpy(), kind[0].cpu().numpy()
+
+    def node_count(self):
+        return int(self.pool.meta[0, 0].item())
+
+
+def _arg(args, name, default):
+    try:
+        return args[name] if name in args else default
+    except TypeError:
+        return getattr(args, name, default)

@@ -45,3 +45,18 @@ class TapeDraw:
 
     def done(self):
         return not self.tape
+
+
+def to_oracle_board(yb):
+    """YachtBoard (or anything with the reference's attributes) -> oracle.yacht_rules.Board."""
+    from oracle import yacht_rules as yr
+    b = yr.Board()
+    b.rnd, b.phase = yb.round_no, yb.phase
+    b.pool_a, b.pool_b = [int(x) for x in yb.rollA], [int(x) for x in yb.rollB]
+
+    def conv(x):
+        return None if x is None else ("AB".index(x[0]), int(x[1]))
+    b.bids = [conv(yb.p1_bid), conv(yb.p2_bid)]
+    for i, p in enumerate((yb.p1, yb.p2)):
+        b.sides[i] = yr.Side([int(x) for x in p.carry], int(p.used_mask), [int(x) for x in p.cat_scores], int(p.bid_score))
+    return b

@@ -1,0 +1,181 @@
+"""Parity of the CUDA MCTS (select / expand / backup kernels through the C ABI) against
+(a) golden traces of the reference's own MCTS.py and (b) the oracle, with identical evaluators and
+identical injected dice.  Visit counts, chosen actions and node creation are exact; root Q values are
+compared bit-for-bit including their numeric type (numpy float32 vs Python float)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import mcts_oracle
+from oracle import yacht_rules as yr
+from conftest import to_oracle_board
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mcts_golden.json")
+EVALUATORS = {
+    "uniform_s25": mcts_oracle.uniform_evaluator,
+    "hashed_s30": mcts_oracle.hashed_evaluator,
+    "hashed_s64_temp0": lambda b: mcts_oracle.hashed_evaluator(b, 7),
+    "hashed_s200_late": lambda b: mcts_oracle.hashed_evaluator(b, 3),
+}
+
+
+def load_cases():
+    with open(GOLDEN) as f:
+        return json.load(f)["cases"]
+
+
+class HostEvaluator:
+    """Test-only evaluator: runs the oracle's deterministic pseudo-network on the host for every leaf."""
+    uniform = False
+
+    def __init__(self, fn, n):
+        self.fn = fn
+        self.evals = 0
+        self.pi = torch.zeros((n, 3226), dtype=torch.float32)
+        self.v = torch.zeros(n, dtype=torch.float32)
+
+    def __call__(self, features, need_eval, leaf_states):
+        from nypc_yacht_auction_b200.layout import planes_to_boards
+        need = need_eval.cpu().numpy()
+        boards = planes_to_boards(leaf_states.cpu().numpy().view(np.uint32))
+        feats = features.cpu().numpy()
+        for g in np.flatnonzero(need):
+            ob = to_oracle_board(boards[g])
+            assert feats[g].tobytes() == yr.features(ob).tobytes()        # the device feature row of the leaf
+            pi, v = self.fn(ob)
+            self.pi[g] = torch.from_numpy(pi)
+            self.v[g] = float(v)
+            self.evals += 1
+        return self.pi.cuda(), self.v.cuda()
+
+
+def _engine(n, seed, base):
+    from nypc_yacht_auction_b200.engine import BatchedYacht
+    return BatchedYacht(n, seed=seed, game_base=base)
+
+
+@pytest.mark.parametrize("case", load_cases(), ids=lambda c: c["name"])
+def test_batched_mcts_reproduces_reference_traces(case):
+    from nypc_yacht_auction_b200.mcts import BatchedMCTS, UniformEvaluator
+    from nypc_yacht_auction_b200.layout import string_key
+    env = _engine(1, case["seed"], case["game"])
+    if case["name"].startswith("uniform"):
+        ev = UniformEvaluator()
+    else:
+        ev = HostEvaluator(EVALUATORS[case["name"]], 1)
+    mcts = BatchedMCTS(env, case["sims"], case["cpuct"], evaluator=ev, temp_threshold=case["temp_threshold"],
+                       want_leaf_states=True)
+    prev_nodes = 0
+    for ref in case["trace"]:
+        canon = env.canonical()
+        from nypc_yacht_auction_b200.layout import planes_to_boards
+        assert string_key(planes_to_boards(canon.cpu().numpy().view(np.uint32))[0]) == ref["key"]
+        before = getattr(ev, "evals", 0)
+        mcts.search()
+        mcts.check_errors()
+        counts, visits = mcts.root_counts()
+        c = counts[0].cpu().numpy()
+        got = {str(int(a)): int(c[a]) for a in np.flatnonzero(c)}
+        assert got == ref["counts"], ref["ply"]
+        assert int(visits.item()) == ref["ns"]
+        if not case["name"].startswith("uniform"):
+            assert ev.evals - before == ref["nodes"] - prev_nodes       # same leaves created this move
+        prev_nodes = ref["nodes"]
+        a = mcts.pick_actions()
+        assert int(a.item()) == ref["action"]
+        last = ref
+        if ref is case["trace"][-1]:
+            _, _, q, kind = mcts.root_counts(with_q=True)
+            q, kind = q[0].cpu().numpy(), kind[0].cpu().numpy()
+            for act, (k, hexval) in ref["q"].items():
+                assert {1: "f32", 2: "f64"}[int(kind[int(act)])] == k
+                assert float(q[int(act)]).hex() == hexval
+        env.next_state(a)
+    assert string_key(env.boards()[0]) == case["final_key"]
+    assert float(env.game_ended().item()) == case["result"]
+    assert int(env.players.item()) == case["final_player"]
+
+
+def test_batched_mcts_many_games_vs_oracle():
+    """Several games in one batch, hashed evaluator, compared per ply with the oracle's self-play."""
+    from nypc_yacht_auction_b200.mcts import BatchedMCTS
+    n, seed, base, sims, cpuct = 6, 21, 5000, 20, 1.5
+    fn = lambda b: mcts_oracle.hashed_evaluator(b, 11)
+    plies = 16
+    traces = [mcts_oracle.self_play_game(fn, sims, cpuct, seed, base + g, temp_threshold=6, max_plies=plies)[0]
+              for g in range(n)]
+    env = _engine(n, seed, base)
+    ev = HostEvaluator(fn, n)
+    mcts = BatchedMCTS(env, sims, cpuct, evaluator=ev, temp_threshold=6, want_leaf_states=True)
+    for ply in range(plies):
+        mcts.search()
+        mcts.check_errors()
+        counts, _ = mcts.root_counts()
+        c = counts.cpu().numpy()
+        acts = mcts.pick_actions().cpu().numpy()
+        for g in range(n):
+            got = {int(a): int(c[g][a]) for a in np.flatnonzero(c[g])}
+            assert got == traces[g][ply]["counts"], (g, ply)
+            assert int(acts[g]) == traces[g][ply]["action"]
+        env.next_state(mcts.picked)
+
+
+def test_uniform_full_games_vs_oracle():
+    """BASELINE.json configs[2] semantics (uniform prior, 25 sims) on a small batch, every ply."""
+    from nypc_yacht_auction_b200.mcts import BatchedMCTS
+    n, seed, base = 3, 2, 300
+    traces = [mcts_oracle.self_play_game(mcts_oracle.uniform_evaluator, 25, 1.5, seed, base + g)[0] for g in range(n)]
+    env = _engine(n, seed, base)
+    mcts = BatchedMCTS(env, 25, 1.5)
+    for ply in range(48):
+        mcts.play_ply()
+        c = mcts.counts.cpu().numpy()
+        for g in range(n):
+            got = {int(a): int(c[g][a]) for a in np.flatnonzero(c[g])}
+            assert got == traces[g][ply]["counts"], (g, ply)
+            assert int(mcts.picked[g].item()) == traces[g][ply]["action"]
+    mcts.check_errors()
+    assert bool((env.game_ended() != 0).all())
+
+
+def test_dropin_mcts_class_matches_reference_trace():
+    """The reference-shaped MCTS(game, nnet, args).getActionProb surface on the 'hashed_s30' golden."""
+    from nypc_yacht_auction_b200.mcts import MCTS
+    from nypc_yacht_auction_b200.engine import BatchedYacht
+    case = [c for c in load_cases() if c["name"] == "hashed_s30"][0]
+
+    class Args(dict):
+        __getattr__ = dict.__getitem__
+
+    class Net:
+        def predict(self, board):
+            return mcts_oracle.hashed_evaluator(to_oracle_board(board))
+
+    env = _engine(1, case["seed"], case["game"])
+    args = Args(numMCTSSims=case["sims"], cpuct=case["cpuct"], search_seed=case["seed"], tree_id=case["game"])
+    mcts = MCTS(None, Net(), args)
+    from nypc_yacht_auction_b200.layout import planes_to_boards
+    for ref in case["trace"][:20]:
+        canon = planes_to_boards(env.canonical().cpu().numpy().view(np.uint32))[0]
+        probs = mcts.getActionProb(canon, temp=1)
+        total = sum(ref["counts"].values())
+        assert len(probs) == 3226 and abs(sum(probs) - 1.0) < 1e-12
+        for a, cnt in ref["counts"].items():
+            assert probs[int(a)] == cnt / float(total)
+        assert sum(1 for p in probs if p) == len(ref["counts"])
+        env.next_state(torch.tensor([ref["action"]], dtype=torch.int32))
+
+
+def test_pool_overflow_is_reported():
+    from nypc_yacht_auction_b200.mcts import BatchedMCTS
+    from nypc_yacht_auction_b200._lib import YachtB200Error
+    env = _engine(2, 0, 0)
+    mcts = BatchedMCTS(env, 25, 1.5, max_nodes=8)
+    mcts.search()
+    with pytest.raises(YachtB200Error):
+        mcts.check_errors()
