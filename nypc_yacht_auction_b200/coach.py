@@ -1,0 +1,115 @@
+"""Self-play surface of the reference's Coach (/root/reference/Coach.py:34-72).
+
+* ``Coach.executeEpisode`` -- the reference's one-game loop, unchanged in behaviour, for use with the
+  drop-in ``YachtGame`` / ``MCTS`` (global numpy RNG for the move sampling, like Coach.py:65).
+* ``BatchedSelfPlay`` -- the same episode for thousands of games in lock-step on the GPU: every
+  ply = numMCTSSims x (select, ONE batched evaluator call, expand/backup), then device-side move
+  sampling and the fused transition.  Training examples stay on the device as compact tensors
+  (feature rows, sparse visit counts, outcomes) instead of pickled Python objects.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .engine import ACTION_SIZE, FEATURE_SIZE, BatchedYacht
+from .mcts import MCTS, BatchedMCTS
+
+
+class Coach:
+    """Coach.py:17-72 (self-play part).  ``learn`` (training / arena gate, Coach.py:74-139) is
+    orchestration outside the accelerated path: use the reference's Coach with this package's
+    YachtGame and MCTS for it."""
+
+    def __init__(self, game, nnet, args):
+        self.game = game
+        self.nnet = nnet
+        self.args = args
+        self.mcts = MCTS(self.game, self.nnet, self.args)
+        self.trainExamplesHistory = []
+        self.skipFirstSelfPlay = False
+
+    def executeEpisode(self):
+        """Coach.py:34-72."""
+        trainExamples = []
+        board = self.game.getInitBoard()
+        self.curPlayer = 1
+        episodeStep = 0
+        while True:
+            episodeStep += 1
+            canonicalBoard = self.game.getCanonicalForm(board, self.curPlayer)
+            temp = int(episodeStep < self.args.tempThreshold)
+            pi = self.mcts.getActionProb(canonicalBoard, temp=temp)
+            sym = self.game.getSymmetries(canonicalBoard, pi)
+            for b, p in sym:
+                trainExamples.append([b, self.curPlayer, p, None])
+            action = np.random.choice(len(pi), p=pi)
+            board, self.curPlayer = self.game.getNextState(board, self.curPlayer, action)
+            r = self.game.getGameEnded(board, self.curPlayer)
+            if r != 0:
+                return [(x[0], x[2], r * ((-1) ** (x[1] != self.curPlayer))) for x in trainExamples]
+
+
+class BatchedSelfPlay:
+    """n concurrent episodes; game g of rank r is global game ``game_base + g``."""
+
+    PLIES = 48
+
+    def __init__(self, n, num_sims, cpuct=1.5, evaluator=None, temp_threshold=15, seed=0, game_base=0,
+                 device="cuda", arena_mb_per_game=None, record_examples=True, max_edges=None):
+        self.env = BatchedYacht(n, seed=seed, game_base=game_base, device=device)
+        self.mcts = BatchedMCTS(self.env, num_sims, cpuct, evaluator, temp_threshold, arena_mb_per_game)
+        self.n = n
+        self.record = record_examples
+        self.k = int(max_edges or min(ACTION_SIZE, 2 * num_sims))
+        d = self.env.device
+        if self.record:
+            self.ex_features = torch.zeros((self.PLIES, n, FEATURE_SIZE), dtype=torch.float32, device=d)
+            self.ex_actions = torch.zeros((self.PLIES, n, self.k), dtype=torch.int16, device=d)
+            self.ex_counts = torch.zeros((self.PLIES, n, self.k), dtype=torch.int32, device=d)
+            self.ex_players = torch.zeros((self.PLIES, n), dtype=torch.int8, device=d)
+
+    def play_ply(self, t):
+        env, m = self.env, self.mcts
+        if self.record:
+            env.features(out=self.ex_features[t])                    # state_to_vec of the canonical root
+            self.ex_players[t].copy_(env.players)
+        m.search()
+        counts, _ = m.root_counts()
+        if self.record:
+            vals, idx = torch.topk(counts, self.k, dim=1)            # the <= k visited root edges
+            self.ex_counts[t].copy_(vals)
+            self.ex_actions[t].copy_(idx.to(torch.int16))
+        actions = m.pick_actions()
+        env.next_state(actions, check=False)
+        return actions
+
+    def execute_episodes(self):
+        """One full episode for every game.  Returns dict(features[T,n,59], actions[T,n,k], counts[T,n,k],
+        value[T,n]) with value = +-1 / 1e-4 from the mover's view (Coach.py:69-72)."""
+        for t in range(self.PLIES):
+            self.play_ply(t)
+        self.mcts.check_errors()
+        env = self.env
+        ones = torch.ones_like(env.players)
+        result_p1 = env.game_ended(players=ones)                     # from player 1's view
+        assert bool((result_p1 != 0).all()), "every game ends after 48 plies"
+        out = None
+        if self.record:
+            # r * (-1)**(player != curPlayer) with curPlayer == 1 at the end of round 13 (Coach.py:69-72):
+            # +-1 for a decided game and +-1e-4 for a draw, both = result_p1 * player
+            value = result_p1.unsqueeze(0) * self.ex_players.float()
+            out = {"features": self.ex_features, "actions": self.ex_actions, "counts": self.ex_counts, "value": value,
+                   "result_p1": result_p1}
+        return out
+
+    def next_episode(self):
+        self.mcts.new_episode()
+
+    @staticmethod
+    def dense_policy(actions, counts):
+        """Sparse (actions, counts) rows -> float64 pi[.., 3226] = counts / sum (MCTS.py:51-54, temp 1)."""
+        shape = actions.shape[:-1]
+        pi = torch.zeros(shape + (ACTION_SIZE,), dtype=torch.float64, device=actions.device)
+        pi.scatter_add_(-1, actions.long() & 0xFFFF, counts.double())
+        return pi / pi.sum(-1, keepdim=True)

@@ -130,6 +130,61 @@ def run_case(name, fn, sims, cpuct, seed, game, temp_threshold, max_plies=None):
         ref_mod.roll_five, ref_mod.tiebreak_uniform = keep
 
 
+def coach_episode_case(mt_seed, sims, cpuct, temp_threshold, search_seed, tree_id):
+    """Reference Coach.executeEpisode (Coach.py:34-72), unmodified, MT19937-seeded; only the dice rolled
+    INSIDE MCTS.search are replaced by the Philox protocol (real moves keep the reference's own hooks)."""
+    from Coach import Coach
+    keep = (ref_mod.roll_five, ref_mod.tiebreak_uniform)
+    inj = Injector(search_seed, tree_id)
+    state = {"ply": -1, "sim": -1, "depth": -1}
+
+    def roll():
+        return inj.roll() if state["depth"] >= 0 else keep[0]()
+
+    def tie():
+        return inj.tie() if state["depth"] >= 0 else keep[1]()
+    ref_mod.roll_five, ref_mod.tiebreak_uniform = roll, tie
+    try:
+        class HashedNet:
+            def __init__(self, game=None, args=None):
+                pass
+
+            def predict(self, board):
+                return mcts_oracle.hashed_evaluator(to_oracle_board(board), 5)
+
+        g = YachtGame(seed=mt_seed)
+        args = dotdict({"numMCTSSims": sims, "cpuct": cpuct, "tempThreshold": temp_threshold})
+        coach = Coach(g, HashedNet(), args)
+        mcts = coach.mcts
+        orig_search, orig_gap = MCTS.search, MCTS.getActionProb
+
+        def search(board):
+            state["depth"] += 1
+            if state["depth"] == 0:
+                state["sim"] += 1
+            inj.arm(state["ply"], philox.TAG_SEARCH, state["depth"], state["sim"])
+            try:
+                return orig_search(mcts, board)
+            finally:
+                state["depth"] -= 1
+
+        def gap(board, temp=1):
+            state["ply"] += 1
+            state["sim"] = -1
+            return orig_gap(mcts, board, temp=temp)
+        mcts.search, mcts.getActionProb = search, gap
+        examples = coach.executeEpisode()
+        out = []
+        for board, pi, v in examples:
+            out.append({"key": g.stringRepresentation(board), "v": float(v),
+                        "pi": {str(a): float(p).hex() for a, p in enumerate(pi) if p}})
+        return {"mt_seed": mt_seed, "sims": sims, "cpuct": cpuct, "temp_threshold": temp_threshold,
+                "search_seed": search_seed, "tree_id": tree_id, "examples": out,
+                "rng_after": int(np.random.randint(0, 2 ** 31))}
+    finally:
+        ref_mod.roll_five, ref_mod.tiebreak_uniform = keep
+
+
 def main():
     cases = [
         run_case("uniform_s25", mcts_oracle.uniform_evaluator, 25, 1.5, 0, 0, 15),
@@ -137,8 +192,11 @@ def main():
         run_case("hashed_s64_temp0", lambda b: mcts_oracle.hashed_evaluator(b, 7), 64, 1.1, 9, 1000003, 3, max_plies=14),
         run_case("hashed_s200_late", lambda b: mcts_oracle.hashed_evaluator(b, 3), 200, 2.0, 11, 77, 100, max_plies=6),
     ]
+    coach = [coach_episode_case(0, 20, 1.5, 15, 3, 9), coach_episode_case(4, 12, 1.0, 4, 8, 123)]
     with open(os.path.join(HERE, "mcts_golden.json"), "w") as f:
-        json.dump({"numpy": np.__version__, "cases": cases}, f, separators=(",", ":"))
+        json.dump({"numpy": np.__version__, "cases": cases, "coach": coach}, f, separators=(",", ":"))
+    for c in coach:
+        print("coach", c["mt_seed"], len(c["examples"]), "examples", c["examples"][-1]["v"], c["rng_after"])
     for c in cases:
         t = c["trace"]
         print(c["name"], "plies", len(t), "result", c["result"], "nodes", c["total_nodes"], "evals", c["leaf_evals"],

@@ -1,0 +1,134 @@
+"""The drop-in a0g surface (YachtGame / MCTS / Coach.executeEpisode) on the GPU against golden runs of
+the reference under the same MT19937 seeds: same hooks, same RNG consumption, same boards."""
+import hashlib
+import json
+import os
+import pickle
+
+import numpy as np
+import pytest
+
+from oracle import mcts_oracle
+from conftest import to_oracle_board
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def arena_play_game(game, player1, player2, on_ply=None):
+    """Restates the loop of Arena.playGame (Arena.py:30-93) to drive the Game API the way Arena does."""
+    players = [player2, None, player1]
+    cur = 1
+    board = game.getInitBoard()
+    while game.getGameEnded(board, cur) == 0:
+        canon = game.getCanonicalForm(board, cur)
+        action = players[cur + 1](canon)
+        valids = game.getValidMoves(game.getCanonicalForm(board, cur), 1)
+        assert valids[action] > 0
+        if on_ply:
+            on_ply(canon, valids, action)
+        board, cur = game.getNextState(board, cur, action)
+    return cur * game.getGameEnded(board, cur), board
+
+
+def test_seeded_arena_games_match_reference(rules_golden):
+    """YachtGame(seed) + RandomYachtPlayer: the MT19937-seeded traces quoted in SURVEY.md section 8c."""
+    from nypc_yacht_auction_b200.game import YachtGame
+    from nypc_yacht_auction_b200.players import RandomYachtPlayer
+    meta, _ = rules_golden
+    for tr in meta["seeded"]:
+        g = YachtGame(seed=tr["seed"])
+        pl = RandomYachtPlayer(g)
+        h = hashlib.sha256()
+        actions = []
+
+        def on_ply(canon, valids, action):
+            h.update(g.stringRepresentation(canon).encode())
+            h.update(valids.tobytes())
+            actions.append(action)
+        # Arena evaluates the player before the legality check; the digest needs the same order
+        result, board = arena_play_game(g, pl.play, pl.play, on_ply)
+        assert actions == [p["action"] for p in tr["plies"]]
+        assert h.hexdigest() == tr["sha256"]
+        assert g.stringRepresentation(board) == tr["final_key"]
+        assert [board.p1.total_with_bonus(), board.p2.total_with_bonus()] == tr["totals"]
+        assert g.getGameEnded(board, 1) == tr["ended_p1"]
+    assert meta["seeded"][0]["sha256"] == "1110e34fdc95c665983452581b2e4d862e3442376f14bd86e701e9326bf5a70c"
+
+
+def test_game_api_contract():
+    from nypc_yacht_auction_b200.game import YachtGame
+    from nypc_yacht_auction_b200.layout import YachtBoard
+    g = YachtGame(seed=3)
+    assert g.getBoardSize() == (1, 59) and g.getActionSize() == 3226
+    b = g.getInitBoard()
+    assert isinstance(b, YachtBoard) and b.round_no == 1 and b.phase == 0 and len(b.rollA) == 5
+    assert g.getCanonicalForm(b, 1) is b
+    v = g.getValidMoves(b, 1)
+    assert v.dtype == np.uint8 and v.shape == (3226,) and int(v.sum()) == 202
+    assert g.getGameEnded(b, 1) == 0.0 and isinstance(g.getGameEnded(b, 1), float)
+    assert g.getSymmetries(b, [1]) == [(b, [1])]
+    nb, nxt = g.getNextState(b, 1, np.int64(7))
+    assert nxt == -1 and nb.p1_bid == ("A", 3500) and b.p1_bid is None          # input untouched
+    c = g.getCanonicalForm(nb, -1)
+    assert c.p2_bid == ("A", 3500) and c.p1_bid is None
+    with pytest.raises(ValueError):
+        g.getNextState(b, 1, 202)
+    with pytest.raises(ValueError):
+        g.getNextState(b, 1, -1)
+    assert pickle.loads(pickle.dumps(nb)) == nb
+    assert g.stringRepresentation(nb).startswith("r1|ph0|A")
+    vec = g.stateToVec(c)
+    assert vec.dtype == np.float32 and vec.shape == (59,)
+    from oracle import yacht_rules as yr
+    assert vec.tobytes() == yr.features(to_oracle_board(c)).tobytes()
+
+
+def test_coach_execute_episode_matches_reference():
+    """Coach.executeEpisode of the reference (golden) vs the drop-in Coach + MCTS + YachtGame."""
+    from nypc_yacht_auction_b200.game import YachtGame
+    from nypc_yacht_auction_b200.coach import Coach
+    with open(os.path.join(GOLDEN, "mcts_golden.json")) as f:
+        cases = json.load(f)["coach"]
+
+    class Args(dict):
+        __getattr__ = dict.__getitem__
+
+    class HashedNet:
+        def predict(self, board):
+            return mcts_oracle.hashed_evaluator(to_oracle_board(board), 5)
+
+    for case in cases:
+        g = YachtGame(seed=case["mt_seed"])
+        args = Args(numMCTSSims=case["sims"], cpuct=case["cpuct"], tempThreshold=case["temp_threshold"],
+                    search_seed=case["search_seed"], tree_id=case["tree_id"])
+        coach = Coach(g, HashedNet(), args)
+        examples = coach.executeEpisode()
+        assert len(examples) == len(case["examples"])
+        for (board, pi, v), ref in zip(examples, case["examples"]):
+            assert g.stringRepresentation(board) == ref["key"]
+            assert float(v) == ref["v"]
+            assert {str(a): float(p).hex() for a, p in enumerate(pi) if p} == ref["pi"]
+        assert int(np.random.randint(0, 2 ** 31)) == case["rng_after"]        # same global RNG consumption
+        blob = pickle.dumps(examples)                                             # Coach.saveTrainExamples pickles these
+        assert len(pickle.loads(blob)) == len(examples)
+
+
+def test_batched_self_play_examples():
+    """BatchedSelfPlay: labels follow Coach.py:69-72, policies are the root visit counts."""
+    import torch
+    from nypc_yacht_auction_b200.coach import BatchedSelfPlay
+    sp = BatchedSelfPlay(5, 10, cpuct=1.5, seed=4, game_base=50, temp_threshold=15)
+    out = sp.execute_episodes()
+    assert out["features"].shape == (48, 5, 59) and out["value"].shape == (48, 5)
+    res = out["result_p1"].cpu().numpy()
+    val = out["value"].cpu().numpy()
+    players = sp.ex_players.cpu().numpy()
+    assert (val == res[None, :] * players).all()
+    pi = BatchedSelfPlay.dense_policy(out["actions"], out["counts"])
+    assert torch.allclose(pi.sum(-1), torch.ones_like(pi.sum(-1)))
+    # oracle self-play of game 52 with the same uniform evaluator gives the same visit counts at ply 0..5
+    trace = mcts_oracle.self_play_game(mcts_oracle.uniform_evaluator, 10, 1.5, 4, 52, max_plies=6)[0]
+    for t in range(6):
+        c = {int(a): int(n) for a, n in zip(out["actions"][t, 2].cpu().numpy(), out["counts"][t, 2].cpu().numpy()) if n}
+        assert c == trace[t]["counts"]
