@@ -240,7 +240,7 @@ def run_ours(args):
 
     extras = {}
     if not args.no_extras:
-        extras = run_extras(args, torch, env, dev, n, peak)
+        extras = run_extras(args, torch, env, dev, n, peak, rank, world, dist)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -315,7 +315,7 @@ def run_e2e(args, torch, dist, _lib, dev, rank, world, n):
             "timing": "host wall clock around synchronous calls, max over ranks"}
 
 
-def run_extras(args, torch, env, dev, n, peak):
+def run_extras(args, torch, env, dev, n, peak, rank=0, world=1, dist=None):
     """Secondary kernels of the path, timed alone (CUDA events, 3 warm-ups)."""
     out = {}
 
@@ -347,7 +347,7 @@ def run_extras(args, torch, env, dev, n, peak):
                               "note": "fused ply without materialising the mask (68 B/step; L2-resident, latency-bound)"}
     try:
         from nypc_yacht_auction_b200 import mcts_bench
-        out.update(mcts_bench.run(args, torch, dev))
+        out.update(mcts_bench.run(args, torch, dev, rank, world, dist))
     except ImportError:
         pass
     return out

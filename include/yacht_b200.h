@@ -120,17 +120,19 @@ int ya_mcts_reset(const ya_mcts_tree* tree, const uint8_t* which, void* stream);
  * canonical form of states[g].  Leaves that need the evaluator get need_eval[g] = 1, their
  * state_to_vec row in features[g][59] and (optionally) their packed state in leaf_states; all other
  * paths (terminal, dead end) are backed up inside this call.  err_flag bits: 0x100 node pool full,
- * 0x200 arena full, 0x400 path deeper than 16, 0x800 | (1 << status) rule error. */
+ * 0x200 arena full, 0x400 path deeper than 16, 0x800 | (1 << status) rule error.  If sim_ptr (device)
+ * is not NULL the simulation index is read from it, so one captured CUDA graph can be replayed. */
 int ya_mcts_select(const ya_mcts_tree* tree, const uint32_t* states, int64_t stride, const int8_t* players,
                    const int32_t* ply, const uint32_t* episode, uint64_t seed, uint64_t game_base, uint32_t sim,
-                   float cpuct, const uint8_t* active, float* features, uint8_t* need_eval, uint32_t* leaf_states,
-                   int32_t* err_flag, void* stream);
+                   const uint32_t* sim_ptr, float cpuct, const uint8_t* active, float* features, uint8_t* need_eval,
+                   uint32_t* leaf_states, int32_t* err_flag, void* stream);
 
 /* Leaf expansion + backup (MCTS.py:86-115,152-164): pi is float32[n][3226] over ALL actions and
  * value float32[n], as NeuralNet.predict returns them (NeuralNet.py:27-37); with uniform != 0 every
- * leaf gets pi = uniform_p, v = uniform_v without reading memory (BASELINE.json configs[2]). */
+ * leaf gets pi = uniform_p, v = uniform_v without reading memory (BASELINE.json configs[2]).
+ * sim_counter (device, may be NULL) is incremented once per call. */
 int ya_mcts_expand(const ya_mcts_tree* tree, const float* pi, const float* value, int uniform, float uniform_p,
-                   float uniform_v, int32_t* err_flag, void* stream);
+                   float uniform_v, uint32_t* sim_counter, int32_t* err_flag, void* stream);
 
 /* counts[g][a] = Nsa[(root, a)] (MCTS.py:40-42), visits[g] = Ns[root] (-1 if the root is unknown);
  * optional qvals (float64) / qkind (1 = numpy float32, 2 = Python float) expose Qsa for tests. */

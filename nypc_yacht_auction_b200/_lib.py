@@ -34,8 +34,8 @@ SIGNATURES = {
     "ya_mcts_cursor_words": [],
     "ya_mcts_node_words": [],
     "ya_mcts_reset": [_vp, _vp, _vp],
-    "ya_mcts_select": [_vp, _vp, _i64, _vp, _vp, _vp, _u64, _u64, _u32, ctypes.c_float, _vp, _vp, _vp, _vp, _vp, _vp],
-    "ya_mcts_expand": [_vp, _vp, _vp, _int, ctypes.c_float, ctypes.c_float, _vp, _vp],
+    "ya_mcts_select": [_vp, _vp, _i64, _vp, _vp, _vp, _u64, _u64, _u32, _vp, ctypes.c_float, _vp, _vp, _vp, _vp, _vp, _vp],
+    "ya_mcts_expand": [_vp, _vp, _vp, _int, ctypes.c_float, ctypes.c_float, _vp, _vp, _vp],
     "ya_mcts_root_counts": [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp],
     "ya_mcts_pick_action": [_vp, _vp, _vp, _i64, _u64, _u64, _int, _vp, _vp],
     "ya_host_create": [_i64, _int, ctypes.POINTER(ctypes.c_void_p)],

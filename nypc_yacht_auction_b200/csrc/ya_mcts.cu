@@ -139,6 +139,7 @@ __device__ __forceinline__ int ucb_select(const View& v, const uint32_t* node, i
 // ---------------------------------------------------------------- backup (MCTS.py:152-164)
 // Returns false if the arena overflowed.
 __device__ __forceinline__ bool backup_edge(const View& v, uint32_t* node, int ai, const Val& val, uint32_t& arena_top, int lane) {
+    int failed = 0;
     // locate the edge
     uint32_t off = node[N_EDGES];
     int n_edges = (int)node[N_NEDGE];
@@ -199,14 +200,15 @@ __device__ __forceinline__ bool backup_edge(const View& v, uint32_t* node, int a
                 node[N_NEDGE] = (uint32_t)(n_edges + 1);
                 v.arena[node[N_PRIOR] + ai] |= 0x80000000u;                 // mark the prior entry as visited
             } else {
-                arena_top = 0xFFFFFFFFu;
+                failed = 1;
             }
         }
         node[N_VISITS] += 1;                                         // Ns[s] += 1
     }
     arena_top = __shfl_sync(0xFFFFFFFFu, arena_top, 0);
+    failed = __shfl_sync(0xFFFFFFFFu, failed, 0);
     __syncwarp();
-    return arena_top != 0xFFFFFFFFu;
+    return !failed;
 }
 
 __device__ __forceinline__ bool backup_path(const View& v, int depth, Val ret, uint32_t& arena_top, int lane) {
@@ -224,9 +226,11 @@ template <bool WRITE_LEAF_STATE>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 ya_k_mcts_select(ya_mcts_tree tree, const uint4* __restrict__ states, int64_t stride, const int8_t* __restrict__ players,
                  const int32_t* __restrict__ ply, const uint32_t* __restrict__ episode, uint64_t seed, uint64_t game_base,
-                 uint32_t sim, float cpuct, const uint8_t* __restrict__ active, float* __restrict__ features,
-                 uint8_t* __restrict__ need_eval, uint32_t* __restrict__ leaf_states, int32_t* __restrict__ err_flag) {
+                 uint32_t sim, const uint32_t* __restrict__ sim_ptr, float cpuct, const uint8_t* __restrict__ active,
+                 float* __restrict__ features, uint8_t* __restrict__ need_eval, uint32_t* __restrict__ leaf_states,
+                 int32_t* __restrict__ err_flag) {
     const int lane = threadIdx.x & 31;
+    if (sim_ptr) sim = *sim_ptr;                                     // CUDA-graph replay: the counter lives in HBM
     const int64_t g = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     if (g >= tree.n) return;
     if (active && !active[g]) { if (lane == 0) need_eval[g] = 0; return; }
@@ -375,9 +379,10 @@ __device__ __forceinline__ float masked_pairwise_sum(const float* __restrict__ p
 template <bool UNIFORM>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 ya_k_mcts_expand(ya_mcts_tree tree, const float* __restrict__ pi_all, const float* __restrict__ value,
-                 float uniform_p, float uniform_v, int32_t* __restrict__ err_flag) {
+                 float uniform_p, float uniform_v, uint32_t* __restrict__ sim_counter, int32_t* __restrict__ err_flag) {
     const int lane = threadIdx.x & 31;
     const int64_t g = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    if (sim_counter && blockIdx.x == 0 && threadIdx.x == 0) *sim_counter += 1;   // next replay = next simulation
     if (g >= tree.n) return;
     View v = make_view(tree, g);
     if (v.cur[C_KIND] != KIND_NEED_EVAL) return;
@@ -532,29 +537,29 @@ int ya_mcts_reset(const ya_mcts_tree* tree, const uint8_t* which, void* stream) 
 
 int ya_mcts_select(const ya_mcts_tree* tree, const uint32_t* states, int64_t stride, const int8_t* players,
                    const int32_t* ply, const uint32_t* episode, uint64_t seed, uint64_t game_base, uint32_t sim,
-                   float cpuct, const uint8_t* active, float* features, uint8_t* need_eval, uint32_t* leaf_states,
-                   int32_t* err_flag, void* stream) {
+                   const uint32_t* sim_ptr, float cpuct, const uint8_t* active, float* features, uint8_t* need_eval,
+                   uint32_t* leaf_states, int32_t* err_flag, void* stream) {
     if (!tree_ok(tree)) return (int)cudaErrorInvalidValue;
     if (leaf_states)
         ya_k_mcts_select<true><<<warp_blocks(tree->n), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
-            *tree, reinterpret_cast<const uint4*>(states), stride, players, ply, episode, seed, game_base, sim, cpuct,
-            active, features, need_eval, leaf_states, err_flag);
+            *tree, reinterpret_cast<const uint4*>(states), stride, players, ply, episode, seed, game_base, sim, sim_ptr,
+            cpuct, active, features, need_eval, leaf_states, err_flag);
     else
         ya_k_mcts_select<false><<<warp_blocks(tree->n), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
-            *tree, reinterpret_cast<const uint4*>(states), stride, players, ply, episode, seed, game_base, sim, cpuct,
-            active, features, need_eval, leaf_states, err_flag);
+            *tree, reinterpret_cast<const uint4*>(states), stride, players, ply, episode, seed, game_base, sim, sim_ptr,
+            cpuct, active, features, need_eval, leaf_states, err_flag);
     return (int)cudaGetLastError();
 }
 
 int ya_mcts_expand(const ya_mcts_tree* tree, const float* pi, const float* value, int uniform, float uniform_p,
-                   float uniform_v, int32_t* err_flag, void* stream) {
+                   float uniform_v, uint32_t* sim_counter, int32_t* err_flag, void* stream) {
     if (!tree_ok(tree)) return (int)cudaErrorInvalidValue;
     if (uniform)
         ya_k_mcts_expand<true><<<warp_blocks(tree->n), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
-            *tree, nullptr, nullptr, uniform_p, uniform_v, err_flag);
+            *tree, nullptr, nullptr, uniform_p, uniform_v, sim_counter, err_flag);
     else
         ya_k_mcts_expand<false><<<warp_blocks(tree->n), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
-            *tree, pi, value, 0.0f, 0.0f, err_flag);
+            *tree, pi, value, 0.0f, 0.0f, sim_counter, err_flag);
     return (int)cudaGetLastError();
 }
 

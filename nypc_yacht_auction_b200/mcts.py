@@ -36,9 +36,9 @@ class TreePool:
         assert self.max_nodes < 65535
         self.ht_size = _next_pow2(2 * self.max_nodes)
         if arena_mb_per_game is None:
-            # worst case: every node of a round owns a full 3024-entry prior row + an edge chunk
-            arena_mb_per_game = min(4.0 * num_sims * (3024 + 114) * 4 / 2 ** 20, 64.0)
-            arena_mb_per_game = max(arena_mb_per_game, 0.25)
+            # measured peak (random-init net, 100 sims): 33 KB per simulation of the longest-lived tree
+            # (rounds 1+2); 40 KB/sim leaves ~20 % head-room, overflow is detected and raised.
+            arena_mb_per_game = max(num_sims * 40.0 / 1024.0, 0.25)
         words = int(arena_mb_per_game * 2 ** 20) // 4
         self.arena_words = words - (words % 2)
         d = self.device
@@ -73,16 +73,24 @@ class UniformEvaluator:
 
 class TorchEvaluator:
     """One batched forward of a policy/value net for all leaves (the only dense contraction).
-    predict semantics of yacht/NNet.py:177-195: pi = exp(log_softmax(logits)) over all 3226 actions."""
+    predict semantics of yacht/NNet.py:177-195: pi = exp(log_softmax(logits)) over all 3226 actions.
+
+    dtype=torch.bfloat16 runs the whole forward in bf16 from a bf16 copy of the weights (no autocast
+    cast kernels per call; LayerNorm still accumulates in fp32 inside the kernel); dtype=None keeps the
+    module's own precision (fp32) -- what the CPU reference computes."""
     uniform = False
 
-    def __init__(self, net, autocast_dtype=None):
-        self.net = net.eval()
+    def __init__(self, net, dtype=None, autocast_dtype=None):
+        import copy
+        self.dtype = dtype
         self.autocast_dtype = autocast_dtype
+        self.net = (copy.deepcopy(net).to(dtype) if dtype is not None else net).eval()
 
     @torch.no_grad()
     def __call__(self, features, need_eval=None, leaf_states=None):
-        if self.autocast_dtype is not None:
+        if self.dtype is not None:
+            logits, v = self.net(features.to(self.dtype))
+        elif self.autocast_dtype is not None:
             with torch.autocast("cuda", dtype=self.autocast_dtype):
                 logits, v = self.net(features)
         else:
@@ -113,6 +121,29 @@ class BatchedMCTS:
         self.visits = torch.zeros(n, dtype=torch.int32, device=d)
         self.err_flag = torch.zeros(1, dtype=torch.int32, device=d)
         self.picked = torch.zeros(n, dtype=torch.int32, device=d)
+        self.sim_counter = torch.zeros(1, dtype=torch.int32, device=d)
+        self.sims_run = 0
+        self.graph = None
+
+    def capture_graph(self):
+        """Capture ONE simulation wave (select, evaluator forward, expand) as a CUDA graph; the
+        simulation index is a device counter the expand kernel bumps, so the same graph is replayed
+        numMCTSSims times per move without any host-side launch work in between."""
+        side = torch.cuda.Stream(device=self.env.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):                 # warm-up outside capture (lazy inits of the evaluator)
+            snap = [t.clone() for t in (self.pool.nodes, self.pool.ht, self.pool.meta, self.pool.cursor)]
+            for _ in range(2):
+                self.simulate(None)
+            for t, s0 in zip((self.pool.nodes, self.pool.ht, self.pool.meta, self.pool.cursor), snap):
+                t.copy_(s0)
+            self.sim_counter.zero_()
+            self.err_flag.zero_()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize(self.env.device)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.simulate(None)
         self.sims_run = 0
 
     # ------------------------------------------------------------------ one simulation wave
@@ -120,22 +151,30 @@ class BatchedMCTS:
         env, s = self.env, _lib.current_stream()
         _lib.check(self.lib.ya_mcts_select(
             self.pool.ref, _lib.ptr(env.states), env.n, _lib.ptr(env.players), _lib.ptr(env.ply), _lib.ptr(env.episode),
-            env.seed, env.game_base, sim, self.cpuct, None, _lib.ptr(self.features), _lib.ptr(self.need_eval),
+            env.seed, env.game_base, 0 if sim is None else sim, _lib.ptr(self.sim_counter) if sim is None else None,
+            self.cpuct, None, _lib.ptr(self.features), _lib.ptr(self.need_eval),
             _lib.ptr(self.leaf_states), _lib.ptr(self.err_flag), s), "ya_mcts_select")
+        counter = _lib.ptr(self.sim_counter) if sim is None else None
         ev = self.evaluator
         if getattr(ev, "uniform", False):
-            _lib.check(self.lib.ya_mcts_expand(self.pool.ref, None, None, 1, ev.p, ev.v, _lib.ptr(self.err_flag), s),
+            _lib.check(self.lib.ya_mcts_expand(self.pool.ref, None, None, 1, ev.p, ev.v, counter, _lib.ptr(self.err_flag), s),
                        "ya_mcts_expand")
         else:
             pi, v = ev(self.features, self.need_eval, self.leaf_states)
             assert pi.dtype == torch.float32 and pi.is_contiguous() and pi.shape == (env.n, ACTION_SIZE)
             assert v.dtype == torch.float32 and v.is_contiguous() and v.shape == (env.n,)
-            _lib.check(self.lib.ya_mcts_expand(self.pool.ref, _lib.ptr(pi), _lib.ptr(v), 0, 0.0, 0.0,
+            _lib.check(self.lib.ya_mcts_expand(self.pool.ref, _lib.ptr(pi), _lib.ptr(v), 0, 0.0, 0.0, counter,
                                                _lib.ptr(self.err_flag), s), "ya_mcts_expand")
         self.sims_run += env.n
 
     def search(self):
         """getActionProb's simulation loop (MCTS.py:37-38) for every game."""
+        if self.graph is not None:
+            self.sim_counter.zero_()
+            for _ in range(self.num_sims):
+                self.graph.replay()
+            self.sims_run += self.env.n * self.num_sims
+            return
         for sim in range(self.num_sims):
             self.simulate(sim)
 
@@ -234,7 +273,7 @@ class MCTS:
         s = _lib.current_stream()
         _lib.check(self.lib.ya_mcts_select(
             self.pool.ref, _lib.ptr(self.states), 1, _lib.ptr(self.players), _lib.ptr(self.ply), None,
-            self.seed, self.tree_id, self.sim_index, float(self.args.cpuct), None, _lib.ptr(self.features),
+            self.seed, self.tree_id, self.sim_index, None, float(self.args.cpuct), None, _lib.ptr(self.features),
             _lib.ptr(self.need_eval), _lib.ptr(self.leaf_states), _lib.ptr(self.err_flag), s), "ya_mcts_select")
         self.sim_index += 1
         if int(self.need_eval.item()):
@@ -243,7 +282,7 @@ class MCTS:
             pi = np.ascontiguousarray(np.asarray(pi, dtype=np.float32).reshape(ACTION_SIZE))
             self.pi_dev.copy_(torch.from_numpy(pi).unsqueeze(0))
             self.v_dev.fill_(float(np.float32(v)))
-            _lib.check(self.lib.ya_mcts_expand(self.pool.ref, _lib.ptr(self.pi_dev), _lib.ptr(self.v_dev), 0, 0.0, 0.0,
+            _lib.check(self.lib.ya_mcts_expand(self.pool.ref, _lib.ptr(self.pi_dev), _lib.ptr(self.v_dev), 0, 0.0, 0.0, None,
                                                _lib.ptr(self.err_flag), s), "ya_mcts_expand")
 
     def getActionProb(self, canonicalBoard, temp=1):
