@@ -134,6 +134,13 @@ int ya_mcts_select(const ya_mcts_tree* tree, const uint32_t* states, int64_t str
 int ya_mcts_expand(const ya_mcts_tree* tree, const float* pi, const float* value, int uniform, float uniform_p,
                    float uniform_v, uint32_t* sim_counter, int32_t* err_flag, void* stream);
 
+/* Same as ya_mcts_expand, fed with the raw policy-head output: bf16 logits [n][ld] (ld >= 3226, e.g. the
+ * head padded to 3232 columns for an aligned GEMM).  pi = exp(l - max) / sum(exp(l - max)) in float32
+ * (the softmax of NNetWrapper.predict, yacht/NNet.py:193), masking and renormalisation are fused in
+ * the kernel, so neither float32 logits nor pi are ever written to HBM. */
+int ya_mcts_expand_logits(const ya_mcts_tree* tree, const void* logits_bf16, int64_t ld, const float* value,
+                          uint32_t* sim_counter, int32_t* err_flag, void* stream);
+
 /* counts[g][a] = Nsa[(root, a)] (MCTS.py:40-42), visits[g] = Ns[root] (-1 if the root is unknown);
  * optional qvals (float64) / qkind (1 = numpy float32, 2 = Python float) expose Qsa for tests. */
 int ya_mcts_root_counts(const ya_mcts_tree* tree, const uint32_t* states, int64_t stride, const int8_t* players,
@@ -144,6 +151,14 @@ int ya_mcts_root_counts(const ya_mcts_tree* tree, const uint32_t* states, int64_
  * randomness = Philox word of tag ACTION. */
 int ya_mcts_pick_action(const int32_t* counts, const int32_t* ply, const uint32_t* episode, int64_t n, uint64_t seed,
                         uint64_t game_base, int temp_threshold, int32_t* actions, void* stream);
+
+/* ---- leaf-evaluator epilogues (YachtNNet.forward, yacht/pytorch/YachtNNet.py:17-21,62-70) ----
+ * Everything between two GEMMs of the yacht NNet in one pass over bf16 [n][256] rows:
+ * mode 0: out = SiLU(LN(x)); 1: out = LN(SiLU(x)); 2: out = residual + LN(SiLU(x));
+ * 3: out = SiLU(LN(x; gamma, beta)), out2 = SiLU(LN(x; gamma2, beta2)) (both heads).  hidden must be 256. */
+int ya_nn_ln_act(int mode, const void* x, const void* gamma, const void* beta, const void* residual,
+                 const void* gamma2, const void* beta2, void* out, void* out2, int64_t n, int64_t hidden,
+                 float eps, void* stream);
 
 /* ---- host-buffer variants (end-to-end path for callers that keep boards in host memory) ----
  * ya_host_create allocates the device mirror for n games once (no allocation per call);

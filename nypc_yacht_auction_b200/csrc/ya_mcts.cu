@@ -15,6 +15,7 @@
 #include "ya_common.cuh"
 #include "../../include/yacht_b200.h"
 #include <math_constants.h>
+#include <cuda_bf16.h>
 
 namespace {
 
@@ -334,9 +335,10 @@ __device__ __forceinline__ bool desc_valid(uint32_t desc, int i) {
 // sum of x[i] = valid(i) ? pi[i] : 0 over i < 3226 in numpy's float32 pairwise order
 // (numpy/_core/src/umath/loops_utils.h.src: blocks of <= 128 with 8 accumulators, halves rounded
 // down to a multiple of 8).  For n = 3226 that is a perfect binary tree over 32 blocks of 96 / 104 /
-// 106 elements: 8 lanes run a block's accumulators, four blocks per pass.
-template <bool UNIFORM>
-__device__ __forceinline__ float masked_pairwise_sum(const float* __restrict__ pi, float uniform_p, uint32_t desc, int lane) {
+// 106 elements: 8 lanes run a block's accumulators, four blocks per pass.  `load(i)` returns pi[i]
+// for a legal action i.
+template <class Load>
+__device__ __forceinline__ float masked_pairwise_sum(Load load, uint32_t desc, int lane) {
     const int sub = lane & 7, grp = lane >> 3;
     float my_leaf = 0.0f;
 #pragma unroll 1
@@ -351,10 +353,10 @@ __device__ __forceinline__ float masked_pairwise_sum(const float* __restrict__ p
         }
         int body = n - (n % 8);
         int i = start + sub;
-        float r = desc_valid(desc, i) ? (UNIFORM ? uniform_p : pi[i]) : 0.0f;
+        float r = desc_valid(desc, i) ? load(i) : 0.0f;
         for (int t = 8; t < body; t += 8) {
             int k = start + t + sub;
-            float x = desc_valid(desc, k) ? (UNIFORM ? uniform_p : pi[k]) : 0.0f;
+            float x = desc_valid(desc, k) ? load(k) : 0.0f;
             r = __fadd_rn(r, x);
         }
         // ((r0+r1)+(r2+r3)) + ((r4+r5)+(r6+r7))
@@ -362,12 +364,11 @@ __device__ __forceinline__ float masked_pairwise_sum(const float* __restrict__ p
         r = __fadd_rn(r, __shfl_xor_sync(0xFFFFFFFFu, r, 2));
         r = __fadd_rn(r, __shfl_xor_sync(0xFFFFFFFFu, r, 4));
         for (int k = start + body; k < start + n; ++k) {              // the n % 8 leftovers, in order
-            float x = desc_valid(desc, k) ? (UNIFORM ? uniform_p : pi[k]) : 0.0f;
+            float x = desc_valid(desc, k) ? load(k) : 0.0f;
             r = __fadd_rn(r, x);
         }
-        float leaf_sum = __shfl_sync(0xFFFFFFFFu, r, (lane & 24));   // sub-lane 0 of my group
         // lane `leaf` keeps block `leaf`
-        float from = __shfl_sync(0xFFFFFFFFu, leaf_sum, ((lane & 3) << 3));
+        float from = __shfl_sync(0xFFFFFFFFu, r, ((lane & 3) << 3));
         if ((lane >> 2) == pass) my_leaf = from;
     }
     // perfect binary tree over the 32 block sums
@@ -376,10 +377,14 @@ __device__ __forceinline__ float masked_pairwise_sum(const float* __restrict__ p
     return my_leaf;
 }
 
-template <bool UNIFORM>
+// MODE 0: pi float32[n][3226] from the evaluator; MODE 1: uniform prior, nothing read;
+// MODE 2: bf16 logits [n][ld] straight from the policy-head GEMM: softmax (float32: exp(l - max) / sum),
+//         mask and renormalisation fused here, so neither the float32 logits nor pi ever touch HBM.
+template <int MODE>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
-ya_k_mcts_expand(ya_mcts_tree tree, const float* __restrict__ pi_all, const float* __restrict__ value,
-                 float uniform_p, float uniform_v, uint32_t* __restrict__ sim_counter, int32_t* __restrict__ err_flag) {
+ya_k_mcts_expand(ya_mcts_tree tree, const float* __restrict__ pi_all, const __nv_bfloat16* __restrict__ logits_all,
+                 int64_t ld, const float* __restrict__ value, float uniform_p, float uniform_v,
+                 uint32_t* __restrict__ sim_counter, int32_t* __restrict__ err_flag) {
     const int lane = threadIdx.x & 31;
     const int64_t g = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     if (sim_counter && blockIdx.x == 0 && threadIdx.x == 0) *sim_counter += 1;   // next replay = next simulation
@@ -389,23 +394,50 @@ ya_k_mcts_expand(ya_mcts_tree tree, const float* __restrict__ pi_all, const floa
     uint32_t* node = v.nodes + (int64_t)v.cur[C_NODE] * kNodeWords;
     const uint32_t desc = node[N_DESC];
     const int L = ya_legal_count(desc);
-    const float* pi = UNIFORM ? nullptr : pi_all + g * YA_N_ACTION;
     if (L > 0) {
-        float total = masked_pairwise_sum<UNIFORM>(pi, uniform_p, desc, lane);
         float* row = reinterpret_cast<float*>(v.arena + node[N_PRIOR]);
-        if (total > 0.0f) {                                          // Ps /= sum, MCTS.py:90-91
-            for (int k = lane; k < L; k += 32) {
-                float p = UNIFORM ? uniform_p : pi[ya_nth_legal(desc, k)];
-                row[k] = __fdiv_rn(p, total);
+        float total;
+        if (MODE == 0) {
+            const float* pi = pi_all + g * YA_N_ACTION;
+            total = masked_pairwise_sum([pi](int i) { return pi[i]; }, desc, lane);
+            if (total > 0.0f)                                        // Ps /= sum, MCTS.py:90-91
+                for (int k = lane; k < L; k += 32) row[k] = __fdiv_rn(pi[ya_nth_legal(desc, k)], total);
+        } else if (MODE == 1) {
+            total = masked_pairwise_sum([uniform_p](int) { return uniform_p; }, desc, lane);
+            if (total > 0.0f) {
+                float p = __fdiv_rn(uniform_p, total);
+                for (int k = lane; k < L; k += 32) row[k] = p;
             }
-        } else {                                                     // all legal moves masked: uniform over legal, :97-101
+        } else {
+            const __nv_bfloat16* lg = logits_all + g * ld;
+            float mx = -CUDART_INF_F;
+            for (int i = lane; i < YA_N_ACTION; i += 32) mx = fmaxf(mx, __bfloat162float(lg[i]));
+#pragma unroll
+            for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, o));
+            float den = 0.0f;
+            for (int i = lane; i < YA_N_ACTION; i += 32) {
+                float e = expf(__bfloat162float(lg[i]) - mx);
+                den += e;
+                if (desc_valid(desc, i)) row[ya_legal_index(desc, i)] = e;     // park exp(l - max) of the legal actions
+            }
+#pragma unroll
+            for (int o = 16; o; o >>= 1) den += __shfl_xor_sync(0xFFFFFFFFu, den, o);
+            __syncwarp();
+            const float* rowc = row;
+            total = masked_pairwise_sum([rowc, den, desc](int i) { return __fdiv_rn(rowc[ya_legal_index(desc, i)], den); },
+                                        desc, lane);
+            __syncwarp();
+            if (total > 0.0f)
+                for (int k = lane; k < L; k += 32) row[k] = __fdiv_rn(__fdiv_rn(row[k], den), total);
+        }
+        if (!(total > 0.0f)) {                                       // all legal moves masked: uniform over legal, :97-101
             float u = __fdiv_rn(1.0f, (float)L);
             for (int k = lane; k < L; k += 32) row[k] = u;
         }
     }
     __syncwarp();
     Val ret;
-    ret.d = -(double)(UNIFORM ? uniform_v : value[g]);               // return -v (numpy float32)
+    ret.d = -(double)(MODE == 1 ? uniform_v : value[g]);             // return -v (numpy float32)
     ret.is_f32 = true;
     uint32_t arena_top = v.meta[M_TOP];
     bool ok = backup_path(v, (int)v.cur[C_DEPTH], ret, arena_top, lane);
@@ -555,11 +587,19 @@ int ya_mcts_expand(const ya_mcts_tree* tree, const float* pi, const float* value
                    float uniform_v, uint32_t* sim_counter, int32_t* err_flag, void* stream) {
     if (!tree_ok(tree)) return (int)cudaErrorInvalidValue;
     if (uniform)
-        ya_k_mcts_expand<true><<<warp_blocks(tree->n), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
-            *tree, nullptr, nullptr, uniform_p, uniform_v, sim_counter, err_flag);
+        ya_k_mcts_expand<1><<<warp_blocks(tree->n), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
+            *tree, nullptr, nullptr, 0, nullptr, uniform_p, uniform_v, sim_counter, err_flag);
     else
-        ya_k_mcts_expand<false><<<warp_blocks(tree->n), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
-            *tree, pi, value, 0.0f, 0.0f, sim_counter, err_flag);
+        ya_k_mcts_expand<0><<<warp_blocks(tree->n), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
+            *tree, pi, nullptr, 0, value, 0.0f, 0.0f, sim_counter, err_flag);
+    return (int)cudaGetLastError();
+}
+
+int ya_mcts_expand_logits(const ya_mcts_tree* tree, const void* logits_bf16, int64_t ld, const float* value,
+                          uint32_t* sim_counter, int32_t* err_flag, void* stream) {
+    if (!tree_ok(tree) || ld < YA_N_ACTION) return (int)cudaErrorInvalidValue;
+    ya_k_mcts_expand<2><<<warp_blocks(tree->n), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
+        *tree, nullptr, static_cast<const __nv_bfloat16*>(logits_bf16), ld, value, 0.0f, 0.0f, sim_counter, err_flag);
     return (int)cudaGetLastError();
 }
 

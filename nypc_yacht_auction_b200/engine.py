@@ -168,3 +168,19 @@ class BatchedYacht:
             _lib.ptr(self.actions), _lib.ptr(self.outcome), _lib.ptr(masks), _lib.ptr(self.err_flag),
             self.n, self.seed, self.game_base, 1 if auto_reset else 0, self._s()), "ya_play_ply")
         return self.actions, self.outcome
+
+    # ------------------------------------------------------------------ CUDA-graph replay of a full game
+    def capture_game_graph(self, masks=None, plies=48, auto_reset=True):
+        """Capture `plies` fused plies (one full game for every slot) as ONE CUDA graph: the launch-bound
+        inner loop is replayed with a single host call (no per-launch gaps)."""
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            self.play_ply(masks=masks, auto_reset=auto_reset)        # warm-up launch outside capture
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            for _ in range(plies):
+                self.play_ply(masks=masks, auto_reset=auto_reset)
+        return graph

@@ -73,18 +73,33 @@ class UniformEvaluator:
 
 class TorchEvaluator:
     """One batched forward of a policy/value net for all leaves (the only dense contraction).
-    predict semantics of yacht/NNet.py:177-195: pi = exp(log_softmax(logits)) over all 3226 actions.
+    predict semantics of yacht/NNet.py:177-195: pi = softmax(logits) over all 3226 actions.
 
     dtype=torch.bfloat16 runs the whole forward in bf16 from a bf16 copy of the weights (no autocast
-    cast kernels per call; LayerNorm still accumulates in fp32 inside the kernel); dtype=None keeps the
-    module's own precision (fp32) -- what the CPU reference computes."""
+    cast kernels per call; LayerNorm still accumulates in fp32 inside its kernel); dtype=None keeps the
+    module's own precision (fp32, what the CPU reference computes).
+    fused_logits=True (bf16 only) pads the policy head to 3232 outputs (16-byte aligned rows -> the fast
+    GEMM path) and hands the raw bf16 logits to ya_mcts_expand_logits, which fuses softmax, masking and
+    renormalisation: neither float32 logits nor pi are written to HBM."""
     uniform = False
+    PADDED = 3232
 
-    def __init__(self, net, dtype=None, autocast_dtype=None):
+    def __init__(self, net, dtype=None, autocast_dtype=None, fused_logits=False):
         import copy
         self.dtype = dtype
         self.autocast_dtype = autocast_dtype
+        self.returns_logits = bool(fused_logits)
         self.net = (copy.deepcopy(net).to(dtype) if dtype is not None else net).eval()
+        if self.returns_logits:
+            assert dtype == torch.bfloat16, "fused logits need the bf16 forward"
+            head = self.net.pi_head[2]
+            padded = torch.nn.Linear(head.in_features, self.PADDED, device=head.weight.device, dtype=head.weight.dtype)
+            with torch.no_grad():
+                padded.weight.zero_()
+                padded.bias.zero_()
+                padded.weight[:head.out_features].copy_(head.weight)
+                padded.bias[:head.out_features].copy_(head.bias)
+            self.net.pi_head[2] = padded
 
     @torch.no_grad()
     def __call__(self, features, need_eval=None, leaf_states=None):
@@ -95,8 +110,79 @@ class TorchEvaluator:
                 logits, v = self.net(features)
         else:
             logits, v = self.net(features)
-        pi = torch.softmax(logits.float(), dim=1)
-        return pi.contiguous(), v.float().reshape(-1).contiguous()
+        v = v.float().reshape(-1).contiguous()
+        if self.returns_logits:
+            return logits.contiguous(), v
+        return torch.softmax(logits.float(), dim=1).contiguous(), v
+
+
+class FusedYachtEvaluator:
+    """The yacht NNet forward for a whole wave of leaves: bf16 GEMMs through PyTorch (cuBLASLt) with every
+    SiLU / LayerNorm / residual between them fused into one hand-written pass (csrc/ya_nn.cu), the policy
+    head padded to 3232 aligned columns, and its raw bf16 logits consumed by ya_mcts_expand_logits.
+    Weights come from any module with YachtNNet's state dict (yacht/pytorch/YachtNNet.py:25-52)."""
+    uniform = False
+    returns_logits = True
+    PADDED = 3232
+
+    def __init__(self, net, max_batch):
+        sd = {k: v.detach() for k, v in net.state_dict().items()}
+        dev = next(net.parameters()).device
+        bf = lambda t: t.to(device=dev, dtype=torch.bfloat16).contiguous()
+        self.hidden = sd["inp.0.weight"].shape[0]
+        if self.hidden != 256:
+            raise ValueError("FusedYachtEvaluator handles hidden=256 (main.py:40); use TorchEvaluator otherwise")
+        self.nblocks = len({k.split(".")[1] for k in sd if k.startswith("blocks.")})
+        self.w_in, self.b_in = bf(sd["inp.0.weight"]).t().contiguous(), bf(sd["inp.0.bias"])
+        self.ln_in = (bf(sd["inp.1.weight"]), bf(sd["inp.1.bias"]))
+        self.blocks = []
+        for i in range(self.nblocks):
+            p = "blocks.%d." % i
+            self.blocks.append((bf(sd[p + "fc1.weight"]).t().contiguous(), bf(sd[p + "fc1.bias"]),
+                                bf(sd[p + "ln1.weight"]), bf(sd[p + "ln1.bias"]),
+                                bf(sd[p + "fc2.weight"]).t().contiguous(), bf(sd[p + "fc2.bias"]),
+                                bf(sd[p + "ln2.weight"]), bf(sd[p + "ln2.bias"])))
+        self.ln_pi = (bf(sd["pi_head.0.weight"]), bf(sd["pi_head.0.bias"]))
+        self.ln_v = (bf(sd["v_head.0.weight"]), bf(sd["v_head.0.bias"]))
+        a = sd["pi_head.2.weight"].shape[0]
+        w = torch.zeros((self.PADDED, self.hidden), dtype=torch.bfloat16, device=dev)
+        b = torch.zeros(self.PADDED, dtype=torch.bfloat16, device=dev)
+        w[:a].copy_(sd["pi_head.2.weight"])
+        b[:a].copy_(sd["pi_head.2.bias"])
+        self.w_pi, self.b_pi = w.t().contiguous(), b
+        self.w_v1, self.b_v1 = bf(sd["v_head.2.weight"]).t().contiguous(), bf(sd["v_head.2.bias"])
+        self.w_v2, self.b_v2 = bf(sd["v_head.4.weight"]).t().contiguous(), bf(sd["v_head.4.bias"])
+        n, h = int(max_batch), self.hidden
+        mk = lambda *shape: torch.empty(shape, dtype=torch.bfloat16, device=dev)
+        self.z, self.h, self.a, self.p, self.q = mk(n, h), mk(n, h), mk(n, h), mk(n, h), mk(n, h)
+        self.logits = mk(n, self.PADDED)
+        self.lib = _lib.load()
+        self.eps = 1e-5
+
+    def _ln(self, mode, x, ln, out, residual=None, ln2=None, out2=None):
+        _lib.check(self.lib.ya_nn_ln_act(mode, _lib.ptr(x), _lib.ptr(ln[0]), _lib.ptr(ln[1]), _lib.ptr(residual),
+                                         _lib.ptr(ln2[0]) if ln2 else None, _lib.ptr(ln2[1]) if ln2 else None,
+                                         _lib.ptr(out), _lib.ptr(out2), x.shape[0], self.hidden, self.eps,
+                                         _lib.current_stream()), "ya_nn_ln_act")
+
+    @torch.no_grad()
+    def __call__(self, features, need_eval=None, leaf_states=None):
+        n = features.shape[0]
+        z, h, a, p, q = self.z[:n], self.h[:n], self.a[:n], self.p[:n], self.q[:n]
+        x = features.to(torch.bfloat16)
+        torch.addmm(self.b_in, x, self.w_in, out=z)
+        self._ln(0, z, self.ln_in, h)                                     # inp: Linear -> LN -> SiLU
+        for (w1, b1, g1, be1, w2, b2, g2, be2) in self.blocks:
+            torch.addmm(b1, h, w1, out=z)
+            self._ln(1, z, (g1, be1), a)                                  # ln1(silu(fc1(x)))
+            torch.addmm(b2, a, w2, out=z)
+            self._ln(2, z, (g2, be2), h, residual=h)                      # x + ln2(silu(fc2(h)))  (in place: row-local)
+        self._ln(3, h, self.ln_pi, p, ln2=self.ln_v, out2=q)              # both heads' LN -> SiLU
+        logits = self.logits[:n]
+        torch.addmm(self.b_pi, p, self.w_pi, out=logits)
+        t = torch.nn.functional.silu(torch.addmm(self.b_v1, q, self.w_v1))
+        v = torch.tanh(torch.addmm(self.b_v2, t, self.w_v2))
+        return logits, v.float().reshape(-1).contiguous()
 
 
 class BatchedMCTS:
@@ -161,8 +247,14 @@ class BatchedMCTS:
                        "ya_mcts_expand")
         else:
             pi, v = ev(self.features, self.need_eval, self.leaf_states)
-            assert pi.dtype == torch.float32 and pi.is_contiguous() and pi.shape == (env.n, ACTION_SIZE)
             assert v.dtype == torch.float32 and v.is_contiguous() and v.shape == (env.n,)
+            if getattr(ev, "returns_logits", False):
+                assert pi.dtype == torch.bfloat16 and pi.is_contiguous() and pi.shape[0] == env.n
+                _lib.check(self.lib.ya_mcts_expand_logits(self.pool.ref, _lib.ptr(pi), pi.shape[1], _lib.ptr(v), counter,
+                                                          _lib.ptr(self.err_flag), s), "ya_mcts_expand_logits")
+                self.sims_run += env.n
+                return
+            assert pi.dtype == torch.float32 and pi.is_contiguous() and pi.shape == (env.n, ACTION_SIZE)
             _lib.check(self.lib.ya_mcts_expand(self.pool.ref, _lib.ptr(pi), _lib.ptr(v), 0, 0.0, 0.0, counter,
                                                _lib.ptr(self.err_flag), s), "ya_mcts_expand")
         self.sims_run += env.n

@@ -43,7 +43,7 @@ def _run_selfplay(torch, dev, n, sims, evaluator, plies, warm_plies, seed, game_
 
 
 def run(args, torch, dev, rank=0, world=1, dist=None):
-    from .mcts import UniformEvaluator, TorchEvaluator
+    from .mcts import UniformEvaluator, FusedYachtEvaluator
     from .nnet import YachtPolicyValueNet
     out = {}
     # configs[2]: MCTS self-play, numMCTSSims=25, uniform prior (no NN), 4,096 concurrent games
@@ -56,12 +56,12 @@ def run(args, torch, dev, rank=0, world=1, dist=None):
     # configs[3]: AlphaZero self-play, random-init yacht NNet (H=256, 6 blocks), numMCTSSims=100, 16,384 games
     torch.manual_seed(0)
     net = YachtPolicyValueNet().to(dev)
-    ev = TorchEvaluator(net, dtype=torch.bfloat16)
+    ev = FusedYachtEvaluator(net, 16384)
     r = _run_selfplay(torch, dev, 16384, 100, ev, plies=4, warm_plies=4, seed=args.seed + 2, game_base=rank * 16384,
                       use_graph=True, dist=dist, world=world)
     out["mcts_nn"] = {
-        "workload": "configs[3]: AlphaZero self-play, random-init YachtNNet (hidden 256, 6 blocks, bf16 weights and activations), "
-                    "numMCTSSims=100, 16384 games/GPU, one batched forward per simulation wave, plies 4..7",
+        "workload": "configs[3]: AlphaZero self-play, random-init YachtNNet (hidden 256, 6 blocks; bf16 cuBLASLt GEMMs via torch, SiLU/LayerNorm/residual fused in csrc/ya_nn.cu), "
+                    "numMCTSSims=100, 16384 games/GPU, one batched forward per simulation wave, softmax+mask fused into the expand kernel, plies 4..7",
         "sims_per_sec": r["sims_per_sec"], "game_steps_per_sec": r["steps_per_sec"], "ms": r["ms"], "gpu_launches": r["launches"],
         "pool_gb": r["pool_gb"], "max_nodes_in_use": r["max_nodes_in_use"],
         "nn_flops_per_leaf": 2 * YachtPolicyValueNet.num_macs()}

@@ -9,7 +9,7 @@ dev = torch.device('cuda', 0)
 n = int(sys.argv[1]); sims = int(sys.argv[2]); uniform = len(sys.argv) > 3
 torch.manual_seed(0)
 net = YachtPolicyValueNet().to(dev)
-ev = UniformEvaluator() if uniform else TorchEvaluator(net, autocast_dtype=torch.bfloat16)
+ev = UniformEvaluator() if uniform else TorchEvaluator(net, dtype=torch.bfloat16, fused_logits=True)
 sp = BatchedSelfPlay(n, sims, evaluator=ev, seed=2, device=dev, record_examples=False)
 m = sp.mcts; env = sp.env; lib = m.lib
 def ev_pair():
@@ -29,7 +29,7 @@ for t in range(12):
         if uniform:
             _lib.check(lib.ya_mcts_expand(m.pool.ref, None, None, 1, ev.p, ev.v, None, _lib.ptr(m.err_flag), s), "exp")
         else:
-            _lib.check(lib.ya_mcts_expand(m.pool.ref, _lib.ptr(pi), _lib.ptr(v), 0, 0.0, 0.0, None, _lib.ptr(m.err_flag), s), "exp")
+            _lib.check(lib.ya_mcts_expand_logits(m.pool.ref, _lib.ptr(pi), pi.shape[1], _lib.ptr(v), None, _lib.ptr(m.err_flag), s), "exp")
         c1.record()
         torch.cuda.synchronize()
         acc["select"] += a0.elapsed_time(a1); acc["eval"] += b0.elapsed_time(b1); acc["expand"] += c0.elapsed_time(c1)

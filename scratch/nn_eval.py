@@ -1,12 +1,12 @@
 import sys
 sys.path.insert(0, '/root/repo')
 import torch
-from nypc_yacht_auction_b200.mcts import TorchEvaluator
+from nypc_yacht_auction_b200.mcts import TorchEvaluator, FusedYachtEvaluator
 from nypc_yacht_auction_b200.nnet import YachtPolicyValueNet
 dev = torch.device('cuda', 0)
 torch.manual_seed(0)
 net = YachtPolicyValueNet().to(dev)
-ev = TorchEvaluator(net, dtype=torch.bfloat16)
+ev = FusedYachtEvaluator(net, 16384)
 x = torch.randn(16384, 59, device=dev)
 for _ in range(3):
     pi, v = ev(x)
@@ -16,4 +16,4 @@ with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     for _ in range(5):
         pi, v = ev(x)
     torch.cuda.synchronize()
-print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=25, max_name_column_width=70))
+print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=16, max_name_column_width=70))

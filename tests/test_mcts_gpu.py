@@ -179,3 +179,111 @@ def test_pool_overflow_is_reported():
     mcts.search()
     with pytest.raises(YachtB200Error):
         mcts.check_errors()
+
+
+def test_fused_logits_expand_matches_softmax_mask_renorm():
+    """ya_mcts_expand_logits: prior rows written from raw bf16 logits equal softmax -> mask -> renormalise
+    (MCTS.py:86-91) computed in numpy, to float32 rounding (tolerance 2e-6 relative: exp differs by ulps)."""
+    from nypc_yacht_auction_b200.mcts import BatchedMCTS
+
+    class LogitEval:
+        uniform = False
+        returns_logits = True
+
+        def __init__(self, n):
+            g = torch.Generator().manual_seed(5)
+            self.logits = (torch.randn((n, 3232), generator=g) * 3).to(torch.bfloat16).cuda()
+            self.v = torch.linspace(-0.9, 0.9, n).cuda()
+
+        def __call__(self, features, need_eval, leaf_states):
+            return self.logits, self.v
+
+    n = 9
+    env = _engine(n, 3, 40)
+    for ply in range(5):                                   # reach a score ply for the first movers
+        env.play_ply(masks=None, auto_reset=False)
+    ev = LogitEval(n)
+    mcts = BatchedMCTS(env, 4, 1.5, evaluator=ev)
+    mcts.simulate(0)                                       # expands every root (node 0 of every tree)
+    mcts.check_errors()
+    masks = env.valid_moves(states=env.canonical(), players=torch.ones(n, dtype=torch.int8, device="cuda")).cpu().numpy()
+    arena = mcts.pool.arena.cpu().numpy().view(np.float32)
+    nodes = mcts.pool.nodes.cpu().numpy()
+    lg = ev.logits.float().cpu().numpy()[:, :3226]
+    for g in range(n):
+        legal = np.flatnonzero(masks[g])
+        off = int(nodes[g, 0, 10])
+        row = arena[g, off:off + len(legal)]
+        e = np.exp((lg[g] - lg[g].max()).astype(np.float32)).astype(np.float32)
+        pi = e / e.sum(dtype=np.float32)
+        p = pi * masks[g]
+        p = p / np.sum(p)
+        assert np.allclose(row, p[legal], rtol=2e-6, atol=1e-12), g
+        assert abs(float(row.sum()) - 1.0) < 1e-5
+
+
+def test_fused_evaluator_matches_module_forward():
+    """FusedYachtEvaluator (bf16 GEMMs + fused SiLU/LayerNorm/residual epilogues) against the fp32 module
+    forward.  bf16 (ulp 2^-8) through 13 layers is the error floor, so the yardstick is PyTorch's own bf16
+    forward of the same module: the fused path must be at least as close to fp32 (stated tolerance:
+    1.25x torch-bf16's max error + 0.01), and the policy within 2 % total variation."""
+    from nypc_yacht_auction_b200.mcts import FusedYachtEvaluator, TorchEvaluator
+    from nypc_yacht_auction_b200.nnet import YachtPolicyValueNet
+    torch.manual_seed(0)
+    net = YachtPolicyValueNet().cuda().eval()
+    with torch.no_grad():
+        for p in net.parameters():                     # non-trivial LayerNorm affine parameters and biases
+            if p.ndim == 1:
+                p.add_(0.1 * torch.randn_like(p))
+    env = _engine(300, 1, 1)
+    for _ in range(7):
+        env.play_ply(masks=None, auto_reset=False)
+    x = env.features()
+    logits, v = FusedYachtEvaluator(net, max_batch=512)(x)
+    t_logits, t_v = TorchEvaluator(net, dtype=torch.bfloat16, fused_logits=True)(x)
+    with torch.no_grad():
+        ref_logits, ref_v = net(x)
+    assert logits.shape == (300, 3232) and logits.dtype == torch.bfloat16
+    err = (logits[:, :3226].float() - ref_logits).abs().max().item()
+    err_torch = (t_logits[:, :3226].float() - ref_logits).abs().max().item()
+    assert err <= 1.25 * err_torch + 0.01, (err, err_torch)
+    verr = (v - ref_v.reshape(-1)).abs().max().item()
+    verr_torch = (t_v - ref_v.reshape(-1)).abs().max().item()
+    assert verr <= 1.25 * verr_torch + 0.01, (verr, verr_torch)
+    tv = 0.5 * (torch.softmax(logits[:, :3226].float(), 1) - torch.softmax(ref_logits, 1)).abs().sum(1).max().item()
+    assert tv < 0.02, tv
+
+
+def test_ln_act_kernel_modes_vs_torch():
+    """csrc/ya_nn.cu: each fused epilogue mode against the float32 torch ops on the same bf16 inputs; the
+    only difference allowed is the final bf16 rounding (1 ulp = 2^-8 relative, + float32 noise)."""
+    import torch.nn.functional as F
+    from nypc_yacht_auction_b200 import _lib
+    lib = _lib.load()
+    torch.manual_seed(3)
+    n, h = 1000, 256
+    bf = torch.bfloat16
+    x = (torch.randn(n, h, device="cuda") * 2).to(bf)
+    res = torch.randn(n, h, device="cuda").to(bf)
+    g1, b1 = (1 + 0.2 * torch.randn(h, device="cuda")).to(bf), (0.3 * torch.randn(h, device="cuda")).to(bf)
+    g2, b2 = (1 + 0.2 * torch.randn(h, device="cuda")).to(bf), (0.3 * torch.randn(h, device="cuda")).to(bf)
+    out, out2 = torch.empty_like(x), torch.empty_like(x)
+
+    def run(mode):
+        _lib.check(lib.ya_nn_ln_act(mode, _lib.ptr(x), _lib.ptr(g1), _lib.ptr(b1), _lib.ptr(res), _lib.ptr(g2), _lib.ptr(b2),
+                                    _lib.ptr(out), _lib.ptr(out2), n, h, 1e-5, _lib.current_stream()), "ya_nn_ln_act")
+        torch.cuda.synchronize()
+
+    def ln(t, g, b):
+        return F.layer_norm(t, (h,), g.float(), b.float(), 1e-5)
+
+    xf = x.float()
+    refs = {0: F.silu(ln(xf, g1, b1)), 1: ln(F.silu(xf), g1, b1), 2: res.float() + ln(F.silu(xf), g1, b1)}
+    for mode, ref in refs.items():
+        run(mode)
+        assert torch.allclose(out.float(), ref, rtol=2 ** -7, atol=2e-3), mode
+    run(3)
+    assert torch.allclose(out.float(), F.silu(ln(xf, g1, b1)), rtol=2 ** -7, atol=2e-3)
+    assert torch.allclose(out2.float(), F.silu(ln(xf, g2, b2)), rtol=2 ** -7, atol=2e-3)
+    assert lib.ya_nn_ln_act(0, _lib.ptr(x), _lib.ptr(g1), _lib.ptr(b1), None, None, None, _lib.ptr(out), None, n, 128, 1e-5,
+                            _lib.current_stream()) != 0            # unsupported width is refused, not mis-computed
