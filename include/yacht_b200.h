@@ -134,12 +134,20 @@ int ya_mcts_select(const ya_mcts_tree* tree, const uint32_t* states, int64_t str
 int ya_mcts_expand(const ya_mcts_tree* tree, const float* pi, const float* value, int uniform, float uniform_p,
                    float uniform_v, uint32_t* sim_counter, int32_t* err_flag, void* stream);
 
-/* Same as ya_mcts_expand, fed with the raw policy-head output: bf16 logits [n][ld] (ld >= 3226, e.g. the
- * head padded to 3232 columns for an aligned GEMM).  pi = exp(l - max) / sum(exp(l - max)) in float32
+/* Same as ya_mcts_expand, fed with the raw policy-head output: bf16 logits [n][ld] (ld >= 3226 and a multiple of 8,
+ * e.g. the head padded to 3232 columns for an aligned GEMM; base 16-byte aligned).  pi = exp(l - max) / sum(exp(l - max)) in float32
  * (the softmax of NNetWrapper.predict, yacht/NNet.py:193), masking and renormalisation are fused in
  * the kernel, so neither float32 logits nor pi are ever written to HBM. */
 int ya_mcts_expand_logits(const ya_mcts_tree* tree, const void* logits_bf16, int64_t ld, const float* value,
                           uint32_t* sim_counter, int32_t* err_flag, void* stream);
+
+/* getActionProb's whole simulation loop (MCTS.py:37-38) in ONE launch for the uniform evaluator
+ * (pi = uniform_p, v = uniform_v; BASELINE.json configs[2]): num_sims x (descent, expansion, backup) per
+ * game without leaving the SM.  Same results as num_sims x (ya_mcts_select, ya_mcts_expand(uniform)). */
+int ya_mcts_search_uniform(const ya_mcts_tree* tree, const uint32_t* states, int64_t stride, const int8_t* players,
+                           const int32_t* ply, const uint32_t* episode, uint64_t seed, uint64_t game_base, int num_sims,
+                           float cpuct, float uniform_p, float uniform_v, const uint8_t* active, int32_t* err_flag,
+                           void* stream);
 
 /* counts[g][a] = Nsa[(root, a)] (MCTS.py:40-42), visits[g] = Ns[root] (-1 if the root is unknown);
  * optional qvals (float64) / qkind (1 = numpy float32, 2 = Python float) expose Qsa for tests. */

@@ -121,12 +121,30 @@ __device__ __forceinline__ int ucb_select(const View& v, const uint32_t* node, i
         off = ch[0];
         remaining -= cnt;
     }
-    // unvisited edges: u = cpuct * P * sqrt(Ns + EPS)
-    for (int i = lane; i < L; i += 32) {
-        uint32_t bits = row[i];
-        if (bits >> 31) continue;
-        float u = __fmul_rn(__fmul_rn(cpuct, __uint_as_float(bits)), sq_new);
-        if (u > best || (u == best && i < besti)) { best = u; besti = i; }
+    // unvisited edges: u = cpuct * P * sqrt(Ns + EPS).  Rows start 16-byte aligned: four priors per load.
+    {
+        const uint4* row4 = reinterpret_cast<const uint4*>(row);
+        const int nvec = L >> 2;
+#pragma unroll 4
+        for (int j = lane; j < nvec; j += 32) {
+            uint4 q = row4[j];
+            uint32_t bits[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                if (bits[t] >> 31) continue;
+                float u = __fmul_rn(__fmul_rn(cpuct, __uint_as_float(bits[t])), sq_new);
+                int i = 4 * j + t;
+                if (u > best || (u == best && i < besti)) { best = u; besti = i; }
+            }
+        }
+        int i = (nvec << 2) + lane;
+        if (i < L) {
+            uint32_t b = row[i];
+            if (!(b >> 31)) {
+                float u = __fmul_rn(__fmul_rn(cpuct, __uint_as_float(b)), sq_new);
+                if (u > best || (u == best && i < besti)) { best = u; besti = i; }
+            }
+        }
     }
 #pragma unroll
     for (int o = 16; o; o >>= 1) {
@@ -223,6 +241,83 @@ __device__ __forceinline__ bool backup_path(const View& v, int depth, Val ret, u
 }
 
 // ---------------------------------------------------------------- select (MCTS.py:56-150)
+struct Walk {
+    uint32_t node_count, arena_top;
+    int depth, kind, err, leaf_node;
+    Val ret;
+    YaState leaf;
+};
+
+// Lazy pruning at round boundaries: inside rounds >= 2 the search never leaves the root's round
+// (quirk Q3), so nothing stored for an earlier round >= 2 can be reached again.
+__device__ __forceinline__ void prune_on_new_round(const View& v, const YaState& root, Walk& w, int lane) {
+    uint32_t old_round = v.meta[M_ROUND], new_round = (uint32_t)ya_round(root);
+    if (old_round == new_round) return;
+    if (old_round >= 2 || new_round < old_round) {
+        for (int i = lane; i < v.ht_size / 2; i += 32) reinterpret_cast<uint32_t*>(v.ht)[i] = 0u;
+        w.node_count = 0;
+        w.arena_top = 4;
+    }
+    if (lane == 0) v.meta[M_ROUND] = new_round;
+    __syncwarp();
+}
+
+// One descent from the canonical root.  On return: kind == KIND_NEED_EVAL (leaf allocated, w.leaf holds its
+// state), KIND_DONE (terminal / dead end: w.ret is the value returned by the deepest call) or KIND_ERROR.
+template <bool FEATURES>
+__device__ __forceinline__ void descend(const View& v, YaState cur, Walk& w, uint64_t seed, uint32_t gid, uint32_t ep,
+                                        uint32_t pl, uint32_t sim, float cpuct, float* __restrict__ feat_row, int lane) {
+    w.depth = 0; w.kind = KIND_DONE; w.err = 0; w.leaf_node = -1;
+    w.ret.d = 0.0; w.ret.is_f32 = false;
+    for (;;) {
+        float es = ya_game_ended(cur, 1);                           // Es[s], MCTS.py:79-83
+        if (es != 0.0f) { w.ret.d = -es_as_double(es); w.ret.is_f32 = false; break; }
+        int free_slot;
+        int idx = ht_find(v, cur, &free_slot);
+        if (idx < 0) {                                               // leaf: MCTS.py:84-115 (evaluation happens outside)
+            uint32_t desc = ya_mask_desc(cur, 1);
+            int L = ya_legal_count(desc);
+            uint32_t row_at = (w.arena_top + 3u) & ~3u;             // 16-byte aligned prior rows
+            if ((int)w.node_count >= v.max_nodes) { w.err = E_NODES_FULL; w.kind = KIND_ERROR; break; }
+            if (row_at + (uint32_t)L > v.arena_words) { w.err = E_ARENA_FULL; w.kind = KIND_ERROR; break; }
+            idx = (int)w.node_count;
+            if (lane == 0) {
+                uint32_t* nd = v.nodes + (int64_t)idx * kNodeWords;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) nd[N_KEY + i] = cur.w[i];
+                nd[N_DESC] = desc; nd[N_VISITS] = 0; nd[N_PRIOR] = row_at; nd[N_EDGES] = 0; nd[N_NEDGE] = 0;
+                v.ht[free_slot] = (uint16_t)(idx + 1);
+            }
+            w.node_count += 1;
+            w.arena_top = row_at + (uint32_t)L;
+            if (FEATURES)
+                for (int f = lane; f < YA_N_FEATURE; f += 32) feat_row[f] = ya_feature(cur, f);
+            w.leaf_node = idx;
+            w.kind = KIND_NEED_EVAL;
+            __syncwarp();
+            break;
+        }
+        uint32_t* node = v.nodes + (int64_t)idx * kNodeWords;
+        uint32_t desc = node[N_DESC];
+        int L = ya_legal_count(desc);
+        if (L == 0) { w.ret.d = 0.0; w.ret.is_f32 = false; break; }    // MCTS.py:138-147: `return 0`, not negated
+        if (w.depth >= kMaxDepth) { w.err = E_DEPTH; w.kind = KIND_ERROR; break; }
+        int ai = ucb_select(v, node, L, cpuct, lane);
+        int a = ya_nth_legal(desc, ai);
+        if (lane == 0) v.cur[C_PATH + w.depth] = (uint32_t)idx | ((uint32_t)ai << 16);
+        YaDraw d;
+        d.roll_a = d.roll_b = d.tie = d.pick = 0;
+        if (ya_draw_needs(cur, 1, a)) d = ya_draw(seed, gid, ep, pl, YA_TAG_SEARCH, (uint32_t)w.depth, sim);
+        int st;
+        int np = ya_transition(cur, 1, a, d, &st);                   // getNextState(canonicalBoard, 1, a), MCTS.py:149
+        if (st != YA_OK) { w.err = E_RULE | (1 << st); w.kind = KIND_ERROR; break; }
+        if (np != 1) cur = ya_flip(cur);                             // getCanonicalForm(next_s, next_player), MCTS.py:150
+        ++w.depth;
+    }
+    w.leaf = cur;
+    __syncwarp();
+}
+
 template <bool WRITE_LEAF_STATE>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 ya_k_mcts_select(ya_mcts_tree tree, const uint4* __restrict__ states, int64_t stride, const int8_t* __restrict__ players,
@@ -236,89 +331,30 @@ ya_k_mcts_select(ya_mcts_tree tree, const uint4* __restrict__ states, int64_t st
     if (g >= tree.n) return;
     if (active && !active[g]) { if (lane == 0) need_eval[g] = 0; return; }
     View v = make_view(tree, g);
-    YaState cur = ya_load(states, stride, g);
-    if (players[g] != 1) cur = ya_flip(cur);                         // getCanonicalForm of the root
+    YaState root = ya_load(states, stride, g);
+    if (players[g] != 1) root = ya_flip(root);                       // getCanonicalForm of the root
     const uint32_t gid = (uint32_t)(game_base + g);
     const uint32_t ep = episode ? episode[g] : 0u, pl = ply ? (uint32_t)ply[g] : 0u;
-
-    uint32_t node_count = v.meta[M_NODES], arena_top = v.meta[M_TOP];
-    // Lazy pruning at round boundaries: inside rounds >= 2 the search never leaves the root's round
-    // (quirk Q3), so nothing stored for an earlier round >= 2 can be reached again.
-    if (sim == 0) {
-        uint32_t old_round = v.meta[M_ROUND], new_round = (uint32_t)ya_round(cur);
-        if (old_round != new_round) {
-            if (old_round >= 2 || new_round < old_round) {
-                for (int i = lane; i < v.ht_size / 2; i += 32) reinterpret_cast<uint32_t*>(v.ht)[i] = 0u;
-                node_count = 0;
-                arena_top = 2;
-            }
-            if (lane == 0) v.meta[M_ROUND] = new_round;
-            __syncwarp();
-        }
-    }
-
-    int depth = 0, kind = KIND_DONE, err = 0, leaf_node = -1;
-    Val ret;
-    ret.d = 0.0; ret.is_f32 = false;
-    for (;;) {
-        float es = ya_game_ended(cur, 1);                           // Es[s], MCTS.py:79-83
-        if (es != 0.0f) { ret.d = -es_as_double(es); ret.is_f32 = false; break; }
-        int free_slot;
-        int idx = ht_find(v, cur, &free_slot);
-        if (idx < 0) {                                               // leaf: MCTS.py:84-115 (evaluation happens outside)
-            uint32_t desc = ya_mask_desc(cur, 1);
-            int L = ya_legal_count(desc);
-            if ((int)node_count >= v.max_nodes) { err = E_NODES_FULL; kind = KIND_ERROR; break; }
-            if (arena_top + (uint32_t)L > v.arena_words) { err = E_ARENA_FULL; kind = KIND_ERROR; break; }
-            idx = (int)node_count;
-            if (lane == 0) {
-                uint32_t* nd = v.nodes + (int64_t)idx * kNodeWords;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) nd[N_KEY + i] = cur.w[i];
-                nd[N_DESC] = desc; nd[N_VISITS] = 0; nd[N_PRIOR] = arena_top; nd[N_EDGES] = 0; nd[N_NEDGE] = 0;
-                v.ht[free_slot] = (uint16_t)(idx + 1);
-            }
-            node_count += 1;
-            arena_top += (uint32_t)L;
-            for (int f = lane; f < YA_N_FEATURE; f += 32) features[g * YA_N_FEATURE + f] = ya_feature(cur, f);
-            leaf_node = idx;
-            kind = KIND_NEED_EVAL;
-            __syncwarp();
-            break;
-        }
-        uint32_t* node = v.nodes + (int64_t)idx * kNodeWords;
-        uint32_t desc = node[N_DESC];
-        int L = ya_legal_count(desc);
-        if (L == 0) { ret.d = 0.0; ret.is_f32 = false; break; }    // MCTS.py:138-147: `return 0`, not negated
-        if (depth >= kMaxDepth) { err = E_DEPTH; kind = KIND_ERROR; break; }
-        int ai = ucb_select(v, node, L, cpuct, lane);
-        int a = ya_nth_legal(desc, ai);
-        if (lane == 0) v.cur[C_PATH + depth] = (uint32_t)idx | ((uint32_t)ai << 16);
-        YaDraw d;
-        d.roll_a = d.roll_b = d.tie = d.pick = 0;
-        if (ya_draw_needs(cur, 1, a)) d = ya_draw(seed, gid, ep, pl, YA_TAG_SEARCH, (uint32_t)depth, sim);
-        int st;
-        int np = ya_transition(cur, 1, a, d, &st);                   // getNextState(canonicalBoard, 1, a), MCTS.py:149
-        if (st != YA_OK) { err = E_RULE | (1 << st); kind = KIND_ERROR; break; }
-        if (np != 1) cur = ya_flip(cur);                             // getCanonicalForm(next_s, next_player), MCTS.py:150
-        ++depth;
-    }
-    __syncwarp();
-    if (kind == KIND_DONE) {
-        if (!backup_path(v, depth, ret, arena_top, lane)) { err = E_ARENA_FULL; kind = KIND_ERROR; }
+    Walk w;
+    w.node_count = v.meta[M_NODES];
+    w.arena_top = v.meta[M_TOP];
+    if (sim == 0) prune_on_new_round(v, root, w, lane);
+    descend<true>(v, root, w, seed, gid, ep, pl, sim, cpuct, features + g * YA_N_FEATURE, lane);
+    if (w.kind == KIND_DONE) {
+        if (!backup_path(v, w.depth, w.ret, w.arena_top, lane)) { w.err = E_ARENA_FULL; w.kind = KIND_ERROR; }
     }
     if (lane == 0) {
-        v.meta[M_NODES] = node_count;
-        v.meta[M_TOP] = arena_top;
-        v.cur[C_DEPTH] = (uint32_t)depth;
-        v.cur[C_KIND] = (uint32_t)kind;
-        v.cur[C_NODE] = (uint32_t)leaf_node;
-        need_eval[g] = kind == KIND_NEED_EVAL ? 1 : 0;
-        if (err && err_flag) atomicOr(err_flag, err);
-        if (WRITE_LEAF_STATE && leaf_states && kind == KIND_NEED_EVAL) {
+        v.meta[M_NODES] = w.node_count;
+        v.meta[M_TOP] = w.arena_top;
+        v.cur[C_DEPTH] = (uint32_t)w.depth;
+        v.cur[C_KIND] = (uint32_t)w.kind;
+        v.cur[C_NODE] = (uint32_t)w.leaf_node;
+        need_eval[g] = w.kind == KIND_NEED_EVAL ? 1 : 0;
+        if (w.err && err_flag) atomicOr(err_flag, w.err);
+        if (WRITE_LEAF_STATE && leaf_states && w.kind == KIND_NEED_EVAL) {
             uint4* o = reinterpret_cast<uint4*>(leaf_states);
-            o[g] = make_uint4(cur.w[0], cur.w[1], cur.w[2], cur.w[3]);
-            o[tree.n + g] = make_uint4(cur.w[4], cur.w[5], cur.w[6], cur.w[7]);
+            o[g] = make_uint4(w.leaf.w[0], w.leaf.w[1], w.leaf.w[2], w.leaf.w[3]);
+            o[tree.n + g] = make_uint4(w.leaf.w[4], w.leaf.w[5], w.leaf.w[6], w.leaf.w[7]);
         }
     }
 }
@@ -377,14 +413,33 @@ __device__ __forceinline__ float masked_pairwise_sum(Load load, uint32_t desc, i
     return my_leaf;
 }
 
-// MODE 0: pi float32[n][3226] from the evaluator; MODE 1: uniform prior, nothing read;
-// MODE 2: bf16 logits [n][ld] straight from the policy-head GEMM: softmax (float32: exp(l - max) / sum),
-//         mask and renormalisation fused here, so neither the float32 logits nor pi ever touch HBM.
+// Writes the leaf's legal-only prior row (MCTS.py:88-113).
+// MODE 0: pi float32[3226] from the evaluator; MODE 1: uniform prior, nothing read.
+template <int MODE>
+__device__ __forceinline__ void write_prior_row(float* __restrict__ row, uint32_t desc, int L, const float* pi,
+                                                float uniform_p, int lane) {
+    float total;
+    if (MODE == 0) {
+        total = masked_pairwise_sum([pi](int i) { return pi[i]; }, desc, lane);
+        if (total > 0.0f)                                            // Ps /= sum, MCTS.py:90-91
+            for (int k = lane; k < L; k += 32) row[k] = __fdiv_rn(pi[ya_nth_legal(desc, k)], total);
+    } else {
+        total = masked_pairwise_sum([uniform_p](int) { return uniform_p; }, desc, lane);
+        if (total > 0.0f) {
+            float p = __fdiv_rn(uniform_p, total);
+            for (int k = lane; k < L; k += 32) row[k] = p;
+        }
+    }
+    if (!(total > 0.0f)) {                                           // all legal moves masked: uniform over legal, :97-101
+        float u = __fdiv_rn(1.0f, (float)L);
+        for (int k = lane; k < L; k += 32) row[k] = u;
+    }
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
-ya_k_mcts_expand(ya_mcts_tree tree, const float* __restrict__ pi_all, const __nv_bfloat16* __restrict__ logits_all,
-                 int64_t ld, const float* __restrict__ value, float uniform_p, float uniform_v,
-                 uint32_t* __restrict__ sim_counter, int32_t* __restrict__ err_flag) {
+ya_k_mcts_expand(ya_mcts_tree tree, const float* __restrict__ pi_all, const float* __restrict__ value, float uniform_p,
+                 float uniform_v, uint32_t* __restrict__ sim_counter, int32_t* __restrict__ err_flag) {
     const int lane = threadIdx.x & 31;
     const int64_t g = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     if (sim_counter && blockIdx.x == 0 && threadIdx.x == 0) *sim_counter += 1;   // next replay = next simulation
@@ -394,47 +449,9 @@ ya_k_mcts_expand(ya_mcts_tree tree, const float* __restrict__ pi_all, const __nv
     uint32_t* node = v.nodes + (int64_t)v.cur[C_NODE] * kNodeWords;
     const uint32_t desc = node[N_DESC];
     const int L = ya_legal_count(desc);
-    if (L > 0) {
-        float* row = reinterpret_cast<float*>(v.arena + node[N_PRIOR]);
-        float total;
-        if (MODE == 0) {
-            const float* pi = pi_all + g * YA_N_ACTION;
-            total = masked_pairwise_sum([pi](int i) { return pi[i]; }, desc, lane);
-            if (total > 0.0f)                                        // Ps /= sum, MCTS.py:90-91
-                for (int k = lane; k < L; k += 32) row[k] = __fdiv_rn(pi[ya_nth_legal(desc, k)], total);
-        } else if (MODE == 1) {
-            total = masked_pairwise_sum([uniform_p](int) { return uniform_p; }, desc, lane);
-            if (total > 0.0f) {
-                float p = __fdiv_rn(uniform_p, total);
-                for (int k = lane; k < L; k += 32) row[k] = p;
-            }
-        } else {
-            const __nv_bfloat16* lg = logits_all + g * ld;
-            float mx = -CUDART_INF_F;
-            for (int i = lane; i < YA_N_ACTION; i += 32) mx = fmaxf(mx, __bfloat162float(lg[i]));
-#pragma unroll
-            for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, o));
-            float den = 0.0f;
-            for (int i = lane; i < YA_N_ACTION; i += 32) {
-                float e = expf(__bfloat162float(lg[i]) - mx);
-                den += e;
-                if (desc_valid(desc, i)) row[ya_legal_index(desc, i)] = e;     // park exp(l - max) of the legal actions
-            }
-#pragma unroll
-            for (int o = 16; o; o >>= 1) den += __shfl_xor_sync(0xFFFFFFFFu, den, o);
-            __syncwarp();
-            const float* rowc = row;
-            total = masked_pairwise_sum([rowc, den, desc](int i) { return __fdiv_rn(rowc[ya_legal_index(desc, i)], den); },
-                                        desc, lane);
-            __syncwarp();
-            if (total > 0.0f)
-                for (int k = lane; k < L; k += 32) row[k] = __fdiv_rn(__fdiv_rn(row[k], den), total);
-        }
-        if (!(total > 0.0f)) {                                       // all legal moves masked: uniform over legal, :97-101
-            float u = __fdiv_rn(1.0f, (float)L);
-            for (int k = lane; k < L; k += 32) row[k] = u;
-        }
-    }
+    if (L > 0)
+        write_prior_row<MODE>(reinterpret_cast<float*>(v.arena + node[N_PRIOR]), desc, L,
+                              MODE == 0 ? pi_all + g * YA_N_ACTION : nullptr, uniform_p, lane);
     __syncwarp();
     Val ret;
     ret.d = -(double)(MODE == 1 ? uniform_v : value[g]);             // return -v (numpy float32)
@@ -445,6 +462,124 @@ ya_k_mcts_expand(ya_mcts_tree tree, const float* __restrict__ pi_all, const __nv
         v.meta[M_TOP] = arena_top;
         v.cur[C_KIND] = KIND_DONE;
         if (!ok && err_flag) atomicOr(err_flag, E_ARENA_FULL);
+    }
+}
+
+// bf16 logits [n][ld] straight from the policy-head GEMM: softmax (float32: exp(l - max) / sum), mask and
+// renormalisation fused, so neither float32 logits nor pi ever touch HBM.  exp(l - max) of all 3226
+// actions is staged once in shared memory (12.9 KB per warp) and reused by the pairwise sum and the row write.
+constexpr int kLogitWarps = 4;
+__global__ void __launch_bounds__(kLogitWarps * 32)
+ya_k_mcts_expand_logits(ya_mcts_tree tree, const __nv_bfloat16* __restrict__ logits_all, int64_t ld,
+                        const float* __restrict__ value, uint32_t* __restrict__ sim_counter, int32_t* __restrict__ err_flag) {
+    extern __shared__ __align__(16) float e_all[];
+    const int lane = threadIdx.x & 31;
+    float* e = e_all + (threadIdx.x >> 5) * YA_N_ACTION;
+    const int64_t g = (int64_t)blockIdx.x * kLogitWarps + (threadIdx.x >> 5);
+    if (sim_counter && blockIdx.x == 0 && threadIdx.x == 0) *sim_counter += 1;
+    if (g >= tree.n) return;
+    View v = make_view(tree, g);
+    if (v.cur[C_KIND] != KIND_NEED_EVAL) return;
+    uint32_t* node = v.nodes + (int64_t)v.cur[C_NODE] * kNodeWords;
+    const uint32_t desc = node[N_DESC];
+    const int L = ya_legal_count(desc);
+    if (L > 0) {
+        const __nv_bfloat16* lg = logits_all + g * ld;
+        const uint4* lg4 = reinterpret_cast<const uint4*>(lg);          // ld * 2 B is a multiple of 16 (checked on the host)
+        constexpr int kVec = YA_N_ACTION / 8;                          // 403 full vectors + 2 trailing logits
+        float mx = -CUDART_INF_F;
+        for (int j = lane; j < kVec; j += 32) {
+            uint4 q = lg4[j];
+            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) { float2 f = __bfloat1622float2(h[t]); e[8 * j + 2 * t] = f.x; e[8 * j + 2 * t + 1] = f.y; mx = fmaxf(mx, fmaxf(f.x, f.y)); }
+        }
+        if (lane < YA_N_ACTION - 8 * kVec) { float f = __bfloat162float(lg[8 * kVec + lane]); e[8 * kVec + lane] = f; mx = fmaxf(mx, f); }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, o));
+        __syncwarp();
+        float den = 0.0f;
+        for (int i = lane; i < YA_N_ACTION; i += 32) { float x = expf(e[i] - mx); e[i] = x; den += x; }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) den += __shfl_xor_sync(0xFFFFFFFFu, den, o);
+        __syncwarp();
+        const float* ec = e;
+        float total = masked_pairwise_sum([ec, den](int i) { return __fdiv_rn(ec[i], den); }, desc, lane);
+        float* row = reinterpret_cast<float*>(v.arena + node[N_PRIOR]);
+        if (total > 0.0f) {
+            if (desc & 1u) {                                           // bid row: actions 0..201
+                for (int k = lane; k < YA_N_BID; k += 32) row[k] = __fdiv_rn(__fdiv_rn(e[k], den), total);
+            } else if (desc >> 13) {                                   // ten dice: 252 subsets per open category
+                int k0 = 0;
+                for (uint32_t open = (desc >> 1) & 0xFFFu; open; open &= open - 1, k0 += YA_N_SUBSET) {
+                    const float* src = e + YA_N_BID + (__ffs(open) - 1) * YA_N_SUBSET;
+                    for (int t = lane; t < YA_N_SUBSET; t += 32) row[k0 + t] = __fdiv_rn(__fdiv_rn(src[t], den), total);
+                }
+            } else {                                                   // five dice: subset 0 of every open category
+                for (int k = lane; k < L; k += 32)
+                    row[k] = __fdiv_rn(__fdiv_rn(e[ya_nth_legal(desc, k)], den), total);
+            }
+        } else {
+            float u = __fdiv_rn(1.0f, (float)L);
+            for (int k = lane; k < L; k += 32) row[k] = u;
+        }
+    }
+    __syncwarp();
+    Val ret;
+    ret.d = -(double)value[g];
+    ret.is_f32 = true;
+    uint32_t arena_top = v.meta[M_TOP];
+    bool ok = backup_path(v, (int)v.cur[C_DEPTH], ret, arena_top, lane);
+    if (lane == 0) {
+        v.meta[M_TOP] = arena_top;
+        v.cur[C_KIND] = KIND_DONE;
+        if (!ok && err_flag) atomicOr(err_flag, E_ARENA_FULL);
+    }
+}
+
+// ---------------------------------------------------------------- whole search, uniform prior
+// BASELINE.json configs[2] (no network): nothing has to leave the SM between select and expand, so all
+// numMCTSSims simulations of a move run inside ONE launch -- one warp walks, expands and backs up its
+// game's tree num_sims times; node / row / edge data stay hot in L1/L2 across simulations.
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+ya_k_mcts_search_uniform(ya_mcts_tree tree, const uint4* __restrict__ states, int64_t stride, const int8_t* __restrict__ players,
+                         const int32_t* __restrict__ ply, const uint32_t* __restrict__ episode, uint64_t seed,
+                         uint64_t game_base, int num_sims, float cpuct, float uniform_p, float uniform_v,
+                         const uint8_t* __restrict__ active, int32_t* __restrict__ err_flag) {
+    const int lane = threadIdx.x & 31;
+    const int64_t g = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    if (g >= tree.n) return;
+    if (active && !active[g]) return;
+    View v = make_view(tree, g);
+    YaState root = ya_load(states, stride, g);
+    if (players[g] != 1) root = ya_flip(root);
+    const uint32_t gid = (uint32_t)(game_base + g);
+    const uint32_t ep = episode ? episode[g] : 0u, pl = ply ? (uint32_t)ply[g] : 0u;
+    Walk w;
+    w.node_count = v.meta[M_NODES];
+    w.arena_top = v.meta[M_TOP];
+    prune_on_new_round(v, root, w, lane);
+    int err = 0;
+    for (int sim = 0; sim < num_sims; ++sim) {
+        descend<false>(v, root, w, seed, gid, ep, pl, (uint32_t)sim, cpuct, nullptr, lane);
+        if (w.kind == KIND_ERROR) { err = w.err; break; }
+        Val ret = w.ret;
+        if (w.kind == KIND_NEED_EVAL) {
+            uint32_t* node = v.nodes + (int64_t)w.leaf_node * kNodeWords;
+            const uint32_t desc = node[N_DESC];
+            const int L = ya_legal_count(desc);
+            if (L > 0) write_prior_row<1>(reinterpret_cast<float*>(v.arena + node[N_PRIOR]), desc, L, nullptr, uniform_p, lane);
+            __syncwarp();
+            ret.d = -(double)uniform_v;
+            ret.is_f32 = true;
+        }
+        if (!backup_path(v, w.depth, ret, w.arena_top, lane)) { err = E_ARENA_FULL; break; }
+    }
+    if (lane == 0) {
+        v.meta[M_NODES] = w.node_count;
+        v.meta[M_TOP] = w.arena_top;
+        v.cur[C_KIND] = KIND_DONE;
+        if (err && err_flag) atomicOr(err_flag, err);
     }
 }
 
@@ -541,7 +676,7 @@ __global__ void ya_k_mcts_reset(ya_mcts_tree tree, const uint8_t* __restrict__ w
     View v = make_view(tree, g);
     for (int i = threadIdx.x; i < v.ht_size / 2; i += blockDim.x) reinterpret_cast<uint32_t*>(v.ht)[i] = 0u;
     if (threadIdx.x == 0) {
-        v.meta[M_NODES] = 0; v.meta[M_TOP] = 2; v.meta[M_ROUND] = 0; v.meta[3] = 0;
+        v.meta[M_NODES] = 0; v.meta[M_TOP] = 4; v.meta[M_ROUND] = 0; v.meta[3] = 0;
         v.cur[C_KIND] = KIND_DONE; v.cur[C_DEPTH] = 0;
     }
 }
@@ -550,7 +685,7 @@ inline int warp_blocks(int64_t n) { return (int)((n + kWarpsPerBlock - 1) / kWar
 
 bool tree_ok(const ya_mcts_tree* t) {
     return t && t->n > 0 && t->max_nodes > 0 && t->max_nodes < 65535 && t->ht_size >= 2 * t->max_nodes &&
-           (t->ht_size & (t->ht_size - 1)) == 0 && t->arena_words > 2 && (t->arena_words % 2) == 0 &&
+           (t->ht_size & (t->ht_size - 1)) == 0 && t->arena_words > 4 && (t->arena_words % 4) == 0 &&
            t->arena_words < (1ll << 32);
 }
 
@@ -588,18 +723,38 @@ int ya_mcts_expand(const ya_mcts_tree* tree, const float* pi, const float* value
     if (!tree_ok(tree)) return (int)cudaErrorInvalidValue;
     if (uniform)
         ya_k_mcts_expand<1><<<warp_blocks(tree->n), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
-            *tree, nullptr, nullptr, 0, nullptr, uniform_p, uniform_v, sim_counter, err_flag);
+            *tree, nullptr, nullptr, uniform_p, uniform_v, sim_counter, err_flag);
     else
         ya_k_mcts_expand<0><<<warp_blocks(tree->n), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
-            *tree, pi, nullptr, 0, value, 0.0f, 0.0f, sim_counter, err_flag);
+            *tree, pi, value, 0.0f, 0.0f, sim_counter, err_flag);
     return (int)cudaGetLastError();
 }
 
 int ya_mcts_expand_logits(const ya_mcts_tree* tree, const void* logits_bf16, int64_t ld, const float* value,
                           uint32_t* sim_counter, int32_t* err_flag, void* stream) {
-    if (!tree_ok(tree) || ld < YA_N_ACTION) return (int)cudaErrorInvalidValue;
-    ya_k_mcts_expand<2><<<warp_blocks(tree->n), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
-        *tree, nullptr, static_cast<const __nv_bfloat16*>(logits_bf16), ld, value, 0.0f, 0.0f, sim_counter, err_flag);
+    if (!tree_ok(tree) || ld < YA_N_ACTION || (ld % 8) != 0 || (reinterpret_cast<uintptr_t>(logits_bf16) & 15u))
+        return (int)cudaErrorInvalidValue;
+    constexpr size_t smem = (size_t)kLogitWarps * YA_N_ACTION * sizeof(float);
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(ya_k_mcts_expand_logits, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        configured = true;
+    }
+    int blocks = (int)((tree->n + kLogitWarps - 1) / kLogitWarps);
+    ya_k_mcts_expand_logits<<<blocks, kLogitWarps * 32, smem, (cudaStream_t)stream>>>(
+        *tree, static_cast<const __nv_bfloat16*>(logits_bf16), ld, value, sim_counter, err_flag);
+    return (int)cudaGetLastError();
+}
+
+int ya_mcts_search_uniform(const ya_mcts_tree* tree, const uint32_t* states, int64_t stride, const int8_t* players,
+                           const int32_t* ply, const uint32_t* episode, uint64_t seed, uint64_t game_base, int num_sims,
+                           float cpuct, float uniform_p, float uniform_v, const uint8_t* active, int32_t* err_flag,
+                           void* stream) {
+    if (!tree_ok(tree) || num_sims < 0) return (int)cudaErrorInvalidValue;
+    ya_k_mcts_search_uniform<<<warp_blocks(tree->n), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
+        *tree, reinterpret_cast<const uint4*>(states), stride, players, ply, episode, seed, game_base, num_sims, cpuct,
+        uniform_p, uniform_v, active, err_flag);
     return (int)cudaGetLastError();
 }
 

@@ -40,7 +40,7 @@ class TreePool:
             # (rounds 1+2); 40 KB/sim leaves ~20 % head-room, overflow is detected and raised.
             arena_mb_per_game = max(num_sims * 40.0 / 1024.0, 0.25)
         words = int(arena_mb_per_game * 2 ** 20) // 4
-        self.arena_words = words - (words % 2)
+        self.arena_words = words - (words % 4)
         d = self.device
         self.nodes = torch.zeros((self.n, self.max_nodes, lib.ya_mcts_node_words()), dtype=torch.int32, device=d)
         self.ht = torch.zeros((self.n, self.ht_size), dtype=torch.int16, device=d)
@@ -210,6 +210,7 @@ class BatchedMCTS:
         self.sim_counter = torch.zeros(1, dtype=torch.int32, device=d)
         self.sims_run = 0
         self.graph = None
+        self.fuse_uniform = True        # uniform evaluator: run all simulations of a move in one kernel
 
     def capture_graph(self):
         """Capture ONE simulation wave (select, evaluator forward, expand) as a CUDA graph; the
@@ -261,6 +262,15 @@ class BatchedMCTS:
 
     def search(self):
         """getActionProb's simulation loop (MCTS.py:37-38) for every game."""
+        ev = self.evaluator
+        if getattr(ev, "uniform", False) and self.fuse_uniform:
+            env = self.env                  # no network between select and expand: the whole loop is one launch
+            _lib.check(self.lib.ya_mcts_search_uniform(
+                self.pool.ref, _lib.ptr(env.states), env.n, _lib.ptr(env.players), _lib.ptr(env.ply), _lib.ptr(env.episode),
+                env.seed, env.game_base, self.num_sims, self.cpuct, ev.p, ev.v, None, _lib.ptr(self.err_flag),
+                _lib.current_stream()), "ya_mcts_search_uniform")
+            self.sims_run += env.n * self.num_sims
+            return
         if self.graph is not None:
             self.sim_counter.zero_()
             for _ in range(self.num_sims):
