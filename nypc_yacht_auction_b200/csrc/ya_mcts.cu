@@ -498,26 +498,30 @@ ya_k_mcts_expand_logits(ya_mcts_tree tree, const __nv_bfloat16* __restrict__ log
 #pragma unroll
         for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, o));
         __syncwarp();
+        // softmax of the evaluator (NNetWrapper.predict, yacht/NNet.py:193): pi = exp(l - max) / sum
         float den = 0.0f;
-        for (int i = lane; i < YA_N_ACTION; i += 32) { float x = expf(e[i] - mx); e[i] = x; den += x; }
+        for (int i = lane; i < YA_N_ACTION; i += 32) { float x = __expf(e[i] - mx); e[i] = x; den += x; }
 #pragma unroll
         for (int o = 16; o; o >>= 1) den += __shfl_xor_sync(0xFFFFFFFFu, den, o);
+        const float rden = __fdiv_rn(1.0f, den);
         __syncwarp();
+        for (int i = lane; i < YA_N_ACTION; i += 32) e[i] = __fmul_rn(e[i], rden);
+        __syncwarp();
+        // MCTS.py:88-91: mask, sum in numpy's pairwise order, renormalise (true float32 divisions)
         const float* ec = e;
-        float total = masked_pairwise_sum([ec, den](int i) { return __fdiv_rn(ec[i], den); }, desc, lane);
+        float total = masked_pairwise_sum([ec](int i) { return ec[i]; }, desc, lane);
         float* row = reinterpret_cast<float*>(v.arena + node[N_PRIOR]);
         if (total > 0.0f) {
             if (desc & 1u) {                                           // bid row: actions 0..201
-                for (int k = lane; k < YA_N_BID; k += 32) row[k] = __fdiv_rn(__fdiv_rn(e[k], den), total);
+                for (int k = lane; k < YA_N_BID; k += 32) row[k] = __fdiv_rn(e[k], total);
             } else if (desc >> 13) {                                   // ten dice: 252 subsets per open category
                 int k0 = 0;
                 for (uint32_t open = (desc >> 1) & 0xFFFu; open; open &= open - 1, k0 += YA_N_SUBSET) {
                     const float* src = e + YA_N_BID + (__ffs(open) - 1) * YA_N_SUBSET;
-                    for (int t = lane; t < YA_N_SUBSET; t += 32) row[k0 + t] = __fdiv_rn(__fdiv_rn(src[t], den), total);
+                    for (int t = lane; t < YA_N_SUBSET; t += 32) row[k0 + t] = __fdiv_rn(src[t], total);
                 }
             } else {                                                   // five dice: subset 0 of every open category
-                for (int k = lane; k < L; k += 32)
-                    row[k] = __fdiv_rn(__fdiv_rn(e[ya_nth_legal(desc, k)], den), total);
+                for (int k = lane; k < L; k += 32) row[k] = __fdiv_rn(e[ya_nth_legal(desc, k)], total);
             }
         } else {
             float u = __fdiv_rn(1.0f, (float)L);
