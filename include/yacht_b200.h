@@ -173,12 +173,23 @@ int ya_nn_ln_act(int mode, const void* x, const void* gamma, const void* beta, c
  * ya_host_play_ply copies the packed states and side arrays host->device, runs ya_play_ply,
  * copies states / players / ply / episode / actions / outcome (and masks if requested and the
  * context was created with_masks) back and synchronises.  All pointers are HOST pointers; the
- * state buffer uses stride = n. */
+ * state buffer uses stride = n.
+ *
+ * Record variant: one 64-byte record per game, uint32[16] = {w0..w7 packed state, episode, ply,
+ * player (+1/-1 as int32), action (out), outcome (out, float bits), 3 reserved}, so a slice of games is
+ * ONE contiguous copy per direction; ya_host_play_ply_records pipelines 4 slices over 4 streams
+ * (H2D, kernel, D2H overlap on the full-duplex link).  ya_play_ply_records is the device-side kernel
+ * entry on records already in HBM.  With a context created with_masks the uint8[n][3226] mask is
+ * materialised in HBM every ply (and copied to `masks` only if that pointer is not NULL). */
 int ya_host_create(int64_t n, int with_masks, void** handle);
 int ya_host_destroy(void* handle);
 int ya_host_play_ply(void* handle, uint32_t* states, int8_t* players, int32_t* ply, uint32_t* episode,
                      int32_t* actions, float* outcome, uint8_t* masks, int32_t* err_flag,
                      uint64_t seed, uint64_t game_base, int auto_reset);
+int ya_host_play_ply_records(void* handle, uint32_t* records, uint8_t* masks, int32_t* err_flag,
+                             uint64_t seed, uint64_t game_base, int auto_reset);
+int ya_play_ply_records(uint32_t* records, uint8_t* masks, int32_t* err_flag, int64_t n, uint64_t seed,
+                        uint64_t game_base, int auto_reset, void* stream);
 
 #ifdef __cplusplus
 }

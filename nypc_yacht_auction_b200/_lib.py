@@ -45,6 +45,8 @@ SIGNATURES = {
     "ya_host_create": [_i64, _int, ctypes.POINTER(ctypes.c_void_p)],
     "ya_host_destroy": [_vp],
     "ya_host_play_ply": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _u64, _u64, _int],
+    "ya_host_play_ply_records": [_vp, _vp, _vp, _vp, _u64, _u64, _int],
+    "ya_play_ply_records": [_vp, _vp, _vp, _i64, _u64, _u64, _int, _vp],
 }
 
 

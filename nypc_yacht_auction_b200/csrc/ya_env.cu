@@ -247,14 +247,34 @@ __global__ void ya_k_random_action(const uint4* __restrict__ states, int64_t str
 // ------------------------------------------------------------------ scoring-move enumeration
 // out[g][cat][subset] = score_category(cat, dice at subset) / 1000 for the player to move, 0
 // where the subset does not fit (YachtPlayers.py:134-169 enumerates exactly this 12 x 252 table).
-// One warp per game: lanes stride over the 252 subsets, the 3024-byte tile is staged in shared
-// memory and leaves as 189 coalesced 16-byte stores.
+// One warp per game.  A subset's face histogram (six 4-bit counters) and pip sum (bits 24..28) are
+// additive over its dice, so they come from two 32-entry tables per game -- partial sums over dice
+// 0..4 and 5..9, built by the 32 lanes in one step -- as T_lo[m & 31] + T_hi[m >> 5]: two shared-
+// memory loads and an add per subset instead of a 10-step gather.  Each lane scores four consecutive
+// subsets and writes one packed 32-bit word per category into the 3,024-byte tile, which leaves as
+// 189 coalesced 16-byte stores.
 constexpr int kEnumWarps = 8;
+
+__device__ __forceinline__ void ya_score_all(uint32_t w, uint32_t out[YA_N_CAT]) {
+    const uint32_t hist = w & 0xFFFFFFu, pips = w >> 24;
+#pragma unroll
+    for (int c = 0; c < 6; ++c) out[c] = (uint32_t)(c + 1) * ((hist >> (4 * c)) & 0xFu);
+    out[6] = pips;
+    out[7] = ((hist + 0x444444u) & 0x888888u) ? pips : 0u;                    // some count >= 4
+    const uint32_t e5 = ya_nibble_eq(hist, 5);
+    out[8] = ((ya_nibble_eq(hist, 2) | e5) && (ya_nibble_eq(hist, 3) | e5)) ? pips : 0u;
+    const uint32_t nz = (hist | (hist >> 1) | (hist >> 2) | (hist >> 3)) & 0x111111u;
+    const uint32_t seen = (nz & 1u) | ((nz >> 3) & 2u) | ((nz >> 6) & 4u) | ((nz >> 9) & 8u) | ((nz >> 12) & 16u) | ((nz >> 15) & 32u);
+    out[9] = (((seen & 0x0Fu) == 0x0Fu) || ((seen & 0x1Eu) == 0x1Eu) || ((seen & 0x3Cu) == 0x3Cu)) ? 15u : 0u;
+    out[10] = (((seen & 0x1Fu) == 0x1Fu) || ((seen & 0x3Eu) == 0x3Eu)) ? 30u : 0u;
+    out[11] = e5 ? 50u : 0u;
+}
 
 __global__ void __launch_bounds__(kEnumWarps * 32)
 ya_k_enumerate_scores(const uint4* __restrict__ states, int64_t stride, const int8_t* __restrict__ players,
                       uint8_t* __restrict__ out, int64_t n) {
-    __shared__ __align__(16) uint8_t tile[kEnumWarps][YA_N_CAT * YA_N_SUBSET];
+    __shared__ __align__(16) uint32_t tile[kEnumWarps][YA_N_CAT * YA_N_SUBSET / 4];
+    __shared__ uint32_t part[kEnumWarps][64];
     __shared__ uint16_t smask[YA_N_SUBSET];
     for (int i = threadIdx.x; i < YA_N_SUBSET; i += blockDim.x) smask[i] = ya_subset_mask[i];
     __syncthreads();
@@ -262,17 +282,37 @@ ya_k_enumerate_scores(const uint4* __restrict__ states, int64_t stride, const in
     const int64_t nwarps = (int64_t)gridDim.x * kEnumWarps;
     for (int64_t g = (int64_t)blockIdx.x * kEnumWarps + warp; g < n; g += nwarps) {
         YaState s = ya_load(states, stride, g);
-        uint32_t carry = s.w[2 + (players[g] == 1 ? 0 : 1)];
-        int nd = ya_dice_count(carry);
-        uint8_t* t = tile[warp];
-        for (int sub = lane; sub < YA_N_SUBSET; sub += 32) {
-            uint32_t m = smask[sub];
-            bool fits = (31 - __clz(m)) < nd;
-            uint32_t hist = 0, pips = 0;
-            if (fits) ya_gather(carry, m, hist, pips);
+        const uint32_t carry = s.w[2 + (players[g] == 1 ? 0 : 1)];
+        const int nd = ya_dice_count(carry);
+        // lane l: partial sums over the dice of 5-bit pattern l, low half (dice 0..4) and high half (5..9)
+        uint32_t lo = 0, hi = 0;
 #pragma unroll
-            for (int cat = 0; cat < YA_N_CAT; ++cat)
-                t[cat * YA_N_SUBSET + sub] = fits ? (uint8_t)ya_category_points_k(cat, hist, pips) : (uint8_t)0;
+        for (int j = 0; j < 5; ++j) {
+            uint32_t dl = (carry >> (3 * j)) & 7u, dh = (carry >> (3 * (j + 5))) & 7u;
+            uint32_t wl = dl ? ((1u << (4 * (dl - 1))) | (dl << 24)) : 0u;
+            uint32_t wh = dh ? ((1u << (4 * (dh - 1))) | (dh << 24)) : 0u;
+            if ((lane >> j) & 1) { lo += wl; hi += wh; }
+        }
+        part[warp][lane] = lo;
+        part[warp][32 + lane] = hi;
+        __syncwarp();
+        uint32_t* t = tile[warp];
+        for (int q = lane; q < YA_N_SUBSET / 4; q += 32) {          // subsets 4q .. 4q+3
+            uint32_t packed[YA_N_CAT];
+#pragma unroll
+            for (int c = 0; c < YA_N_CAT; ++c) packed[c] = 0u;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t m = smask[4 * q + k];
+                if ((31 - __clz(m)) < nd) {
+                    uint32_t sc[YA_N_CAT];
+                    ya_score_all(part[warp][m & 31u] + part[warp][32 + (m >> 5)], sc);
+#pragma unroll
+                    for (int c = 0; c < YA_N_CAT; ++c) packed[c] |= sc[c] << (8 * k);
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < YA_N_CAT; ++c) t[c * (YA_N_SUBSET / 4) + q] = packed[c];
         }
         __syncwarp();
         const uint4* src = reinterpret_cast<const uint4*>(t);
@@ -334,6 +374,62 @@ ya_k_play_ply(uint4* __restrict__ states, int64_t stride, int8_t* __restrict__ p
         episode[g] = ep;
         actions[g] = a;
         outcome[g] = res;
+    }
+    if (masks) {
+        __syncthreads();
+        ya_mask_smem_link(sm, fill_s, ng, GAMES, threadIdx.x, blockDim.x);
+        __syncthreads();
+        uint8_t* out = masks + g0 * YA_N_ACTION;
+        ya_write_mask_chunk(out, ng, sm, threadIdx.x, blockDim.x);
+        __syncthreads();
+        ya_patch_five_dice_rows(out, ng, desc_s, threadIdx.x, blockDim.x);
+    }
+}
+
+// Same ply, array-of-records I/O for the host-buffer path: one 64-byte record per game
+// {w0..w7, episode, ply, player, action(out), outcome(out), 3 reserved} so a slice of games is ONE
+// contiguous PCIe copy in each direction.  The mask (if requested) is still streamed to HBM.
+template <int GAMES>
+__global__ void __launch_bounds__(kThreads, 4)
+ya_k_play_ply_records(uint4* __restrict__ rec, uint8_t* __restrict__ masks, int32_t* __restrict__ err_flag,
+                      int64_t n, uint64_t seed, uint64_t game_base, int auto_reset) {
+    __shared__ YaMaskSmem sm;
+    __shared__ uint32_t desc_s[GAMES];
+    __shared__ uint32_t fill_s[GAMES];
+    const int64_t g0 = (int64_t)blockIdx.x * GAMES;
+    const int ng = (int)min((int64_t)GAMES, n - g0);
+    if (masks) ya_mask_smem_init(sm, threadIdx.x, blockDim.x);
+    for (int t = threadIdx.x; t < ng; t += blockDim.x) {
+        uint4* r = rec + (g0 + t) * 4;
+        uint4 a = r[0], b = r[1], c = r[2];
+        YaState s;
+        s.w[0] = a.x; s.w[1] = a.y; s.w[2] = a.z; s.w[3] = a.w;
+        s.w[4] = b.x; s.w[5] = b.y; s.w[6] = b.z; s.w[7] = b.w;
+        uint32_t ep = c.x, p = c.y;
+        int pl = (int)c.z;
+        uint32_t gid = (uint32_t)(game_base + g0 + t);
+        uint32_t desc = ya_mask_desc(s, pl);
+        desc_s[t] = desc;
+        fill_s[t] = ya_fill_bits(desc);
+        int count = ya_legal_count(desc);
+        int act = 0;
+        if (count) {
+            YaDraw da = ya_draw(seed, gid, ep, p, YA_TAG_ACTION, 0, 0);
+            act = ya_nth_legal(desc, (int)__umulhi(da.pick, (uint32_t)count));
+        }
+        YaDraw d;
+        d.roll_a = d.roll_b = d.tie = d.pick = 0;
+        if (ya_draw_needs(s, pl, act)) d = ya_draw(seed, gid, ep, p, YA_TAG_REAL, 0, 0);
+        int st;
+        int np = ya_transition(s, pl, act, d, &st);
+        if (st != YA_OK && err_flag) atomicOr(err_flag, 1 << st);
+        float res = ya_game_ended(s, 1);
+        p += 1;
+        if (res != 0.0f && auto_reset) { ep += 1; p = 0; np = 1; s = ya_fresh_state(seed, gid, ep); }
+        r[0] = make_uint4(s.w[0], s.w[1], s.w[2], s.w[3]);
+        r[1] = make_uint4(s.w[4], s.w[5], s.w[6], s.w[7]);
+        r[2] = make_uint4(ep, p, (uint32_t)np, (uint32_t)act);
+        r[3] = make_uint4(__float_as_uint(res), 0u, 0u, 0u);
     }
     if (masks) {
         __syncthreads();
@@ -434,6 +530,17 @@ int ya_play_ply(uint32_t* states, int64_t stride, int8_t* players, int32_t* ply,
     ya_k_play_ply<G><<<blocks_for(n, G), kThreads, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<uint4*>(states), stride, players, ply, episode, actions, outcome, masks, err_flag,
         n, seed, game_base, auto_reset);
+    return (int)cudaGetLastError();
+}
+
+int ya_play_ply_records(uint32_t* records, uint8_t* masks, int32_t* err_flag, int64_t n, uint64_t seed,
+                        uint64_t game_base, int auto_reset, void* stream) {
+    if (n <= 0) return 0;
+    if (masks && (reinterpret_cast<uintptr_t>(masks) & 15u) != 0) return (int)cudaErrorMisalignedAddress;
+    if ((reinterpret_cast<uintptr_t>(records) & 15u) != 0) return (int)cudaErrorMisalignedAddress;
+    constexpr int G = 64;
+    ya_k_play_ply_records<G><<<blocks_for(n, G), kThreads, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<uint4*>(records), masks, err_flag, n, seed, game_base, auto_reset);
     return (int)cudaGetLastError();
 }
 

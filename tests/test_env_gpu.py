@@ -277,3 +277,64 @@ def test_full_size_properties():
     for ply in range(48):
         _, out2 = env2.play_ply(masks=None, auto_reset=False)
     assert torch.equal(out2, outcome[40000:41000])
+
+
+def test_host_buffer_abi_matches_device_path():
+    """ya_host_play_ply (host pointers, sliced over 4 copy/compute streams) gives exactly what the
+    device-resident fused ply gives, including the masks, for a ragged batch size."""
+    import ctypes
+    from nypc_yacht_auction_b200 import _lib
+    lib = _lib.load()
+    n, seed, base = 1003, 9, 77
+    dev_env = _engine(n, seed, base)
+    dmask = torch.empty((n, 3226), dtype=torch.uint8, device="cuda")
+    h = ctypes.c_void_p()
+    _lib.check(lib.ya_host_create(n, 1, ctypes.byref(h)), "create")
+    hs = dev_env.states.cpu().clone()
+    hp = torch.ones(n, dtype=torch.int8)
+    hply = torch.zeros(n, dtype=torch.int32)
+    hep = torch.zeros(n, dtype=torch.int32)
+    ha = torch.zeros(n, dtype=torch.int32)
+    ho = torch.zeros(n, dtype=torch.float32)
+    hm = torch.zeros((n, 3226), dtype=torch.uint8)
+    herr = torch.zeros(1, dtype=torch.int32)
+    for ply in range(50):
+        acts, out = dev_env.play_ply(masks=dmask, auto_reset=True)
+        _lib.check(lib.ya_host_play_ply(h, _lib.ptr(hs), _lib.ptr(hp), _lib.ptr(hply), _lib.ptr(hep), _lib.ptr(ha), _lib.ptr(ho),
+                                        _lib.ptr(hm), _lib.ptr(herr), seed, base, 1), "host ply")
+        assert torch.equal(hs, dev_env.states.cpu()) and torch.equal(hp, dev_env.players.cpu())
+        assert torch.equal(ha, acts.cpu()) and torch.equal(ho, out.cpu()) and torch.equal(hm, dmask.cpu())
+        assert torch.equal(hply, dev_env.ply.cpu()) and torch.equal(hep, dev_env.episode.cpu())
+    assert int(herr.item()) == 0
+    lib.ya_host_destroy(h)
+
+
+def test_record_host_abi_matches_device_path():
+    """ya_host_play_ply_records: 64-byte records, 4 pipelined slices -- same boards / actions / outcomes /
+    masks as the device-resident fused ply (ragged batch so slices and superblocks are uneven)."""
+    import ctypes
+    from nypc_yacht_auction_b200 import _lib
+    lib = _lib.load()
+    n, seed, base = 1003, 21, 300
+    dev_env = _engine(n, seed, base)
+    dmask = torch.empty((n, 3226), dtype=torch.uint8, device="cuda")
+    h = ctypes.c_void_p()
+    _lib.check(lib.ya_host_create(n, 1, ctypes.byref(h)), "create")
+    rec = torch.zeros((n, 16), dtype=torch.int32).pin_memory()
+    st = dev_env.states.cpu()
+    rec[:, 0:4] = st[0]
+    rec[:, 4:8] = st[1]
+    rec[:, 10] = 1
+    hm = torch.zeros((n, 3226), dtype=torch.uint8).pin_memory()
+    herr = torch.zeros(1, dtype=torch.int32)
+    for ply in range(50):
+        acts, out = dev_env.play_ply(masks=dmask, auto_reset=True)
+        _lib.check(lib.ya_host_play_ply_records(h, _lib.ptr(rec), _lib.ptr(hm), _lib.ptr(herr), seed, base, 1), "records ply")
+        st = dev_env.states.cpu()
+        assert torch.equal(rec[:, 0:4], st[0]) and torch.equal(rec[:, 4:8], st[1])
+        assert torch.equal(rec[:, 8], dev_env.episode.cpu()) and torch.equal(rec[:, 9], dev_env.ply.cpu())
+        assert torch.equal(rec[:, 10], dev_env.players.cpu().int()) and torch.equal(rec[:, 11], acts.cpu())
+        assert torch.equal(rec[:, 12].view(torch.float32), out.cpu())
+        assert torch.equal(hm, dmask.cpu())
+    assert int(herr.item()) == 0
+    lib.ya_host_destroy(h)
