@@ -79,6 +79,15 @@ int ya_random_action(const uint32_t* states, int64_t stride, const int8_t* playe
 int ya_enumerate_scores(const uint32_t* states, int64_t stride, const int8_t* players, uint8_t* scores, int64_t n,
                         void* stream);
 
+/* GreedyYachtPlayer.play (yacht/YachtPlayers.py:186-214) for the player to move of every game: greedy
+ * best-immediate-gain scoring (:134-169) and the value-gap bid heuristic (:39-129, including the bid
+ * overflow quirk).  raw (may be NULL) receives the heuristic's own choice; when that is not a legal
+ * action the reference plays a random legal move: with fallback != 0 that move is drawn on device
+ * (Philox, tag ACTION), otherwise actions[g] = -1 and the host draws it. */
+int ya_greedy_action(const uint32_t* states, int64_t stride, const int8_t* players, int32_t* actions, int32_t* raw,
+                     int64_t n, int fallback, uint64_t seed, uint64_t game_base, const uint32_t* episode,
+                     const int32_t* ply, void* stream);
+
 /* One ply of Arena.playGame (Arena.py:49-71) with RandomYachtPlayer on both sides, for n games at
  * once: legal mask written to masks (uint8[n][3226], may be NULL), action sampled, transition
  * applied in place, outcome[g] = getGameEnded(board, 1) after the move (0 while running).  With

@@ -30,6 +30,7 @@ SIGNATURES = {
     "ya_features": [_vp, _i64, _vp, _i64, _vp],
     "ya_random_action": [_vp, _i64, _vp, _vp, _i64, _u64, _u64, _vp, _vp, _vp],
     "ya_enumerate_scores": [_vp, _i64, _vp, _vp, _i64, _vp],
+    "ya_greedy_action": [_vp, _i64, _vp, _vp, _vp, _i64, _int, _u64, _u64, _vp, _vp, _vp],
     "ya_play_ply": [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _u64, _u64, _int, _vp],
     "ya_mcts_cursor_words": [],
     "ya_mcts_node_words": [],

@@ -322,6 +322,132 @@ ya_k_enumerate_scores(const uint4* __restrict__ states, int64_t stride, const in
     }
 }
 
+// ------------------------------------------------------------------ greedy heuristic player
+// GreedyYachtPlayer (yacht/YachtPlayers.py:39-214): the scoring move maximising the immediate gain
+// (score + 35000 when it crosses the upper-section bonus, first maximum wins) and the value-gap bid
+// heuristic, both on top of the same table-driven subset enumeration.  One warp per game.
+__device__ __forceinline__ void ya_greedy_best(uint32_t dice10, int nd, uint32_t used, uint32_t upper_before,
+                                               uint32_t* part, const uint16_t* smask, int lane, int& best, int& best_idx) {
+    uint32_t lo = 0, hi = 0;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+        uint32_t dl = (dice10 >> (3 * j)) & 7u, dh = (dice10 >> (3 * (j + 5))) & 7u;
+        uint32_t wl = dl ? ((1u << (4 * (dl - 1))) | (dl << 24)) : 0u;
+        uint32_t wh = dh ? ((1u << (4 * (dh - 1))) | (dh << 24)) : 0u;
+        if ((lane >> j) & 1) { lo += wl; hi += wh; }
+    }
+    __syncwarp();
+    part[lane] = lo;
+    part[32 + lane] = hi;
+    __syncwarp();
+    best = -1; best_idx = 0x7FFFFFFF;
+    for (int sub = lane; sub < YA_N_SUBSET; sub += 32) {
+        const uint32_t m = smask[sub];
+        if ((31 - __clz(m)) >= nd) continue;
+        uint32_t sc[YA_N_CAT];
+        ya_score_all(part[m & 31u] + part[32 + (m >> 5)], sc);
+#pragma unroll
+        for (int c = 0; c < YA_N_CAT; ++c) {
+            if ((used >> c) & 1u) continue;
+            int g = (int)sc[c];
+            if (c < 6 && upper_before < 63u && upper_before + sc[c] >= 63u) g += 35;   // YachtPlayers.py:158-162
+            int idx = c * YA_N_SUBSET + sub;
+            if (g > best || (g == best && idx < best_idx)) { best = g; best_idx = idx; }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        int ob = __shfl_xor_sync(0xFFFFFFFFu, best, o), oi = __shfl_xor_sync(0xFFFFFFFFu, best_idx, o);
+        if (ob > best || (ob == best && oi < best_idx)) { best = ob; best_idx = oi; }
+    }
+}
+
+__device__ __forceinline__ uint32_t ya_upper_k(uint32_t w5) {
+    uint32_t u = 0;
+#pragma unroll
+    for (int c = 0; c < 6; ++c) u += (uint32_t)(c + 1) * ((w5 >> (3 * c)) & 7u);
+    return u;
+}
+
+__global__ void __launch_bounds__(kEnumWarps * 32)
+ya_k_greedy_action(const uint4* __restrict__ states, int64_t stride, const int8_t* __restrict__ players,
+                   int32_t* __restrict__ actions, int32_t* __restrict__ raw, int64_t n, int fallback,
+                   uint64_t seed, uint64_t game_base, const uint32_t* __restrict__ episode, const int32_t* __restrict__ ply) {
+    __shared__ uint32_t part[kEnumWarps][64];
+    __shared__ uint16_t smask[YA_N_SUBSET];
+    for (int i = threadIdx.x; i < YA_N_SUBSET; i += blockDim.x) smask[i] = ya_subset_mask[i];
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t nwarps = (int64_t)gridDim.x * kEnumWarps;
+    for (int64_t g = (int64_t)blockIdx.x * kEnumWarps + warp; g < n; g += nwarps) {
+        YaState s = ya_load(states, stride, g);
+        const int pl = players[g];
+        if (pl != 1) s = ya_flip(s);                              // the players see canonical boards (Arena.py:55-56)
+        const uint32_t used = s.w[4] & 0xFFFu, upper = ya_upper_k(s.w[5]);
+        const uint32_t desc = ya_mask_desc(s, 1);
+        int a;
+        if (ya_bidding(s)) {                                       // _choose_bid, YachtPlayers.py:98-129
+            int val[2];
+            const uint32_t carry = s.w[2];
+            const int nc = ya_dice_count(carry);
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+                const uint32_t bundle = (s.w[1] >> (15 * b)) & 0x7FFFu;
+                if (ya_round(s) == 1) {                            // forward heuristic, :47-64
+                    uint32_t dice = carry | (bundle << (3 * nc));
+                    uint32_t hist, pips;
+                    ya_gather(dice, (1u << (nc + 5)) - 1u, hist, pips);
+                    int v = (int)pips;
+                    if ((hist + 0x444444u) & 0x888888u) v += 6;
+                    else if (ya_nibble_eq(hist, 3)) v += 3;
+                    if (ya_category_points_k(9, hist, pips)) v += 5;
+                    val[b] = v;
+                } else {
+                    int best, idx;
+                    const int nd = nc + 5;
+                    if (nd > 10) { val[b] = 0; continue; }
+                    ya_greedy_best(carry | (bundle << (3 * nc)), nd, used, upper, part[warp], smask, lane, best, idx);
+                    val[b] = best < 0 ? 0 : best;                   // :95 (nothing playable -> 0)
+                }
+            }
+            const int target = val[0] >= val[1] ? 0 : 1;
+            const int gap = abs(val[0] - val[1]);                  // thousands
+            const int diff500 = ya_total_500(s.w[4], s.w[5]) - ya_total_500(s.w[6], s.w[7]);
+            // bid_k = 0.5 * (gap / 1000.0) - 0.15 * (diff / 1000.0); bid = int(max(0, min(100000, round(1000 * bid_k))))
+            const double bid_k = 0.5 * ((double)(gap * 1000) / 1000.0) - 0.15 * ((double)(diff500 * 500) / 1000.0);
+            double bid = rint(1000.0 * bid_k);                     // Python round(): half to even
+            bid = fmax(0.0, fmin(100000.0, bid));
+            a = target * YA_N_BID_LEVEL + (int)bid / 500;          // can leave 0..201: quirk Q11
+        } else {                                                   // _choose_scoring, :134-169
+            const uint32_t carry = s.w[2];
+            const int nd = ya_dice_count(carry);
+            a = 0;
+            if (nd >= 5) {
+                int best, idx;
+                ya_greedy_best(carry, nd, used, upper, part[warp], smask, lane, best, idx);
+                if (best >= 0) a = YA_N_BID + idx;
+            }
+        }
+        if (lane == 0) {
+            if (raw) raw[g] = a;
+            if (!ya_is_legal(desc, a)) {                           // :202-206 / :211-214: random legal move instead
+                if (fallback) {
+                    int count = ya_legal_count(desc);
+                    a = 0;
+                    if (count) {
+                        YaDraw d = ya_draw(seed, (uint32_t)(game_base + g), episode ? episode[g] : 0u,
+                                           ply ? (uint32_t)ply[g] : 0u, YA_TAG_ACTION, 0, 0);
+                        a = ya_nth_legal(desc, (int)__umulhi(d.pick, (uint32_t)count));
+                    }
+                } else {
+                    a = -1;                                        // the host falls back (np.random.choice, like the reference)
+                }
+            }
+            actions[g] = a;
+        }
+    }
+}
+
 // ------------------------------------------------------------------ fused ply
 // One launch = one ply of every game under the uniform random-legal policy
 // (YachtPlayers.py:174-183 + Arena.py:49-71): legal mask materialised (optional), action
@@ -518,6 +644,16 @@ int ya_enumerate_scores(const uint32_t* states, int64_t stride, const int8_t* pl
     int blocks = (int)min((int64_t)148 * 8, (n + kEnumWarps - 1) / kEnumWarps);
     ya_k_enumerate_scores<<<blocks, kEnumWarps * 32, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<const uint4*>(states), stride, players, scores, n);
+    return (int)cudaGetLastError();
+}
+
+int ya_greedy_action(const uint32_t* states, int64_t stride, const int8_t* players, int32_t* actions, int32_t* raw,
+                     int64_t n, int fallback, uint64_t seed, uint64_t game_base, const uint32_t* episode,
+                     const int32_t* ply, void* stream) {
+    if (n <= 0) return 0;
+    int blocks = (int)min((int64_t)148 * 8, (n + kEnumWarps - 1) / kEnumWarps);
+    ya_k_greedy_action<<<blocks, kEnumWarps * 32, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const uint4*>(states), stride, players, actions, raw, n, fallback, seed, game_base, episode, ply);
     return (int)cudaGetLastError();
 }
 

@@ -160,6 +160,15 @@ class BatchedYacht:
                                                 self.n, self._s()), "ya_enumerate_scores")
         return out
 
+    def greedy_actions(self, out=None, raw=None, fallback=True):
+        """GreedyYachtPlayer.play (yacht/YachtPlayers.py:186-214) for the player to move of every game."""
+        if out is None:
+            out = torch.empty(self.n, dtype=torch.int32, device=self.device)
+        _lib.check(self.lib.ya_greedy_action(_lib.ptr(self.states), self.n, _lib.ptr(self.players), _lib.ptr(out), _lib.ptr(raw),
+                                             self.n, 1 if fallback else 0, self.seed, self.game_base, _lib.ptr(self.episode),
+                                             _lib.ptr(self.ply), self._s()), "ya_greedy_action")
+        return out
+
     def play_ply(self, masks=None, auto_reset=True):
         """One fused ply under the random-legal policy (Arena.py:49-71 with RandomYachtPlayer):
         mask (optional) + sampled action + transition + outcome, one kernel launch."""
