@@ -244,6 +244,69 @@ __global__ void ya_k_random_action(const uint4* __restrict__ states, int64_t str
     actions[g] = a;
 }
 
+// ------------------------------------------------------------------ score table
+// score_category depends only on the multiset of the five dice: 252 multisets.  A multiplicative
+// perfect hash of the 24-bit face histogram ((hist * 0xB923B81B) >> 22, collision-free on the 252
+// reachable histograms, found offline) indexes a 1024-slot table holding the 12 category scores / 1000
+// as three packed words {cats 0-3, 4-7, 8-11}.  Built once per process and device by a tiny kernel.
+constexpr uint32_t kHistHashMul = 0xB923B81Bu;
+__device__ uint32_t g_score_table[3][1024];
+
+__global__ void ya_k_build_score_table() {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;          // one ordered 5-tuple per thread (7776)
+    if (t >= 7776) return;
+    uint32_t hist = 0, pips = 0;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) { uint32_t d = 1 + t % 6; t /= 6; hist += 1u << (4 * (d - 1)); pips += d; }
+    uint32_t w[3] = {0, 0, 0};
+#pragma unroll
+    for (int c = 0; c < YA_N_CAT; ++c) w[c >> 2] |= ya_category_points_k(c, hist, pips) << (8 * (c & 3));
+    uint32_t slot = (hist * kHistHashMul) >> 22;
+    g_score_table[0][slot] = w[0]; g_score_table[1][slot] = w[1]; g_score_table[2][slot] = w[2];
+}
+
+int ya_ensure_score_table(cudaStream_t stream) {
+    static bool built[64] = {};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return (int)e;
+    if (dev < 0 || dev >= 64) return (int)cudaErrorInvalidDevice;
+    if (!built[dev]) {
+        ya_k_build_score_table<<<(7776 + 255) / 256, 256, 0, stream>>>();   // stream-ordered before its first user
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return (int)e;
+        built[dev] = true;
+    }
+    return 0;
+}
+
+struct YaScoreSmem {
+    uint32_t tab[3][1024];
+    uint16_t smask[YA_N_SUBSET];
+};
+
+__device__ __forceinline__ void ya_score_smem_init(YaScoreSmem& sm, int tid, int nthr) {
+    for (int i = tid; i < 3 * 1024; i += nthr) (&sm.tab[0][0])[i] = (&g_score_table[0][0])[i];
+    for (int i = tid; i < YA_N_SUBSET; i += nthr) sm.smask[i] = ya_subset_mask[i];
+}
+
+// partial (histogram | pips << 24) sums over the dice of every 5-bit pattern: lane l serves pattern l of the
+// low half (dice 0..4) and of the high half (dice 5..9); a subset's word is part[m & 31] + part[32 + (m >> 5)]
+__device__ __forceinline__ void ya_build_parts(uint32_t dice10, uint32_t* part, int lane) {
+    uint32_t lo = 0, hi = 0;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+        uint32_t dl = (dice10 >> (3 * j)) & 7u, dh = (dice10 >> (3 * (j + 5))) & 7u;
+        uint32_t wl = dl ? ((1u << (4 * (dl - 1))) | (dl << 24)) : 0u;
+        uint32_t wh = dh ? ((1u << (4 * (dh - 1))) | (dh << 24)) : 0u;
+        if ((lane >> j) & 1) { lo += wl; hi += wh; }
+    }
+    __syncwarp();
+    part[lane] = lo;
+    part[32 + lane] = hi;
+    __syncwarp();
+}
+
 // ------------------------------------------------------------------ scoring-move enumeration
 // out[g][cat][subset] = score_category(cat, dice at subset) / 1000 for the player to move, 0
 // where the subset does not fit (YachtPlayers.py:134-169 enumerates exactly this 12 x 252 table).
@@ -255,19 +318,12 @@ __global__ void ya_k_random_action(const uint4* __restrict__ states, int64_t str
 // 189 coalesced 16-byte stores.
 constexpr int kEnumWarps = 8;
 
-__device__ __forceinline__ void ya_score_all(uint32_t w, uint32_t out[YA_N_CAT]) {
-    const uint32_t hist = w & 0xFFFFFFu, pips = w >> 24;
-#pragma unroll
-    for (int c = 0; c < 6; ++c) out[c] = (uint32_t)(c + 1) * ((hist >> (4 * c)) & 0xFu);
-    out[6] = pips;
-    out[7] = ((hist + 0x444444u) & 0x888888u) ? pips : 0u;                    // some count >= 4
-    const uint32_t e5 = ya_nibble_eq(hist, 5);
-    out[8] = ((ya_nibble_eq(hist, 2) | e5) && (ya_nibble_eq(hist, 3) | e5)) ? pips : 0u;
-    const uint32_t nz = (hist | (hist >> 1) | (hist >> 2) | (hist >> 3)) & 0x111111u;
-    const uint32_t seen = (nz & 1u) | ((nz >> 3) & 2u) | ((nz >> 6) & 4u) | ((nz >> 9) & 8u) | ((nz >> 12) & 16u) | ((nz >> 15) & 32u);
-    out[9] = (((seen & 0x0Fu) == 0x0Fu) || ((seen & 0x1Eu) == 0x1Eu) || ((seen & 0x3Cu) == 0x3Cu)) ? 15u : 0u;
-    out[10] = (((seen & 0x1Fu) == 0x1Fu) || ((seen & 0x3Eu) == 0x3Eu)) ? 30u : 0u;
-    out[11] = e5 ? 50u : 0u;
+// 4x4 byte transpose: in[k] = {b0,b1,b2,b3} of subset k  ->  out[b] = {in[0].b, in[1].b, in[2].b, in[3].b}
+__device__ __forceinline__ void ya_transpose4(const uint32_t in[4], uint32_t out[4]) {
+    uint32_t t0 = __byte_perm(in[0], in[1], 0x5140), t1 = __byte_perm(in[0], in[1], 0x7362);
+    uint32_t t2 = __byte_perm(in[2], in[3], 0x5140), t3 = __byte_perm(in[2], in[3], 0x7362);
+    out[0] = __byte_perm(t0, t2, 0x5410); out[1] = __byte_perm(t0, t2, 0x7632);
+    out[2] = __byte_perm(t1, t3, 0x5410); out[3] = __byte_perm(t1, t3, 0x7632);
 }
 
 __global__ void __launch_bounds__(kEnumWarps * 32)
@@ -275,8 +331,8 @@ ya_k_enumerate_scores(const uint4* __restrict__ states, int64_t stride, const in
                       uint8_t* __restrict__ out, int64_t n) {
     __shared__ __align__(16) uint32_t tile[kEnumWarps][YA_N_CAT * YA_N_SUBSET / 4];
     __shared__ uint32_t part[kEnumWarps][64];
-    __shared__ uint16_t smask[YA_N_SUBSET];
-    for (int i = threadIdx.x; i < YA_N_SUBSET; i += blockDim.x) smask[i] = ya_subset_mask[i];
+    __shared__ YaScoreSmem sm;
+    ya_score_smem_init(sm, threadIdx.x, blockDim.x);
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t nwarps = (int64_t)gridDim.x * kEnumWarps;
@@ -284,35 +340,26 @@ ya_k_enumerate_scores(const uint4* __restrict__ states, int64_t stride, const in
         YaState s = ya_load(states, stride, g);
         const uint32_t carry = s.w[2 + (players[g] == 1 ? 0 : 1)];
         const int nd = ya_dice_count(carry);
-        // lane l: partial sums over the dice of 5-bit pattern l, low half (dice 0..4) and high half (5..9)
-        uint32_t lo = 0, hi = 0;
-#pragma unroll
-        for (int j = 0; j < 5; ++j) {
-            uint32_t dl = (carry >> (3 * j)) & 7u, dh = (carry >> (3 * (j + 5))) & 7u;
-            uint32_t wl = dl ? ((1u << (4 * (dl - 1))) | (dl << 24)) : 0u;
-            uint32_t wh = dh ? ((1u << (4 * (dh - 1))) | (dh << 24)) : 0u;
-            if ((lane >> j) & 1) { lo += wl; hi += wh; }
-        }
-        part[warp][lane] = lo;
-        part[warp][32 + lane] = hi;
-        __syncwarp();
+        ya_build_parts(carry, part[warp], lane);
         uint32_t* t = tile[warp];
         for (int q = lane; q < YA_N_SUBSET / 4; q += 32) {          // subsets 4q .. 4q+3
-            uint32_t packed[YA_N_CAT];
-#pragma unroll
-            for (int c = 0; c < YA_N_CAT; ++c) packed[c] = 0u;
+            uint32_t w[3][4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                const uint32_t m = smask[4 * q + k];
-                if ((31 - __clz(m)) < nd) {
-                    uint32_t sc[YA_N_CAT];
-                    ya_score_all(part[warp][m & 31u] + part[warp][32 + (m >> 5)], sc);
+                const uint32_t m = sm.smask[4 * q + k];
+                const bool fits = (31 - __clz(m)) < nd;
+                const uint32_t hist = (part[warp][m & 31u] + part[warp][32 + (m >> 5)]) & 0xFFFFFFu;
+                const uint32_t slot = (hist * kHistHashMul) >> 22;
 #pragma unroll
-                    for (int c = 0; c < YA_N_CAT; ++c) packed[c] |= sc[c] << (8 * k);
-                }
+                for (int j = 0; j < 3; ++j) w[j][k] = fits ? sm.tab[j][slot] : 0u;
             }
 #pragma unroll
-            for (int c = 0; c < YA_N_CAT; ++c) t[c * (YA_N_SUBSET / 4) + q] = packed[c];
+            for (int j = 0; j < 3; ++j) {                            // categories 4j .. 4j+3
+                uint32_t o[4];
+                ya_transpose4(w[j], o);
+#pragma unroll
+                for (int b = 0; b < 4; ++b) t[(4 * j + b) * (YA_N_SUBSET / 4) + q] = o[b];
+            }
         }
         __syncwarp();
         const uint4* src = reinterpret_cast<const uint4*>(t);
@@ -327,32 +374,27 @@ ya_k_enumerate_scores(const uint4* __restrict__ states, int64_t stride, const in
 // (score + 35000 when it crosses the upper-section bonus, first maximum wins) and the value-gap bid
 // heuristic, both on top of the same table-driven subset enumeration.  One warp per game.
 __device__ __forceinline__ void ya_greedy_best(uint32_t dice10, int nd, uint32_t used, uint32_t upper_before,
-                                               uint32_t* part, const uint16_t* smask, int lane, int& best, int& best_idx) {
-    uint32_t lo = 0, hi = 0;
-#pragma unroll
-    for (int j = 0; j < 5; ++j) {
-        uint32_t dl = (dice10 >> (3 * j)) & 7u, dh = (dice10 >> (3 * (j + 5))) & 7u;
-        uint32_t wl = dl ? ((1u << (4 * (dl - 1))) | (dl << 24)) : 0u;
-        uint32_t wh = dh ? ((1u << (4 * (dh - 1))) | (dh << 24)) : 0u;
-        if ((lane >> j) & 1) { lo += wl; hi += wh; }
-    }
-    __syncwarp();
-    part[lane] = lo;
-    part[32 + lane] = hi;
-    __syncwarp();
+                                               uint32_t* part, const YaScoreSmem& sm, int lane, int& best, int& best_idx) {
+    ya_build_parts(dice10, part, lane);
     best = -1; best_idx = 0x7FFFFFFF;
     for (int sub = lane; sub < YA_N_SUBSET; sub += 32) {
-        const uint32_t m = smask[sub];
+        const uint32_t m = sm.smask[sub];
         if ((31 - __clz(m)) >= nd) continue;
-        uint32_t sc[YA_N_CAT];
-        ya_score_all(part[m & 31u] + part[32 + (m >> 5)], sc);
+        const uint32_t hist = (part[m & 31u] + part[32 + (m >> 5)]) & 0xFFFFFFu;
+        const uint32_t slot = (hist * kHistHashMul) >> 22;
 #pragma unroll
-        for (int c = 0; c < YA_N_CAT; ++c) {
-            if ((used >> c) & 1u) continue;
-            int g = (int)sc[c];
-            if (c < 6 && upper_before < 63u && upper_before + sc[c] >= 63u) g += 35;   // YachtPlayers.py:158-162
-            int idx = c * YA_N_SUBSET + sub;
-            if (g > best || (g == best && idx < best_idx)) { best = g; best_idx = idx; }
+        for (int j = 0; j < 3; ++j) {
+            const uint32_t w = sm.tab[j][slot];
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const int c = 4 * j + b;
+                if ((used >> c) & 1u) continue;
+                const uint32_t sc = (w >> (8 * b)) & 0xFFu;
+                int g = (int)sc;
+                if (c < 6 && upper_before < 63u && upper_before + sc >= 63u) g += 35;   // YachtPlayers.py:158-162
+                int idx = c * YA_N_SUBSET + sub;
+                if (g > best || (g == best && idx < best_idx)) { best = g; best_idx = idx; }
+            }
         }
     }
 #pragma unroll
@@ -374,8 +416,8 @@ ya_k_greedy_action(const uint4* __restrict__ states, int64_t stride, const int8_
                    int32_t* __restrict__ actions, int32_t* __restrict__ raw, int64_t n, int fallback,
                    uint64_t seed, uint64_t game_base, const uint32_t* __restrict__ episode, const int32_t* __restrict__ ply) {
     __shared__ uint32_t part[kEnumWarps][64];
-    __shared__ uint16_t smask[YA_N_SUBSET];
-    for (int i = threadIdx.x; i < YA_N_SUBSET; i += blockDim.x) smask[i] = ya_subset_mask[i];
+    __shared__ YaScoreSmem sm;
+    ya_score_smem_init(sm, threadIdx.x, blockDim.x);
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t nwarps = (int64_t)gridDim.x * kEnumWarps;
@@ -406,7 +448,7 @@ ya_k_greedy_action(const uint4* __restrict__ states, int64_t stride, const int8_
                     int best, idx;
                     const int nd = nc + 5;
                     if (nd > 10) { val[b] = 0; continue; }
-                    ya_greedy_best(carry | (bundle << (3 * nc)), nd, used, upper, part[warp], smask, lane, best, idx);
+                    ya_greedy_best(carry | (bundle << (3 * nc)), nd, used, upper, part[warp], sm, lane, best, idx);
                     val[b] = best < 0 ? 0 : best;                   // :95 (nothing playable -> 0)
                 }
             }
@@ -424,7 +466,7 @@ ya_k_greedy_action(const uint4* __restrict__ states, int64_t stride, const int8_
             a = 0;
             if (nd >= 5) {
                 int best, idx;
-                ya_greedy_best(carry, nd, used, upper, part[warp], smask, lane, best, idx);
+                ya_greedy_best(carry, nd, used, upper, part[warp], sm, lane, best, idx);
                 if (best >= 0) a = YA_N_BID + idx;
             }
         }
@@ -641,7 +683,9 @@ int ya_enumerate_scores(const uint32_t* states, int64_t stride, const int8_t* pl
                         void* stream) {
     if (n <= 0) return 0;
     if ((reinterpret_cast<uintptr_t>(scores) & 15u) != 0) return (int)cudaErrorMisalignedAddress;
-    int blocks = (int)min((int64_t)148 * 8, (n + kEnumWarps - 1) / kEnumWarps);
+    int rc = ya_ensure_score_table((cudaStream_t)stream);
+    if (rc) return rc;
+    int blocks = (int)min((int64_t)148 * 5, (n + kEnumWarps - 1) / kEnumWarps);
     ya_k_enumerate_scores<<<blocks, kEnumWarps * 32, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<const uint4*>(states), stride, players, scores, n);
     return (int)cudaGetLastError();
@@ -651,6 +695,8 @@ int ya_greedy_action(const uint32_t* states, int64_t stride, const int8_t* playe
                      int64_t n, int fallback, uint64_t seed, uint64_t game_base, const uint32_t* episode,
                      const int32_t* ply, void* stream) {
     if (n <= 0) return 0;
+    int rc = ya_ensure_score_table((cudaStream_t)stream);
+    if (rc) return rc;
     int blocks = (int)min((int64_t)148 * 8, (n + kEnumWarps - 1) / kEnumWarps);
     ya_k_greedy_action<<<blocks, kEnumWarps * 32, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<const uint4*>(states), stride, players, actions, raw, n, fallback, seed, game_base, episode, ply);

@@ -25,6 +25,9 @@ constexpr int kMaxDepth = 16;
 constexpr int kChunkEdges = 32;
 constexpr int kChunkWords = 114;      // [0] next, [1] pad, [2..17] idx u16 x32, [18..49] nsa u32 x32, [50..113] q f64 x32
 constexpr int kWarpsPerBlock = 4;
+#ifndef YA_MCTS_MIN_BLOCKS
+#define YA_MCTS_MIN_BLOCKS 8          // <= 64 registers: 32 resident warps per SM for the latency-bound tree walks
+#endif
 
 // node words
 enum { N_KEY = 0, N_DESC = 8, N_VISITS = 9, N_PRIOR = 10, N_EDGES = 11, N_NEDGE = 12 };
@@ -319,7 +322,7 @@ __device__ __forceinline__ void descend(const View& v, YaState cur, Walk& w, uin
 }
 
 template <bool WRITE_LEAF_STATE>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, YA_MCTS_MIN_BLOCKS)
 ya_k_mcts_select(ya_mcts_tree tree, const uint4* __restrict__ states, int64_t stride, const int8_t* __restrict__ players,
                  const int32_t* __restrict__ ply, const uint32_t* __restrict__ episode, uint64_t seed, uint64_t game_base,
                  uint32_t sim, const uint32_t* __restrict__ sim_ptr, float cpuct, const uint8_t* __restrict__ active,
@@ -545,7 +548,7 @@ ya_k_mcts_expand_logits(ya_mcts_tree tree, const __nv_bfloat16* __restrict__ log
 // BASELINE.json configs[2] (no network): nothing has to leave the SM between select and expand, so all
 // numMCTSSims simulations of a move run inside ONE launch -- one warp walks, expands and backs up its
 // game's tree num_sims times; node / row / edge data stay hot in L1/L2 across simulations.
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, YA_MCTS_MIN_BLOCKS)
 ya_k_mcts_search_uniform(ya_mcts_tree tree, const uint4* __restrict__ states, int64_t stride, const int8_t* __restrict__ players,
                          const int32_t* __restrict__ ply, const uint32_t* __restrict__ episode, uint64_t seed,
                          uint64_t game_base, int num_sims, float cpuct, float uniform_p, float uniform_v,
