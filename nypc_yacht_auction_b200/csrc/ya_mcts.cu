@@ -128,16 +128,25 @@ __device__ __forceinline__ int ucb_select(const View& v, const uint32_t* node, i
     {
         const uint4* row4 = reinterpret_cast<const uint4*>(row);
         const int nvec = L >> 2;
-#pragma unroll 4
-        for (int j = lane; j < nvec; j += 32) {
-            uint4 q = row4[j];
-            uint32_t bits[4] = {q.x, q.y, q.z, q.w};
+        constexpr int kBatch = 6;                                   // 6 x 16 B in flight per lane before first use
+        for (int j0 = lane; j0 < nvec; j0 += 32 * kBatch) {
+            uint4 q[kBatch];
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                if (bits[t] >> 31) continue;
-                float u = __fmul_rn(__fmul_rn(cpuct, __uint_as_float(bits[t])), sq_new);
-                int i = 4 * j + t;
-                if (u > best || (u == best && i < besti)) { best = u; besti = i; }
+            for (int b = 0; b < kBatch; ++b) {
+                int j = j0 + 32 * b;
+                q[b] = j < nvec ? row4[j] : make_uint4(0x80000000u, 0x80000000u, 0x80000000u, 0x80000000u);
+            }
+#pragma unroll
+            for (int b = 0; b < kBatch; ++b) {
+                const uint32_t bits[4] = {q[b].x, q[b].y, q[b].z, q[b].w};
+                const int base = 4 * (j0 + 32 * b);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    if (bits[t] >> 31) continue;                    // visited (or padding)
+                    float u = __fmul_rn(__fmul_rn(cpuct, __uint_as_float(bits[t])), sq_new);
+                    int i = base + t;
+                    if (u > best || (u == best && i < besti)) { best = u; besti = i; }
+                }
             }
         }
         int i = (nvec << 2) + lane;
@@ -371,6 +380,21 @@ __device__ __forceinline__ bool desc_valid(uint32_t desc, int i) {
     return i == YA_N_BID + YA_N_SUBSET * (r - 1);
 }
 
+// does [lo, hi) contain a legal action?  (runs: 0 = bids [0,202), r = category r-1 [202+252(r-1), +252))
+__device__ __forceinline__ bool range_has_legal(uint32_t desc, int lo, int hi) {
+    int r0 = ((lo + 50) * 4162) >> 20, r1 = ((hi - 1 + 50) * 4162) >> 20;
+    uint32_t runs = ((2u << r1) - 1u) & ~((1u << r0) - 1u);          // bits r0..r1
+    uint32_t hit = desc & runs & 0x1FFFu;
+    if (!hit) return false;
+    if ((desc >> 13) || (hit & 1u)) return true;
+    // five dice: only the first byte of each open category run is legal
+    for (uint32_t m = hit >> 1; m; m &= m - 1) {
+        int first = YA_N_BID + YA_N_SUBSET * (__ffs(m) - 1);
+        if (first >= lo && first < hi) return true;
+    }
+    return false;
+}
+
 // sum of x[i] = valid(i) ? pi[i] : 0 over i < 3226 in numpy's float32 pairwise order
 // (numpy/_core/src/umath/loops_utils.h.src: blocks of <= 128 with 8 accumulators, halves rounded
 // down to a multiple of 8).  For n = 3226 that is a perfect binary tree over 32 blocks of 96 / 104 /
@@ -391,12 +415,16 @@ __device__ __forceinline__ float masked_pairwise_sum(Load load, uint32_t desc, i
             if ((leaf >> lvl) & 1) { start += n2; n -= n2; } else { n = n2; }
         }
         int body = n - (n % 8);
-        int i = start + sub;
-        float r = desc_valid(desc, i) ? load(i) : 0.0f;
-        for (int t = 8; t < body; t += 8) {
-            int k = start + t + sub;
-            float x = desc_valid(desc, k) ? load(k) : 0.0f;
-            r = __fadd_rn(r, x);
+        float r = 0.0f;
+        // a block whose actions are all illegal sums to exactly +0: skip it (bid rows touch 3 of 32 blocks)
+        if (range_has_legal(desc, start, start + n)) {
+            int i = start + sub;
+            r = desc_valid(desc, i) ? load(i) : 0.0f;
+            for (int t = 8; t < body; t += 8) {
+                int k = start + t + sub;
+                float x = desc_valid(desc, k) ? load(k) : 0.0f;
+                r = __fadd_rn(r, x);
+            }
         }
         // ((r0+r1)+(r2+r3)) + ((r4+r5)+(r6+r7))
         r = __fadd_rn(r, __shfl_xor_sync(0xFFFFFFFFu, r, 1));
@@ -491,11 +519,27 @@ ya_k_mcts_expand_logits(ya_mcts_tree tree, const __nv_bfloat16* __restrict__ log
         const uint4* lg4 = reinterpret_cast<const uint4*>(lg);          // ld * 2 B is a multiple of 16 (checked on the host)
         constexpr int kVec = YA_N_ACTION / 8;                          // 403 full vectors + 2 trailing logits
         float mx = -CUDART_INF_F;
-        for (int j = lane; j < kVec; j += 32) {
-            uint4 q = lg4[j];
-            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+        {
+            constexpr int kRounds = (kVec + 31) / 32;                   // 13: the whole row is requested before first use
+            uint4 q[kRounds];
 #pragma unroll
-            for (int t = 0; t < 4; ++t) { float2 f = __bfloat1622float2(h[t]); e[8 * j + 2 * t] = f.x; e[8 * j + 2 * t + 1] = f.y; mx = fmaxf(mx, fmaxf(f.x, f.y)); }
+            for (int r = 0; r < kRounds; ++r) {
+                int j = lane + 32 * r;
+                if (j < kVec) q[r] = lg4[j];
+            }
+#pragma unroll
+            for (int r = 0; r < kRounds; ++r) {
+                int j = lane + 32 * r;
+                if (j < kVec) {
+                    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q[r]);
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        float2 f = __bfloat1622float2(h[t]);
+                        e[8 * j + 2 * t] = f.x; e[8 * j + 2 * t + 1] = f.y;
+                        mx = fmaxf(mx, fmaxf(f.x, f.y));
+                    }
+                }
+            }
         }
         if (lane < YA_N_ACTION - 8 * kVec) { float f = __bfloat162float(lg[8 * kVec + lane]); e[8 * kVec + lane] = f; mx = fmaxf(mx, f); }
 #pragma unroll
@@ -506,25 +550,23 @@ ya_k_mcts_expand_logits(ya_mcts_tree tree, const __nv_bfloat16* __restrict__ log
         for (int i = lane; i < YA_N_ACTION; i += 32) { float x = __expf(e[i] - mx); e[i] = x; den += x; }
 #pragma unroll
         for (int o = 16; o; o >>= 1) den += __shfl_xor_sync(0xFFFFFFFFu, den, o);
-        const float rden = __fdiv_rn(1.0f, den);
-        __syncwarp();
-        for (int i = lane; i < YA_N_ACTION; i += 32) e[i] = __fmul_rn(e[i], rden);
+        const float rden = __fdiv_rn(1.0f, den);                        // pi[i] = e[i] * (1 / sum)
         __syncwarp();
         // MCTS.py:88-91: mask, sum in numpy's pairwise order, renormalise (true float32 divisions)
         const float* ec = e;
-        float total = masked_pairwise_sum([ec](int i) { return ec[i]; }, desc, lane);
+        float total = masked_pairwise_sum([ec, rden](int i) { return __fmul_rn(ec[i], rden); }, desc, lane);
         float* row = reinterpret_cast<float*>(v.arena + node[N_PRIOR]);
         if (total > 0.0f) {
             if (desc & 1u) {                                           // bid row: actions 0..201
-                for (int k = lane; k < YA_N_BID; k += 32) row[k] = __fdiv_rn(e[k], total);
+                for (int k = lane; k < YA_N_BID; k += 32) row[k] = __fdiv_rn(__fmul_rn(e[k], rden), total);
             } else if (desc >> 13) {                                   // ten dice: 252 subsets per open category
                 int k0 = 0;
                 for (uint32_t open = (desc >> 1) & 0xFFFu; open; open &= open - 1, k0 += YA_N_SUBSET) {
                     const float* src = e + YA_N_BID + (__ffs(open) - 1) * YA_N_SUBSET;
-                    for (int t = lane; t < YA_N_SUBSET; t += 32) row[k0 + t] = __fdiv_rn(src[t], total);
+                    for (int t = lane; t < YA_N_SUBSET; t += 32) row[k0 + t] = __fdiv_rn(__fmul_rn(src[t], rden), total);
                 }
             } else {                                                   // five dice: subset 0 of every open category
-                for (int k = lane; k < L; k += 32) row[k] = __fdiv_rn(e[ya_nth_legal(desc, k)], total);
+                for (int k = lane; k < L; k += 32) row[k] = __fdiv_rn(__fmul_rn(e[ya_nth_legal(desc, k)], rden), total);
             }
         } else {
             float u = __fdiv_rn(1.0f, (float)L);

@@ -152,12 +152,22 @@ class FusedYachtEvaluator:
         self.w_pi, self.b_pi = w.t().contiguous(), b
         self.w_v1, self.b_v1 = bf(sd["v_head.2.weight"]).t().contiguous(), bf(sd["v_head.2.bias"])
         self.w_v2, self.b_v2 = bf(sd["v_head.4.weight"]).t().contiguous(), bf(sd["v_head.4.bias"])
-        n, h = int(max_batch), self.hidden
+        self.lib = _lib.load()
+        self.eps = 1e-5
+        self._alloc(int(max_batch), dev)
+
+    def _alloc(self, n, dev):
+        h = self.hidden
         mk = lambda *shape: torch.empty(shape, dtype=torch.bfloat16, device=dev)
         self.z, self.h, self.a, self.p, self.q = mk(n, h), mk(n, h), mk(n, h), mk(n, h), mk(n, h)
         self.logits = mk(n, self.PADDED)
-        self.lib = _lib.load()
-        self.eps = 1e-5
+
+    def with_private_buffers(self, max_batch):
+        """Same weights, own activation buffers (one instance per concurrently running game group)."""
+        import copy
+        other = copy.copy(self)
+        other._alloc(int(max_batch), self.w_in.device)
+        return other
 
     def _ln(self, mode, x, ln, out, residual=None, ln2=None, out2=None):
         _lib.check(self.lib.ya_nn_ln_act(mode, _lib.ptr(x), _lib.ptr(ln[0]), _lib.ptr(ln[1]), _lib.ptr(residual),
@@ -185,12 +195,34 @@ class FusedYachtEvaluator:
         return logits, v.float().reshape(-1).contiguous()
 
 
+class _Group:
+    """A contiguous slice of the games with its own view of the tree pool, buffers and stream."""
+
+    def __init__(self, mcts, g0, g1, evaluator, stream):
+        pool, env = mcts.pool, mcts.env
+        self.g0, self.g1, self.n = g0, g1, g1 - g0
+        self.struct = _lib.MctsTreeStruct(
+            pool.nodes[g0:g1].data_ptr(), pool.ht[g0:g1].data_ptr(), pool.arena[g0:g1].data_ptr(),
+            pool.meta[g0:g1].data_ptr(), pool.cursor[g0:g1].data_ptr(), self.n, pool.max_nodes, pool.ht_size, pool.arena_words)
+        self.ref = ctypes.byref(self.struct)
+        self.states_ptr = ctypes.c_void_p(env.states.data_ptr() + 16 * g0)     # plane stride stays env.n
+        self.players, self.ply, self.episode = env.players[g0:g1], env.ply[g0:g1], env.episode[g0:g1]
+        self.features, self.need_eval = mcts.features[g0:g1], mcts.need_eval[g0:g1]
+        self.sim_counter = torch.zeros(1, dtype=torch.int32, device=env.device)
+        self.evaluator = evaluator
+        self.stream = stream
+
+
 class BatchedMCTS:
     """numMCTSSims simulations for every game of a BatchedYacht per move, tree kept per episode
-    (Coach.py:93) and pruned at round boundaries."""
+    (Coach.py:93) and pruned at round boundaries.
+
+    With a network evaluator the games are split into `groups` independent slices whose
+    select -> forward -> expand chains run on separate streams: the latency-bound tree kernels of one
+    slice overlap the tensor-core forward of the other (games never interact, so this is exact)."""
 
     def __init__(self, env: BatchedYacht, num_sims, cpuct=1.5, evaluator=None, temp_threshold=15,
-                 arena_mb_per_game=None, max_nodes=None, want_leaf_states=False):
+                 arena_mb_per_game=None, max_nodes=None, want_leaf_states=False, groups=None):
         self.env = env
         self.lib = env.lib
         self.num_sims = int(num_sims)
@@ -207,14 +239,30 @@ class BatchedMCTS:
         self.visits = torch.zeros(n, dtype=torch.int32, device=d)
         self.err_flag = torch.zeros(1, dtype=torch.int32, device=d)
         self.picked = torch.zeros(n, dtype=torch.int32, device=d)
-        self.sim_counter = torch.zeros(1, dtype=torch.int32, device=d)
         self.sims_run = 0
         self.graph = None
         self.fuse_uniform = True        # uniform evaluator: run all simulations of a move in one kernel
+        uniform = getattr(self.evaluator, "uniform", False)
+        if groups is None:
+            groups = 1       # >1 overlaps slices on separate streams; measured gain on B200 is ~2 %, off by default
+        if want_leaf_states or uniform:
+            groups = 1
+        self.groups = []
+        per = (n + groups - 1) // groups
+        for i in range(groups):
+            g0, g1 = i * per, min(n, (i + 1) * per)
+            if g0 >= g1:
+                break
+            ev = self.evaluator
+            if i > 0 and hasattr(ev, "with_private_buffers"):
+                ev = ev.with_private_buffers(g1 - g0)
+            stream = torch.cuda.Stream(device=d) if groups > 1 else None
+            self.groups.append(_Group(self, g0, g1, ev, stream))
+        self.sim_counter = self.groups[0].sim_counter
 
     def capture_graph(self):
-        """Capture ONE simulation wave (select, evaluator forward, expand) as a CUDA graph; the
-        simulation index is a device counter the expand kernel bumps, so the same graph is replayed
+        """Capture ONE simulation wave (select, evaluator forward, expand of every group) as a CUDA graph;
+        the simulation index is a device counter the expand kernel bumps, so the same graph is replayed
         numMCTSSims times per move without any host-side launch work in between."""
         side = torch.cuda.Stream(device=self.env.device)
         side.wait_stream(torch.cuda.current_stream())
@@ -224,7 +272,8 @@ class BatchedMCTS:
                 self.simulate(None)
             for t, s0 in zip((self.pool.nodes, self.pool.ht, self.pool.meta, self.pool.cursor), snap):
                 t.copy_(s0)
-            self.sim_counter.zero_()
+            for grp in self.groups:
+                grp.sim_counter.zero_()
             self.err_flag.zero_()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize(self.env.device)
@@ -234,31 +283,43 @@ class BatchedMCTS:
         self.sims_run = 0
 
     # ------------------------------------------------------------------ one simulation wave
-    def simulate(self, sim):
+    def _simulate_group(self, grp, sim):
         env, s = self.env, _lib.current_stream()
+        leaf = self.leaf_states if len(self.groups) == 1 else None
         _lib.check(self.lib.ya_mcts_select(
-            self.pool.ref, _lib.ptr(env.states), env.n, _lib.ptr(env.players), _lib.ptr(env.ply), _lib.ptr(env.episode),
-            env.seed, env.game_base, 0 if sim is None else sim, _lib.ptr(self.sim_counter) if sim is None else None,
-            self.cpuct, None, _lib.ptr(self.features), _lib.ptr(self.need_eval),
-            _lib.ptr(self.leaf_states), _lib.ptr(self.err_flag), s), "ya_mcts_select")
-        counter = _lib.ptr(self.sim_counter) if sim is None else None
-        ev = self.evaluator
+            grp.ref, grp.states_ptr, env.n, _lib.ptr(grp.players), _lib.ptr(grp.ply), _lib.ptr(grp.episode),
+            env.seed, env.game_base + grp.g0, 0 if sim is None else sim, _lib.ptr(grp.sim_counter) if sim is None else None,
+            self.cpuct, None, _lib.ptr(grp.features), _lib.ptr(grp.need_eval),
+            _lib.ptr(leaf), _lib.ptr(self.err_flag), s), "ya_mcts_select")
+        counter = _lib.ptr(grp.sim_counter) if sim is None else None
+        ev = grp.evaluator
         if getattr(ev, "uniform", False):
-            _lib.check(self.lib.ya_mcts_expand(self.pool.ref, None, None, 1, ev.p, ev.v, counter, _lib.ptr(self.err_flag), s),
+            _lib.check(self.lib.ya_mcts_expand(grp.ref, None, None, 1, ev.p, ev.v, counter, _lib.ptr(self.err_flag), s),
                        "ya_mcts_expand")
+            return
+        pi, v = ev(grp.features, grp.need_eval, leaf)
+        assert v.dtype == torch.float32 and v.is_contiguous() and v.shape == (grp.n,)
+        if getattr(ev, "returns_logits", False):
+            assert pi.dtype == torch.bfloat16 and pi.is_contiguous() and pi.shape[0] == grp.n
+            _lib.check(self.lib.ya_mcts_expand_logits(grp.ref, _lib.ptr(pi), pi.shape[1], _lib.ptr(v), counter,
+                                                      _lib.ptr(self.err_flag), s), "ya_mcts_expand_logits")
+            return
+        assert pi.dtype == torch.float32 and pi.is_contiguous() and pi.shape == (grp.n, ACTION_SIZE)
+        _lib.check(self.lib.ya_mcts_expand(grp.ref, _lib.ptr(pi), _lib.ptr(v), 0, 0.0, 0.0, counter,
+                                           _lib.ptr(self.err_flag), s), "ya_mcts_expand")
+
+    def simulate(self, sim):
+        if len(self.groups) == 1:
+            self._simulate_group(self.groups[0], sim)
         else:
-            pi, v = ev(self.features, self.need_eval, self.leaf_states)
-            assert v.dtype == torch.float32 and v.is_contiguous() and v.shape == (env.n,)
-            if getattr(ev, "returns_logits", False):
-                assert pi.dtype == torch.bfloat16 and pi.is_contiguous() and pi.shape[0] == env.n
-                _lib.check(self.lib.ya_mcts_expand_logits(self.pool.ref, _lib.ptr(pi), pi.shape[1], _lib.ptr(v), counter,
-                                                          _lib.ptr(self.err_flag), s), "ya_mcts_expand_logits")
-                self.sims_run += env.n
-                return
-            assert pi.dtype == torch.float32 and pi.is_contiguous() and pi.shape == (env.n, ACTION_SIZE)
-            _lib.check(self.lib.ya_mcts_expand(self.pool.ref, _lib.ptr(pi), _lib.ptr(v), 0, 0.0, 0.0, counter,
-                                               _lib.ptr(self.err_flag), s), "ya_mcts_expand")
-        self.sims_run += env.n
+            cur = torch.cuda.current_stream()
+            for grp in self.groups:
+                grp.stream.wait_stream(cur)
+                with torch.cuda.stream(grp.stream):
+                    self._simulate_group(grp, sim)
+            for grp in self.groups:
+                cur.wait_stream(grp.stream)
+        self.sims_run += self.env.n
 
     def search(self):
         """getActionProb's simulation loop (MCTS.py:37-38) for every game."""
@@ -272,7 +333,8 @@ class BatchedMCTS:
             self.sims_run += env.n * self.num_sims
             return
         if self.graph is not None:
-            self.sim_counter.zero_()
+            for grp in self.groups:
+                grp.sim_counter.zero_()
             for _ in range(self.num_sims):
                 self.graph.replay()
             self.sims_run += self.env.n * self.num_sims

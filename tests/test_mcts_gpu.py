@@ -287,3 +287,30 @@ def test_ln_act_kernel_modes_vs_torch():
     assert torch.allclose(out2.float(), F.silu(ln(xf, g2, b2)), rtol=2 ** -7, atol=2e-3)
     assert lib.ya_nn_ln_act(0, _lib.ptr(x), _lib.ptr(g1), _lib.ptr(b1), None, None, None, _lib.ptr(out), None, n, 128, 1e-5,
                             _lib.current_stream()) != 0            # unsupported width is refused, not mis-computed
+
+
+def test_grouped_streams_give_identical_trees():
+    """Splitting the games into two groups on two streams (overlap of tree kernels and forward) must not
+    change anything: same counts and actions as the single-group run, eager and under CUDA-graph replay."""
+    from nypc_yacht_auction_b200.mcts import BatchedMCTS, FusedYachtEvaluator
+    from nypc_yacht_auction_b200.nnet import YachtPolicyValueNet
+    torch.manual_seed(1)
+    net = YachtPolicyValueNet().cuda().eval()
+    n, sims = 96, 12
+    results = []
+    for groups, graph in ((1, False), (2, False), (3, True)):
+        env = _engine(n, 5, 900)
+        mcts = BatchedMCTS(env, sims, 1.5, evaluator=FusedYachtEvaluator(net, n), groups=groups)
+        if graph:
+            mcts.capture_graph()
+        trace = []
+        for ply in range(7):
+            mcts.search()
+            counts, visits = mcts.root_counts()
+            trace.append((counts.cpu().clone(), visits.cpu().clone(), mcts.pick_actions().cpu().clone()))
+            env.next_state(mcts.picked)
+        mcts.check_errors()
+        results.append(trace)
+    for other in results[1:]:
+        for (c0, v0, a0), (c1, v1, a1) in zip(results[0], other):
+            assert torch.equal(c0, c1) and torch.equal(v0, v1) and torch.equal(a0, a1)
