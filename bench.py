@@ -251,6 +251,14 @@ def run_ours(args):
         cpu = {"value": r["steps_per_s"], "unit": "steps/s", "cores": r["cores"], "kind": "port",
                "sample": "%d full random-vs-random games (%d plies) in %.1f s on %d processes: oracle port of "
                          "Arena.playGame + RandomYachtPlayer" % (r["games"], r["steps"], r["seconds"], r["cores"])}
+        try:                                  # context only: the same workload in plain C (OpenMP), not the reference's cost
+            from oracle import c_oracle
+            t0 = time.perf_counter()
+            c_steps = c_oracle.timed_steps(400000, PLIES_PER_GAME, args.seed)
+            cpu["c_oracle_steps_per_s"] = c_steps / (time.perf_counter() - t0)
+        except Exception as exc:              # noqa: BLE001 -- the C oracle is optional test infrastructure
+            cpu["c_oracle_steps_per_s"] = None
+            cpu["c_oracle_error"] = str(exc)[:100]
 
     if rank == 0:
         clocks = sampler.summary()
