@@ -113,3 +113,48 @@ class BatchedSelfPlay:
         pi = torch.zeros(shape + (ACTION_SIZE,), dtype=torch.float64, device=actions.device)
         pi.scatter_add_(-1, actions.long() & 0xFFFF, counts.double())
         return pi / pi.sum(-1, keepdim=True)
+
+
+class BatchedArena:
+    """The arena gate of Coach.learn (Coach.py:118-126, Arena.playGames Arena.py:95-130) for two MCTS
+    populations: `n` games with evaluator A as player 1 and `n` games with the sides swapped, every player
+    moving greedily on its own visit counts (temp = 0: np.argmax(getActionProb(x, temp=0)), ties broken
+    uniformly).  Each side keeps its own trees, like the reference's separate pmcts / nmcts objects.
+    All games follow the same ply schedule, so at every ply one population searches a whole batch."""
+
+    PLIES = 48
+
+    def __init__(self, n, num_sims, evaluator_a, evaluator_b, cpuct=1.5, seed=0, game_base=0, device="cuda",
+                 arena_mb_per_game=None):
+        self.n = n
+        self.envs = [BatchedYacht(n, seed=seed, game_base=game_base, device=device),
+                     BatchedYacht(n, seed=seed, game_base=game_base + n, device=device)]
+        evs = (evaluator_a, evaluator_b)
+        # searchers[e][k]: the searcher of evaluator k on env e; env 0: A is player +1, env 1: B is player +1
+        self.searchers = [[BatchedMCTS(env, num_sims, cpuct, evs[k], temp_threshold=0, arena_mb_per_game=arena_mb_per_game)
+                           for k in range(2)] for env in self.envs]
+
+    def play_games(self):
+        """Returns (a_wins, b_wins, draws) over the 2n games."""
+        for t in range(self.PLIES):
+            for e, env in enumerate(self.envs):
+                mover = int(env.players[0].item())                  # identical for every game of the batch
+                k = (0 if mover == 1 else 1) ^ e                    # which evaluator owns this seat
+                m = self.searchers[e][k]
+                m.search()
+                m.root_counts()
+                env.next_state(m.pick_actions(), check=False)
+        a_wins = b_wins = draws = 0
+        for e, env in enumerate(self.envs):
+            for row in self.searchers[e]:
+                row.check_errors()
+            r = env.game_ended(players=torch.ones_like(env.players))
+            assert bool((r != 0).all())
+            p1 = int((r > 0.5).sum().item())
+            p2 = int((r < -0.5).sum().item())
+            draws += self.n - p1 - p2
+            if e == 0:
+                a_wins, b_wins = a_wins + p1, b_wins + p2
+            else:
+                a_wins, b_wins = a_wins + p2, b_wins + p1
+        return a_wins, b_wins, draws

@@ -314,3 +314,40 @@ def test_grouped_streams_give_identical_trees():
     for other in results[1:]:
         for (c0, v0, a0), (c1, v1, a1) in zip(results[0], other):
             assert torch.equal(c0, c1) and torch.equal(v0, v1) and torch.equal(a0, a1)
+
+
+def test_batched_arena_vs_oracle():
+    """BatchedArena (two searchers per game, greedy moves) against two oracle TreeSearch objects playing the
+    same games with the same Philox streams."""
+    from nypc_yacht_auction_b200.coach import BatchedArena
+    from nypc_yacht_auction_b200.mcts import UniformEvaluator
+    from oracle import philox
+    n, sims, seed, base = 3, 8, 13, 70
+
+    def oracle_game(gid, first_is_a):
+        trees = {1: mcts_oracle.TreeSearch(mcts_oracle.uniform_evaluator, sims, 1.5, seed, gid),
+                 -1: mcts_oracle.TreeSearch(mcts_oracle.uniform_evaluator, sims, 1.5, seed, gid)}
+        board = yr.new_game(philox.Draw(seed, gid, 0, 0, philox.TAG_INIT))
+        cur, ply = 1, 0
+        while yr.outcome(board, cur) == 0:
+            counts = trees[cur].root_counts(yr.canonical(board, cur), ply)
+            best = np.flatnonzero(counts == counts.max())
+            word = philox.draw_words(seed, gid, 0, ply, philox.TAG_ACTION)[3]
+            a = int(best[(word * len(best)) >> 32])
+            board, cur = yr.next_state(board, cur, a, philox.Draw(seed, gid, 0, ply, philox.TAG_REAL))
+            ply += 1
+        return yr.outcome(board, 1)
+
+    arena = BatchedArena(n, sims, UniformEvaluator(), UniformEvaluator(), seed=seed, game_base=base)
+    a, b, d = arena.play_games()
+    exp_a = exp_b = exp_d = 0
+    for e in range(2):
+        for g in range(n):
+            r = oracle_game(base + e * n + g, e == 0)
+            if abs(r) < 0.5:
+                exp_d += 1
+            elif (r > 0) == (e == 0):
+                exp_a += 1
+            else:
+                exp_b += 1
+    assert (a, b, d) == (exp_a, exp_b, exp_d) and a + b + d == 2 * n
