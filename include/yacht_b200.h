@@ -143,7 +143,7 @@ int ya_mcts_select(const ya_mcts_tree* tree, const uint32_t* states, int64_t str
 int ya_mcts_expand(const ya_mcts_tree* tree, const float* pi, const float* value, int uniform, float uniform_p,
                    float uniform_v, uint32_t* sim_counter, int32_t* err_flag, void* stream);
 
-/* Same as ya_mcts_expand, fed with the raw policy-head output: bf16 logits [n][ld] (ld >= 3226 and a multiple of 8,
+/* Same as ya_mcts_expand, fed with the raw policy-head output: bf16 logits [n][ld] (ld >= 3232 and a multiple of 8,
  * e.g. the head padded to 3232 columns for an aligned GEMM; base 16-byte aligned).  pi = exp(l - max) / sum(exp(l - max)) in float32
  * (the softmax of NNetWrapper.predict, yacht/NNet.py:193), masking and renormalisation are fused in
  * the kernel, so neither float32 logits nor pi are ever written to HBM. */

@@ -416,13 +416,20 @@ __device__ __forceinline__ float masked_pairwise_sum(Load load, uint32_t desc, i
         }
         int body = n - (n % 8);
         float r = 0.0f;
+        // A block (<= 106 actions) spans at most two runs of the mask.  For bid / ten-dice rows a run is
+        // all-legal or all-illegal: validity is one compare against the run boundary.
+        const bool simple = (desc & 1u) || (desc >> 13);
+        const int r0 = ((start + 50) * 4162) >> 20;
+        const int bnd = 202 + 252 * r0;
+        const bool v0 = (desc >> r0) & 1u, v1 = (desc >> (r0 + 1)) & 1u & (r0 < 12);
+        auto valid = [&](int k) { return simple ? (k < bnd ? v0 : v1) : desc_valid(desc, k); };
         // a block whose actions are all illegal sums to exactly +0: skip it (bid rows touch 3 of 32 blocks)
         if (range_has_legal(desc, start, start + n)) {
             int i = start + sub;
-            r = desc_valid(desc, i) ? load(i) : 0.0f;
+            r = valid(i) ? load(i) : 0.0f;
             for (int t = 8; t < body; t += 8) {
                 int k = start + t + sub;
-                float x = desc_valid(desc, k) ? load(k) : 0.0f;
+                float x = valid(k) ? load(k) : 0.0f;
                 r = __fadd_rn(r, x);
             }
         }
@@ -431,7 +438,7 @@ __device__ __forceinline__ float masked_pairwise_sum(Load load, uint32_t desc, i
         r = __fadd_rn(r, __shfl_xor_sync(0xFFFFFFFFu, r, 2));
         r = __fadd_rn(r, __shfl_xor_sync(0xFFFFFFFFu, r, 4));
         for (int k = start + body; k < start + n; ++k) {              // the n % 8 leftovers, in order
-            float x = desc_valid(desc, k) ? load(k) : 0.0f;
+            float x = valid(k) ? load(k) : 0.0f;
             r = __fadd_rn(r, x);
         }
         // lane `leaf` keeps block `leaf`
@@ -497,15 +504,17 @@ ya_k_mcts_expand(ya_mcts_tree tree, const float* __restrict__ pi_all, const floa
 }
 
 // bf16 logits [n][ld] straight from the policy-head GEMM: softmax (float32: exp(l - max) / sum), mask and
-// renormalisation fused, so neither float32 logits nor pi ever touch HBM.  exp(l - max) of all 3226
-// actions is staged once in shared memory (12.9 KB per warp) and reused by the pairwise sum and the row write.
+// renormalisation fused, so neither float32 logits nor pi ever touch HBM.  The raw bf16 row is staged once
+// in shared memory (6.3 KB per warp -> 32 resident warps per SM); exp() is two instructions and is simply
+// re-evaluated by each pass (sum, pairwise sum, row write) with the identical expression.
 constexpr int kLogitWarps = 4;
+constexpr int kLogitCols = 3232;                                       // 404 vectors of 8 bf16
 __global__ void __launch_bounds__(kLogitWarps * 32)
 ya_k_mcts_expand_logits(ya_mcts_tree tree, const __nv_bfloat16* __restrict__ logits_all, int64_t ld,
                         const float* __restrict__ value, uint32_t* __restrict__ sim_counter, int32_t* __restrict__ err_flag) {
-    extern __shared__ __align__(16) float e_all[];
+    __shared__ __align__(16) uint16_t raw_all[kLogitWarps][kLogitCols];
     const int lane = threadIdx.x & 31;
-    float* e = e_all + (threadIdx.x >> 5) * YA_N_ACTION;
+    uint16_t* raw = raw_all[threadIdx.x >> 5];
     const int64_t g = (int64_t)blockIdx.x * kLogitWarps + (threadIdx.x >> 5);
     if (sim_counter && blockIdx.x == 0 && threadIdx.x == 0) *sim_counter += 1;
     if (g >= tree.n) return;
@@ -515,58 +524,63 @@ ya_k_mcts_expand_logits(ya_mcts_tree tree, const __nv_bfloat16* __restrict__ log
     const uint32_t desc = node[N_DESC];
     const int L = ya_legal_count(desc);
     if (L > 0) {
-        const __nv_bfloat16* lg = logits_all + g * ld;
-        const uint4* lg4 = reinterpret_cast<const uint4*>(lg);          // ld * 2 B is a multiple of 16 (checked on the host)
-        constexpr int kVec = YA_N_ACTION / 8;                          // 403 full vectors + 2 trailing logits
+        const uint4* lg4 = reinterpret_cast<const uint4*>(logits_all + g * ld);   // ld % 8 == 0, base 16-byte aligned
+        uint4* raw4 = reinterpret_cast<uint4*>(raw);
+        constexpr int kVec = kLogitCols / 8;                           // 404; vector 403 holds actions 3224, 3225 + padding
+        constexpr int kRounds = (kVec + 31) / 32;
         float mx = -CUDART_INF_F;
         {
-            constexpr int kRounds = (kVec + 31) / 32;                   // 13: the whole row is requested before first use
             uint4 q[kRounds];
 #pragma unroll
-            for (int r = 0; r < kRounds; ++r) {
-                int j = lane + 32 * r;
-                if (j < kVec) q[r] = lg4[j];
-            }
+            for (int r = 0; r < kRounds; ++r) { int j = lane + 32 * r; if (j < kVec) q[r] = lg4[j]; }   // whole row in flight
 #pragma unroll
             for (int r = 0; r < kRounds; ++r) {
                 int j = lane + 32 * r;
                 if (j < kVec) {
-                    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q[r]);
+                    raw4[j] = q[r];
+                    const uint32_t w[4] = {q[r].x, q[r].y, q[r].z, q[r].w};
 #pragma unroll
                     for (int t = 0; t < 4; ++t) {
-                        float2 f = __bfloat1622float2(h[t]);
-                        e[8 * j + 2 * t] = f.x; e[8 * j + 2 * t + 1] = f.y;
-                        mx = fmaxf(mx, fmaxf(f.x, f.y));
+                        if (8 * j + 2 * t < YA_N_ACTION) {             // both halves valid or both padding (3226 is even)
+                            mx = fmaxf(mx, fmaxf(__uint_as_float(w[t] << 16), __uint_as_float(w[t] & 0xFFFF0000u)));
+                        }
                     }
                 }
             }
         }
-        if (lane < YA_N_ACTION - 8 * kVec) { float f = __bfloat162float(lg[8 * kVec + lane]); e[8 * kVec + lane] = f; mx = fmaxf(mx, f); }
 #pragma unroll
         for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, o));
         __syncwarp();
         // softmax of the evaluator (NNetWrapper.predict, yacht/NNet.py:193): pi = exp(l - max) / sum
         float den = 0.0f;
-        for (int i = lane; i < YA_N_ACTION; i += 32) { float x = __expf(e[i] - mx); e[i] = x; den += x; }
+        for (int j = lane; j < kVec; j += 32) {
+            uint4 q = raw4[j];
+            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                if (8 * j + 2 * t < YA_N_ACTION)
+                    den += __expf(__uint_as_float(w[t] << 16) - mx) + __expf(__uint_as_float(w[t] & 0xFFFF0000u) - mx);
+            }
+        }
 #pragma unroll
         for (int o = 16; o; o >>= 1) den += __shfl_xor_sync(0xFFFFFFFFu, den, o);
-        const float rden = __fdiv_rn(1.0f, den);                        // pi[i] = e[i] * (1 / sum)
-        __syncwarp();
+        const float rden = __fdiv_rn(1.0f, den);
+        const uint16_t* rc = raw;
+        auto pi = [rc, mx, rden](int i) { return __fmul_rn(__expf(__uint_as_float((uint32_t)rc[i] << 16) - mx), rden); };
         // MCTS.py:88-91: mask, sum in numpy's pairwise order, renormalise (true float32 divisions)
-        const float* ec = e;
-        float total = masked_pairwise_sum([ec, rden](int i) { return __fmul_rn(ec[i], rden); }, desc, lane);
+        float total = masked_pairwise_sum(pi, desc, lane);
         float* row = reinterpret_cast<float*>(v.arena + node[N_PRIOR]);
         if (total > 0.0f) {
             if (desc & 1u) {                                           // bid row: actions 0..201
-                for (int k = lane; k < YA_N_BID; k += 32) row[k] = __fdiv_rn(__fmul_rn(e[k], rden), total);
+                for (int k = lane; k < YA_N_BID; k += 32) row[k] = __fdiv_rn(pi(k), total);
             } else if (desc >> 13) {                                   // ten dice: 252 subsets per open category
                 int k0 = 0;
                 for (uint32_t open = (desc >> 1) & 0xFFFu; open; open &= open - 1, k0 += YA_N_SUBSET) {
-                    const float* src = e + YA_N_BID + (__ffs(open) - 1) * YA_N_SUBSET;
-                    for (int t = lane; t < YA_N_SUBSET; t += 32) row[k0 + t] = __fdiv_rn(__fmul_rn(src[t], rden), total);
+                    const int a0 = YA_N_BID + (__ffs(open) - 1) * YA_N_SUBSET;
+                    for (int t = lane; t < YA_N_SUBSET; t += 32) row[k0 + t] = __fdiv_rn(pi(a0 + t), total);
                 }
             } else {                                                   // five dice: subset 0 of every open category
-                for (int k = lane; k < L; k += 32) row[k] = __fdiv_rn(__fmul_rn(e[ya_nth_legal(desc, k)], rden), total);
+                for (int k = lane; k < L; k += 32) row[k] = __fdiv_rn(pi(ya_nth_legal(desc, k)), total);
             }
         } else {
             float u = __fdiv_rn(1.0f, (float)L);
@@ -781,17 +795,10 @@ int ya_mcts_expand(const ya_mcts_tree* tree, const float* pi, const float* value
 
 int ya_mcts_expand_logits(const ya_mcts_tree* tree, const void* logits_bf16, int64_t ld, const float* value,
                           uint32_t* sim_counter, int32_t* err_flag, void* stream) {
-    if (!tree_ok(tree) || ld < YA_N_ACTION || (ld % 8) != 0 || (reinterpret_cast<uintptr_t>(logits_bf16) & 15u))
+    if (!tree_ok(tree) || ld < kLogitCols || (ld % 8) != 0 || (reinterpret_cast<uintptr_t>(logits_bf16) & 15u))
         return (int)cudaErrorInvalidValue;
-    constexpr size_t smem = (size_t)kLogitWarps * YA_N_ACTION * sizeof(float);
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(ya_k_mcts_expand_logits, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        configured = true;
-    }
     int blocks = (int)((tree->n + kLogitWarps - 1) / kLogitWarps);
-    ya_k_mcts_expand_logits<<<blocks, kLogitWarps * 32, smem, (cudaStream_t)stream>>>(
+    ya_k_mcts_expand_logits<<<blocks, kLogitWarps * 32, 0, (cudaStream_t)stream>>>(
         *tree, static_cast<const __nv_bfloat16*>(logits_bf16), ld, value, sim_counter, err_flag);
     return (int)cudaGetLastError();
 }
