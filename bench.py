@@ -251,6 +251,11 @@ def run_ours(args):
         cpu = {"value": r["steps_per_s"], "unit": "steps/s", "cores": r["cores"], "kind": "port",
                "sample": "%d full random-vs-random games (%d plies) in %.1f s on %d processes: oracle port of "
                          "Arena.playGame + RandomYachtPlayer" % (r["games"], r["steps"], r["seconds"], r["cores"])}
+        if not args.no_extras:                # CPU arm of the MCTS lines, bounded sample
+            m = arena_port.timed_mcts_sample(seed=args.seed, sims=25, budget_s=min(8.0, args.cpu_seconds))
+            cpu["mcts_uniform_sims_per_s"] = m["sims_per_s"]
+            cpu["mcts_sample"] = "oracle port of MCTS.py self-play, uniform evaluator, numMCTSSims=25, %d sims in %.1f s on %d processes" % (
+                m["sims"], m["seconds"], m["cores"])
         try:                                  # context only: the same workload in plain C (OpenMP), not the reference's cost
             from oracle import c_oracle
             t0 = time.perf_counter()

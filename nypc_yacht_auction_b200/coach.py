@@ -158,3 +158,30 @@ class BatchedArena:
             else:
                 a_wins, b_wins = a_wins + p2, b_wins + p1
         return a_wins, b_wins, draws
+
+
+def self_play_in_waves(total_games, wave_games, num_sims, evaluator, first_game=0, on_wave=None, **kwargs):
+    """BASELINE.json configs[4]: more concurrent games than one tree pool fits in HBM (1,048,576 games over
+    8 GPUs = 131,072 per GPU at ~4 MB of tree per game) are played as consecutive waves of `wave_games`
+    games on ONE pool; wave w owns global games [first_game + w*wave_games, ...), so the result is the same
+    as one huge batch (Philox streams are keyed by the global game id).  `on_wave(w, examples)` receives
+    each wave's example tensors (copy or reduce them there: the buffers are reused).  Returns the total
+    (p1_wins, p2_wins, draws)."""
+    assert total_games % wave_games == 0, "total_games must be a multiple of wave_games"
+    sp = BatchedSelfPlay(wave_games, num_sims, evaluator=evaluator, game_base=first_game, **kwargs)
+    p1 = p2 = dr = 0
+    for w in range(total_games // wave_games):
+        if w:
+            base = first_game + w * wave_games
+            sp.env.game_base = base                              # same pool, next slice of global game ids
+            sp.mcts.pool.reset()
+            sp.env.episode.zero_()
+            sp.env.reset()
+        ex = sp.execute_episodes()
+        r = (ex["result_p1"] if ex is not None else sp.env.game_ended(players=torch.ones_like(sp.env.players)))
+        p1 += int((r > 0.5).sum().item())
+        p2 += int((r < -0.5).sum().item())
+        dr += int((r.abs() < 0.5).sum().item())
+        if on_wave is not None:
+            on_wave(w, ex)
+    return p1, p2, dr

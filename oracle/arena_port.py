@@ -65,3 +65,32 @@ def timed_sample(seed=0, budget_s=10.0, procs=None, games_per_proc=100000):
     # aggregate throughput: every worker ran for its own measured time
     rate = sum(r[0] / r[2] for r in res)
     return {"steps_per_s": rate, "games": games, "steps": steps, "cores": procs, "seconds": wall}
+
+
+# ---------------------------------------------------------------------------- MCTS baseline
+def _mcts_worker(args):
+    from . import mcts_oracle
+    seed, first, sims, budget_s = args
+    t0 = time.perf_counter()
+    done = plies = 0
+    g = first
+    while time.perf_counter() - t0 < budget_s:
+        trace, *_ = mcts_oracle.self_play_game(mcts_oracle.uniform_evaluator, sims, 1.5, seed, g, max_plies=12)
+        plies += len(trace)
+        done += len(trace) * sims
+        g += 1
+    return done, plies, time.perf_counter() - t0
+
+
+def timed_mcts_sample(seed=0, sims=25, budget_s=8.0, procs=None):
+    """Oracle restatement of MCTS.py self-play (uniform evaluator, numMCTSSims=sims, first 12 plies of each
+    game) on `procs` processes for about budget_s seconds.  Returns dict(sims_per_s, cores, ...)."""
+    procs = procs or os.cpu_count() or 1
+    jobs = [(seed, 1000 * i, sims, budget_s) for i in range(procs)]
+    if procs == 1:
+        res = [_mcts_worker(jobs[0])]
+    else:
+        with mp.get_context("fork").Pool(procs) as pool:
+            res = pool.map(_mcts_worker, jobs)
+    return {"sims_per_s": sum(r[0] / r[2] for r in res), "steps_per_s": sum(r[1] / r[2] for r in res), "cores": procs,
+            "sims": sum(r[0] for r in res), "seconds": max(r[2] for r in res)}

@@ -132,3 +132,24 @@ def test_batched_self_play_examples():
     for t in range(6):
         c = {int(a): int(n) for a, n in zip(out["actions"][t, 2].cpu().numpy(), out["counts"][t, 2].cpu().numpy()) if n}
         assert c == trace[t]["counts"]
+
+
+def test_waves_equal_one_big_batch():
+    """configs[4] driver: playing 3 waves of 4 games on one tree pool gives exactly the games of one batch of
+    12 (global game ids key the Philox streams), so sharding over waves / GPUs never changes results."""
+    import torch
+    from nypc_yacht_auction_b200.coach import BatchedSelfPlay, self_play_in_waves
+    big = BatchedSelfPlay(12, 6, seed=9, game_base=200)
+    ref = big.execute_episodes()
+    got = {}
+
+    def on_wave(w, ex):
+        got[w] = {k: v.clone() for k, v in ex.items()}
+    totals = self_play_in_waves(12, 4, 6, None, first_game=200, on_wave=on_wave, seed=9)
+    for w in range(3):
+        sl = slice(4 * w, 4 * w + 4)
+        assert torch.equal(got[w]["result_p1"], ref["result_p1"][sl])
+        assert torch.equal(got[w]["counts"], ref["counts"][:, sl]) and torch.equal(got[w]["actions"], ref["actions"][:, sl])
+        assert torch.equal(got[w]["features"], ref["features"][:, sl])
+    r = ref["result_p1"]
+    assert totals == (int((r > 0.5).sum()), int((r < -0.5).sum()), int((r.abs() < 0.5).sum()))
