@@ -284,8 +284,10 @@ def run_ours(args):
 
 def run_e2e(args, torch, dist, _lib, dev, rank, world, n):
     """The same 48-ply step through the host-buffer C ABI: boards live in pinned HOST memory as 64-byte
-    records; every ply copies them host->device, runs the fused ply (mask materialised in HBM, exactly
-    like the device-resident path), and copies the records (next boards, actions, outcomes) back."""
+    records; every bench step (= 48 plies = one full game per slot, like one Arena.playGames call) copies
+    them host->device, runs the 48 fused plies (mask materialised in HBM, exactly like the device-resident
+    path) and copies the records (boards, outcomes, win tallies) back.  The variant with a host round trip
+    after EVERY ply is reported next to it."""
     import ctypes
     lib = _lib.load()
     handle = ctypes.c_void_p()
@@ -300,31 +302,47 @@ def run_e2e(args, torch, dist, _lib, dev, rank, world, n):
     rec[:, 10] = 1                                           # player
     del tmp
 
-    def host_step():
+    def host_step():            # ONE host call = one bench step: 48 plies = one full game for every slot
+        _lib.check(lib.ya_host_play_plies_records(handle, _lib.ptr(rec), PLIES_PER_GAME, None, _lib.ptr(h_err),
+                                                  args.seed + 17, rank * n, 1), "ya_host_play_plies_records")
+
+    def host_step_per_ply():    # host round trip after every ply (what a host-side policy would need)
         for _ in range(PLIES_PER_GAME):
             _lib.check(lib.ya_host_play_ply_records(handle, _lib.ptr(rec), None, _lib.ptr(h_err), args.seed + 17,
                                                     rank * n, 1), "ya_host_play_ply_records")
 
-    steps = max(1, min(args.steps, 20))
-    host_step()
-    torch.cuda.synchronize(dev)
-    if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        host_step()                          # synchronous: returns after the D2H copies completed
-    dt = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([dt], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt = float(t.item())
+    def timed(fn, steps):
+        fn()
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            fn()                             # synchronous: returns after the D2H copies completed
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        return dt
+
+    steps = max(1, min(args.steps, 50))
+    dt = timed(host_step, steps)
+    finished = int(rec[:, 13].min())
+    assert finished >= steps, "every slot must have finished a game per step"
+    steps_pp = max(1, min(args.steps, 10))
+    dt_pp = timed(host_step_per_ply, steps_pp)
     assert int(h_err.item()) == 0
-    assert int(rec[:, 8].min()) >= steps                     # every slot finished >= steps games
     lib.ya_host_destroy(handle)
     return {"value": steps * PLIES_PER_GAME * n * world / dt, "unit": "steps/s",
-            "h2d_bytes_per_step": n * 64 * PLIES_PER_GAME, "d2h_bytes_per_step": (n * 64 + 4) * PLIES_PER_GAME,
-            "steps": steps, "api": "ya_host_play_ply_records (C ABI; 64-byte game records in pinned host memory, 4 slices "
-            "pipelined over 4 streams; uint8 mask materialised in HBM every ply, not copied back)",
+            "h2d_bytes_per_step": n * 64, "d2h_bytes_per_step": n * 64 + 4,
+            "steps": steps, "api": "ya_host_play_plies_records(plies=48) (C ABI): per bench step the 64-byte game records go "
+            "host->device from pinned memory, 48 fused plies run (uint8 mask materialised in HBM every ply, finished games "
+            "re-dealt and tallied), the records (boards, last actions, outcomes, win tallies) come back; 4 slices pipelined "
+            "over 4 streams",
+            "per_ply_round_trip": {"value": steps_pp * PLIES_PER_GAME * n * world / dt_pp, "unit": "steps/s",
+                                   "h2d_bytes_per_step": n * 64 * PLIES_PER_GAME, "d2h_bytes_per_step": (n * 64 + 4) * PLIES_PER_GAME,
+                                   "api": "ya_host_play_ply_records: host round trip after every ply (PCIe-bound)"},
             "timing": "host wall clock around synchronous calls, max over ranks"}
 
 

@@ -185,9 +185,12 @@ int ya_nn_ln_act(int mode, const void* x, const void* gamma, const void* beta, c
  * state buffer uses stride = n.
  *
  * Record variant: one 64-byte record per game, uint32[16] = {w0..w7 packed state, episode, ply,
- * player (+1/-1 as int32), action (out), outcome (out, float bits), 3 reserved}, so a slice of games is
+ * player (+1/-1 as int32), action of the last ply (out), outcome of the last ply (out, float bits),
+ * games finished / won by player 1 / won by player 2 (running tallies, in-out)}, so a slice of games is
  * ONE contiguous copy per direction; ya_host_play_ply_records pipelines 4 slices over 4 streams
- * (H2D, kernel, D2H overlap on the full-duplex link).  ya_play_ply_records is the device-side kernel
+ * (H2D, kernel, D2H overlap on the full-duplex link).  ya_host_play_plies_records plays `plies` plies
+ * per call (e.g. 48 = Arena.playGames for every slot: one full game each, finished games re-dealt and
+ * tallied) with a single round trip.  ya_play_ply_records is the device-side kernel
  * entry on records already in HBM.  With a context created with_masks the uint8[n][3226] mask is
  * materialised in HBM every ply (and copied to `masks` only if that pointer is not NULL). */
 int ya_host_create(int64_t n, int with_masks, void** handle);
@@ -197,6 +200,8 @@ int ya_host_play_ply(void* handle, uint32_t* states, int8_t* players, int32_t* p
                      uint64_t seed, uint64_t game_base, int auto_reset);
 int ya_host_play_ply_records(void* handle, uint32_t* records, uint8_t* masks, int32_t* err_flag,
                              uint64_t seed, uint64_t game_base, int auto_reset);
+int ya_host_play_plies_records(void* handle, uint32_t* records, int plies, uint8_t* masks, int32_t* err_flag,
+                               uint64_t seed, uint64_t game_base, int auto_reset);
 int ya_play_ply_records(uint32_t* records, uint8_t* masks, int32_t* err_flag, int64_t n, uint64_t seed,
                         uint64_t game_base, int auto_reset, void* stream);
 

@@ -47,6 +47,7 @@ SIGNATURES = {
     "ya_host_destroy": [_vp],
     "ya_host_play_ply": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _u64, _u64, _int],
     "ya_host_play_ply_records": [_vp, _vp, _vp, _vp, _u64, _u64, _int],
+    "ya_host_play_plies_records": [_vp, _vp, _int, _vp, _vp, _u64, _u64, _int],
     "ya_play_ply_records": [_vp, _vp, _vp, _i64, _u64, _u64, _int, _vp],
 }
 

@@ -555,7 +555,7 @@ ya_k_play_ply(uint4* __restrict__ states, int64_t stride, int8_t* __restrict__ p
 }
 
 // Same ply, array-of-records I/O for the host-buffer path: one 64-byte record per game
-// {w0..w7, episode, ply, player, action(out), outcome(out), 3 reserved} so a slice of games is ONE
+// {w0..w7, episode, ply, player, action(out), outcome(out), finished, P1 wins, P2 wins} so a slice is ONE
 // contiguous PCIe copy in each direction.  The mask (if requested) is still streamed to HBM.
 template <int GAMES>
 __global__ void __launch_bounds__(kThreads, 4)
@@ -569,7 +569,7 @@ ya_k_play_ply_records(uint4* __restrict__ rec, uint8_t* __restrict__ masks, int3
     if (masks) ya_mask_smem_init(sm, threadIdx.x, blockDim.x);
     for (int t = threadIdx.x; t < ng; t += blockDim.x) {
         uint4* r = rec + (g0 + t) * 4;
-        uint4 a = r[0], b = r[1], c = r[2];
+        uint4 a = r[0], b = r[1], c = r[2], tally = r[3];
         YaState s;
         s.w[0] = a.x; s.w[1] = a.y; s.w[2] = a.z; s.w[3] = a.w;
         s.w[4] = b.x; s.w[5] = b.y; s.w[6] = b.z; s.w[7] = b.w;
@@ -597,7 +597,8 @@ ya_k_play_ply_records(uint4* __restrict__ rec, uint8_t* __restrict__ masks, int3
         r[0] = make_uint4(s.w[0], s.w[1], s.w[2], s.w[3]);
         r[1] = make_uint4(s.w[4], s.w[5], s.w[6], s.w[7]);
         r[2] = make_uint4(ep, p, (uint32_t)np, (uint32_t)act);
-        r[3] = make_uint4(__float_as_uint(res), 0u, 0u, 0u);
+        if (res != 0.0f) { tally.y += 1; tally.z += res > 0.5f; tally.w += res < -0.5f; }   // finished / P1 wins / P2 wins
+        r[3] = make_uint4(__float_as_uint(res), tally.y, tally.z, tally.w);
     }
     if (masks) {
         __syncthreads();

@@ -95,15 +95,15 @@ int ya_host_play_ply(void* handle, uint32_t* states, int8_t* players, int32_t* p
     return 0;
 }
 
-int ya_host_play_ply_records(void* handle, uint32_t* records, uint8_t* masks, int32_t* err_flag,
-                             uint64_t seed, uint64_t game_base, int auto_reset) {
+int ya_host_play_plies_records(void* handle, uint32_t* records, int plies, uint8_t* masks, int32_t* err_flag,
+                               uint64_t seed, uint64_t game_base, int auto_reset) {
     HostCtx* c = static_cast<HostCtx*>(handle);
-    if (!c || !records) return (int)cudaErrorInvalidValue;
+    if (!c || !records || plies < 1) return (int)cudaErrorInvalidValue;
     const int64_t n = c->n;
     cudaError_t e;
 #define YA_TRY(x) do { e = (x); if (e != cudaSuccess) return (int)e; } while (0)
     // Games are independent: the batch is cut into kStreams slices (multiples of 8 games keep the mask
-    // rows 16-byte aligned); each slice is one H2D copy, one kernel, one D2H copy on its own stream,
+    // rows 16-byte aligned); each slice is one H2D copy, `plies` kernels, one D2H copy on its own stream,
     // so one slice's results travel back over the full-duplex link while the next slice travels in.
     const int64_t per = ((n + kStreams - 1) / kStreams + 7) & ~int64_t(7);
     uint8_t* dmasks = c->with_masks ? c->masks : nullptr;
@@ -113,9 +113,11 @@ int ya_host_play_ply_records(void* handle, uint32_t* records, uint8_t* masks, in
         const int64_t m = (g0 + per <= n) ? per : n - g0;
         cudaStream_t s = c->lanes[k];
         YA_TRY(cudaMemcpyAsync(c->records + 16 * g0, records + 16 * g0, (size_t)m * 64, cudaMemcpyHostToDevice, s));
-        int rc = ya_play_ply_records(c->records + 16 * g0, dmasks ? dmasks + g0 * YA_ACTION_SIZE : nullptr, c->err, m, seed,
-                                     game_base + (uint64_t)g0, auto_reset, s);
-        if (rc) return rc;
+        for (int p = 0; p < plies; ++p) {
+            int rc = ya_play_ply_records(c->records + 16 * g0, dmasks ? dmasks + g0 * YA_ACTION_SIZE : nullptr, c->err, m, seed,
+                                         game_base + (uint64_t)g0, auto_reset, s);
+            if (rc) return rc;
+        }
         YA_TRY(cudaMemcpyAsync(records + 16 * g0, c->records + 16 * g0, (size_t)m * 64, cudaMemcpyDeviceToHost, s));
         if (masks && dmasks) YA_TRY(cudaMemcpyAsync(masks + g0 * YA_ACTION_SIZE, dmasks + g0 * YA_ACTION_SIZE,
                                                     (size_t)m * YA_ACTION_SIZE, cudaMemcpyDeviceToHost, s));
@@ -127,6 +129,11 @@ int ya_host_play_ply_records(void* handle, uint32_t* records, uint8_t* masks, in
     }
 #undef YA_TRY
     return 0;
+}
+
+int ya_host_play_ply_records(void* handle, uint32_t* records, uint8_t* masks, int32_t* err_flag,
+                             uint64_t seed, uint64_t game_base, int auto_reset) {
+    return ya_host_play_plies_records(handle, records, 1, masks, err_flag, seed, game_base, auto_reset);
 }
 
 }  // extern "C"

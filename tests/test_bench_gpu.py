@@ -25,7 +25,8 @@ def test_bench_json_line_has_every_contract_key():
     rf = d["roofline"]
     assert rf["bound"] == "hbm" and rf["unit"] == "GB/s" and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-9
     assert rf["algorithmic_bytes_per_launch"] == 3294 * 65536
-    assert d["e2e"]["h2d_bytes_per_step"] == 65536 * 64 * 48 and d["e2e"]["value"] > 0
+    assert d["e2e"]["h2d_bytes_per_step"] == 65536 * 64 and d["e2e"]["value"] > 0
+    assert d["e2e"]["per_ply_round_trip"]["h2d_bytes_per_step"] == 65536 * 64 * 48
     assert d["value"] > 1e8
 
 

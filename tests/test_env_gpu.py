@@ -337,4 +337,13 @@ def test_record_host_abi_matches_device_path():
         assert torch.equal(rec[:, 12].view(torch.float32), out.cpu())
         assert torch.equal(hm, dmask.cpu())
     assert int(herr.item()) == 0
+    assert (rec[:, 13] == 1).all() and (rec[:, 14] + rec[:, 15] <= 1).all()      # one finished game per slot so far
+    # a multi-ply call (46 more plies = the rest of episode 1) equals 46 single-ply calls on the device path
+    _lib.check(lib.ya_host_play_plies_records(h, _lib.ptr(rec), 46, None, _lib.ptr(herr), seed, base, 1), "records plies")
+    wins = torch.zeros(2, dtype=torch.int64)
+    for ply in range(46):
+        acts, out = dev_env.play_ply(masks=None, auto_reset=True)
+    st = dev_env.states.cpu()
+    assert torch.equal(rec[:, 0:4], st[0]) and torch.equal(rec[:, 4:8], st[1]) and torch.equal(rec[:, 8], dev_env.episode.cpu())
+    assert (rec[:, 13] == 2).all() and int(herr.item()) == 0
     lib.ya_host_destroy(h)
