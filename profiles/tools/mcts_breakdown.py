@@ -1,5 +1,5 @@
 import sys, json
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__)))))
 import torch
 from nypc_yacht_auction_b200 import _lib
 from nypc_yacht_auction_b200.coach import BatchedSelfPlay
