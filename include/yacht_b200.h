@@ -177,6 +177,15 @@ int ya_nn_ln_act(int mode, const void* x, const void* gamma, const void* beta, c
                  const void* gamma2, const void* beta2, void* out, void* out2, int64_t n, int64_t hidden,
                  float eps, void* stream);
 
+/* The residual trunk of YachtNNet (yacht/pytorch/YachtNNet.py:8-21,64-66) as one persistent tcgen05 kernel:
+ * x, out: bf16 [n][256]; weight_images: `layers` x 128 KB, each the [256 out][256 in] bf16 weight of a
+ * Linear in the 128-byte-swizzled K-major image the tensor core reads (4 K-blocks of [256][64]; the 16-byte
+ * chunk c of row r is stored at chunk c ^ (r & 7)); params: float32 [layers][3][256] = bias, LayerNorm
+ * gamma, beta; kinds[l] = 1: act = LN(SiLU(act W^T + b)), 2: act = skip + LN(SiLU(act W^T + b)), skip = act
+ * (skip starts as x).  Activations stay in shared memory, the skip connection in TMEM. */
+int ya_nn_trunk(const void* x, void* out, const void* weight_images, const float* params, const int32_t* kinds,
+                int layers, int64_t n, int64_t hidden, float eps, void* stream);
+
 /* ---- host-buffer variants (end-to-end path for callers that keep boards in host memory) ----
  * ya_host_create allocates the device mirror for n games once (no allocation per call);
  * ya_host_play_ply copies the packed states and side arrays host->device, runs ya_play_ply,

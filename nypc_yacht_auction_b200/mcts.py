@@ -125,7 +125,7 @@ class FusedYachtEvaluator:
     returns_logits = True
     PADDED = 3232
 
-    def __init__(self, net, max_batch):
+    def __init__(self, net, max_batch, trunk_kernel=True):
         sd = {k: v.detach() for k, v in net.state_dict().items()}
         dev = next(net.parameters()).device
         bf = lambda t: t.to(device=dev, dtype=torch.bfloat16).contiguous()
@@ -155,6 +155,29 @@ class FusedYachtEvaluator:
         self.lib = _lib.load()
         self.eps = 1e-5
         self._alloc(int(max_batch), dev)
+        # the 2 * nblocks trunk layers for the persistent tcgen05 kernel (csrc/ya_trunk.cu)
+        self.trunk_kernel = bool(trunk_kernel) and self.nblocks > 0
+        if self.trunk_kernel:
+            images, params, kinds = [], [], []
+            for i in range(self.nblocks):
+                p = "blocks.%d." % i
+                for fc, ln, kind in (("fc1", "ln1", 1), ("fc2", "ln2", 2)):
+                    images.append(self.swizzled_weight_image(sd[p + fc + ".weight"].to(dev)))
+                    params.append(torch.stack([sd[p + fc + ".bias"], sd[p + ln + ".weight"], sd[p + ln + ".bias"]]).float())
+                    kinds.append(kind)
+            self.trunk_w = torch.cat(images).contiguous()
+            self.trunk_p = torch.stack(params).to(dev).contiguous()
+            self.trunk_kinds = torch.tensor(kinds, dtype=torch.int32, device=dev)
+
+    @staticmethod
+    def swizzled_weight_image(w):
+        """[256 out][256 in] weight -> the 128 KB shared-memory image tcgen05.mma reads: 4 K-blocks of
+        [256 rows][64 bf16], 16-byte chunk c of row r stored at chunk c ^ (r & 7) (128-byte swizzle)."""
+        w = w.to(torch.bfloat16).contiguous().view(256, 4, 8, 8)              # [row, k-block, chunk, 8 elements]
+        rows = torch.arange(256, device=w.device).view(256, 1, 1)
+        src_chunk = (torch.arange(8, device=w.device).view(1, 1, 8) ^ (rows & 7)).expand(256, 4, 8)   # position p holds chunk p ^ (r & 7)
+        img = torch.gather(w, 2, src_chunk.unsqueeze(-1).expand(256, 4, 8, 8))
+        return img.permute(1, 0, 2, 3).contiguous().view(torch.uint8).reshape(-1)                   # [k-block][row][128 B]
 
     def _alloc(self, n, dev):
         h = self.hidden
@@ -182,7 +205,12 @@ class FusedYachtEvaluator:
         x = features.to(torch.bfloat16)
         torch.addmm(self.b_in, x, self.w_in, out=z)
         self._ln(0, z, self.ln_in, h)                                     # inp: Linear -> LN -> SiLU
-        for (w1, b1, g1, be1, w2, b2, g2, be2) in self.blocks:
+        if self.trunk_kernel:                                             # all residual blocks in one tcgen05 kernel
+            _lib.check(self.lib.ya_nn_trunk(_lib.ptr(h), _lib.ptr(a), _lib.ptr(self.trunk_w), _lib.ptr(self.trunk_p),
+                                            _lib.ptr(self.trunk_kinds), 2 * self.nblocks, n, self.hidden, self.eps,
+                                            _lib.current_stream()), "ya_nn_trunk")
+            h = a
+        for (w1, b1, g1, be1, w2, b2, g2, be2) in (() if self.trunk_kernel else self.blocks):
             torch.addmm(b1, h, w1, out=z)
             self._ln(1, z, (g1, be1), a)                                  # ln1(silu(fc1(x)))
             torch.addmm(b2, a, w2, out=z)

@@ -351,3 +351,34 @@ def test_batched_arena_vs_oracle():
             else:
                 exp_b += 1
     assert (a, b, d) == (exp_a, exp_b, exp_d) and a + b + d == 2 * n
+
+
+def test_tcgen05_trunk_kernel_matches_layerwise_path():
+    """csrc/ya_trunk.cu (persistent tcgen05 kernel for all residual blocks) against the layer-by-layer path
+    (cuBLASLt GEMM + fused epilogue per layer) and the fp32 module: same bf16-level agreement, ragged row
+    count (not a multiple of the 128-row tile)."""
+    from nypc_yacht_auction_b200.mcts import FusedYachtEvaluator
+    from nypc_yacht_auction_b200.nnet import YachtPolicyValueNet
+    torch.manual_seed(2)
+    net = YachtPolicyValueNet().cuda().eval()
+    with torch.no_grad():
+        for p in net.parameters():
+            if p.ndim == 1:
+                p.add_(0.1 * torch.randn_like(p))
+    n = 1000
+    env = _engine(n, 4, 4)
+    for _ in range(9):
+        env.play_ply(masks=None, auto_reset=False)
+    x = env.features()
+    fast = FusedYachtEvaluator(net, max_batch=n, trunk_kernel=True)
+    slow = FusedYachtEvaluator(net, max_batch=n, trunk_kernel=False)
+    lf, vf = fast(x)
+    lf, vf = lf.clone(), vf.clone()
+    ls, vs = slow(x)
+    with torch.no_grad():
+        ref_logits, ref_v = net(x)
+    err_fast = (lf[:, :3226].float() - ref_logits).abs().max().item()
+    err_slow = (ls[:, :3226].float() - ref_logits).abs().max().item()
+    assert err_fast <= 1.25 * err_slow + 0.01, (err_fast, err_slow)
+    assert (vf - ref_v.reshape(-1)).abs().max().item() <= 1.25 * (vs - ref_v.reshape(-1)).abs().max().item() + 0.01
+    assert (lf[:, :3226].float() - ls[:, :3226].float()).abs().max().item() < 0.02 * ref_logits.abs().max().item()
