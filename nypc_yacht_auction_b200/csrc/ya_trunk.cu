@@ -86,8 +86,8 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
           "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
           "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
     asm volatile(
         "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
@@ -104,7 +104,14 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void proxy_fence() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-__device__ __forceinline__ float silu(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+// SiLU with ONE special-function op: x * sigmoid(x), sigmoid(x) = 0.5 * tanh(x / 2) + 0.5 (tanh.approx: 2^-11
+// relative error, far below the bf16 activations' 2^-8).  The epilogue is MUFU/issue bound, so explicit
+// FMAs are used throughout (the library is otherwise built with --fmad=false for the MCTS arithmetic).
+__device__ __forceinline__ float silu(float x) {
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
+    return x * fmaf(0.5f, t, 0.5f);
+}
 
 // byte offset of 8 consecutive bf16 (columns c8*8 .. c8*8+7) of row r inside the swizzled A tile
 __device__ __forceinline__ uint32_t a_tile_offset(int r, int c8) {
@@ -200,19 +207,25 @@ ya_k_trunk(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out,
             for (int kb = 0; kb < 4; ++kb) bulk_g2s(w_tile + kb * 32768, src + kb * 32768, 32768, &bars[0]);
         }
         // ---- pass 1: z + bias -> SiLU, row statistics, values parked back in TMEM
+        // (TMEM loads are software-pipelined: chunk c+1 is in flight while chunk c is processed)
         float s = 0.0f, ss = 0.0f;
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-            uint32_t r[32];
-            tmem_ld32(t_acc + c * 32, r);
-            const float* bias = prm + half * 128 + c * 32;
+        {
+            uint32_t buf[2][32];
+            tmem_ld32(t_acc, buf[0]);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                float v = silu(__uint_as_float(r[i]) + bias[i]);
-                s += v; ss += v * v;
-                r[i] = __float_as_uint(v);
+            for (int c = 0; c < 4; ++c) {
+                tmem_ld_wait();
+                if (c + 1 < 4) tmem_ld32(t_acc + (c + 1) * 32, buf[(c + 1) & 1]);
+                uint32_t (&r)[32] = buf[c & 1];
+                const float* bias = prm + half * 128 + c * 32;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    float v = silu(__uint_as_float(r[i]) + bias[i]);
+                    s += v; ss = fmaf(v, v, ss);
+                    r[i] = __float_as_uint(v);
+                }
+                tmem_st32(t_acc + c * 32, r);
             }
-            tmem_st32(t_acc + c * 32, r);
         }
         tmem_st_wait();
         xchg[half * kRows + row] = make_float2(s, ss);
@@ -225,31 +238,41 @@ ya_k_trunk(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out,
         const float rstd = rsqrtf(fmaxf(ss * (1.0f / kDim) - mean * mean, 0.0f) + eps);
         // ---- pass 2: LayerNorm (+ skip), bf16 into the next layer's A tile (and to HBM after the last layer)
         const bool last = l + 1 == layers;
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-            uint32_t r[32], sk[32];
-            tmem_ld32(t_acc + c * 32, r);
-            if (kind == 2) tmem_ld32(t_skip + c * 32, sk);
-            const float* gamma = prm + kDim + half * 128 + c * 32;
-            const float* beta = prm + 2 * kDim + half * 128 + c * 32;
-            uint32_t packed[16];
+        {
+            uint32_t buf[2][32], skb[2][32];
+            tmem_ld32(t_acc, buf[0]);
+            if (kind == 2) tmem_ld32(t_skip, skb[0]);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                float v = (__uint_as_float(r[i]) - mean) * rstd * gamma[i] + beta[i];
-                if (kind == 2) { v += __uint_as_float(sk[i]); sk[i] = __float_as_uint(v); }
-                r[i] = __float_as_uint(v);
-            }
+            for (int c = 0; c < 4; ++c) {
+                tmem_ld_wait();
+                if (c + 1 < 4) {
+                    tmem_ld32(t_acc + (c + 1) * 32, buf[(c + 1) & 1]);
+                    if (kind == 2) tmem_ld32(t_skip + (c + 1) * 32, skb[(c + 1) & 1]);
+                }
+                uint32_t (&r)[32] = buf[c & 1];
+                uint32_t (&sk)[32] = skb[c & 1];
+                const float* gamma = prm + kDim + half * 128 + c * 32;
+                const float* beta = prm + 2 * kDim + half * 128 + c * 32;
+                uint32_t packed[16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                __nv_bfloat162 p = __floats2bfloat162_rn(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
-                packed[i] = *reinterpret_cast<uint32_t*>(&p);
-            }
-            if (kind == 2) tmem_st32(t_skip + c * 32, sk);
+                for (int i = 0; i < 32; ++i) {
+                    const float ga = rstd * gamma[i];                  // (v - mean) * rstd * gamma + beta as two FMAs
+                    float v = fmaf(__uint_as_float(r[i]), ga, fmaf(-mean, ga, beta[i]));
+                    if (kind == 2) { v += __uint_as_float(sk[i]); sk[i] = __float_as_uint(v); }
+                    r[i] = __float_as_uint(v);
+                }
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                uint4 v = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
-                *reinterpret_cast<uint4*>(a_tile + a_tile_offset(row, half * 16 + c * 4 + q)) = v;
-                if (last && grow < n) reinterpret_cast<uint4*>(out + grow * kDim + half * 128)[c * 4 + q] = v;
+                for (int i = 0; i < 16; ++i) {
+                    __nv_bfloat162 p = __floats2bfloat162_rn(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
+                    packed[i] = *reinterpret_cast<uint32_t*>(&p);
+                }
+                if (kind == 2) tmem_st32(t_skip + c * 32, sk);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    uint4 v = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+                    *reinterpret_cast<uint4*>(a_tile + a_tile_offset(row, half * 16 + c * 4 + q)) = v;
+                    if (last && grow < n) reinterpret_cast<uint4*>(out + grow * kDim + half * 128)[c * 4 + q] = v;
+                }
             }
         }
         if (kind == 2) tmem_st_wait();
