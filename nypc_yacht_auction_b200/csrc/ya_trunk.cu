@@ -12,7 +12,7 @@
 //   * the next layer's 128 KB weight image (pre-swizzled on the host) streams in with cp.async.bulk
 //     (complete_tx on an mbarrier) while the epilogue of the current layer runs,
 //   * the epilogue reads the accumulator with tcgen05.ld (thread = row, so LayerNorm statistics need only
-//     one exchange between the two threads that share a row), applies bias + SiLU + LayerNorm
+//     one exchange between the four threads that share a row), applies bias + SiLU + LayerNorm
 //     (+ skip connection), and writes the bf16 result straight into the swizzled A tile of the next layer.
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
@@ -23,11 +23,14 @@ namespace {
 
 constexpr int kRows = 128;                 // rows per CTA = UMMA M
 constexpr int kDim = 256;                  // hidden width = UMMA N = K
-constexpr int kThreads = 256;              // 8 warps: warp w and w+4 share TMEM lanes 32*(w%4).., each takes 128 columns
+constexpr int kThreads = 512;              // 16 warps: warps w, w+4, w+8, w+12 share TMEM lanes 32*(w%4).., 64 columns each
+constexpr int kParts = kThreads / 128;     // threads per row
+constexpr int kCols = kDim / kParts;       // columns per thread
+constexpr int kChunks = kCols / 32;        // 32-column TMEM accesses per thread and pass
 constexpr int kABytes = kRows * kDim * 2;  // 64 KB
 constexpr int kWBytes = kDim * kDim * 2;   // 128 KB
 constexpr int kParamFloats = 3 * kDim;     // bias, gamma, beta
-constexpr int kSmemBytes = 1024 + kABytes + kWBytes + 2 * kParamFloats * 4 + kRows * 2 * 8 + 64;
+constexpr int kSmemBytes = 1024 + kABytes + kWBytes + 2 * kParamFloats * 4 + kRows * kParts * 8 + 64;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -104,13 +107,14 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void proxy_fence() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// SiLU with ONE special-function op: x * sigmoid(x), sigmoid(x) = 0.5 * tanh(x / 2) + 0.5 (tanh.approx: 2^-11
-// relative error, far below the bf16 activations' 2^-8).  The epilogue is MUFU/issue bound, so explicit
-// FMAs are used throughout (the library is otherwise built with --fmad=false for the MCTS arithmetic).
-__device__ __forceinline__ float silu(float x) {
+// SiLU with ONE special-function op and two FMAs: with t = x / 2, x * sigmoid(x) = t * (1 + tanh(t)) = fma(t, tanh(t), t)
+// (tanh.approx: 2^-11 relative error, far below the bf16 activations' 2^-8).  The epilogue is bound by the
+// FP32 pipe (128 lanes per SM), so explicit FMAs are used throughout (the library is otherwise built with
+// --fmad=false for the MCTS arithmetic).  `half_x` = (z + bias) / 2 comes from one FMA: fma(z, 0.5, bias / 2).
+__device__ __forceinline__ float silu_from_half(float half_x) {
     float t;
-    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
-    return x * fmaf(0.5f, t, 0.5f);
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(half_x));
+    return fmaf(half_x, t, half_x);
 }
 
 // byte offset of 8 consecutive bf16 (columns c8*8 .. c8*8+7) of row r inside the swizzled A tile
@@ -128,13 +132,13 @@ ya_k_trunk(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out,
     uint8_t* a_tile = base;                                   // 64 KB, 1024-aligned
     uint8_t* w_tile = base + kABytes;                         // 128 KB, 1024-aligned
     float* prm_all = reinterpret_cast<float*>(w_tile + kWBytes);         // 2 x (bias | gamma | beta), double-buffered per layer
-    float2* xchg = reinterpret_cast<float2*>(prm_all + 2 * kParamFloats);  // [2][128] partial (sum, sumsq)
-    uint64_t* bars = reinterpret_cast<uint64_t*>(xchg + 2 * kRows);      // [0] weights landed, [1] mma done
+    float2* xchg = reinterpret_cast<float2*>(prm_all + 2 * kParamFloats);  // [kParts][128] partial (sum, sumsq)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(xchg + kParts * kRows);  // [0] weights landed, [1] mma done
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int row = (warp & 3) * 32 + lane;                   // TMEM lane = row of the tile
-    const int half = warp >> 2;                               // which 128 columns this thread owns
+    const int half = warp >> 2;                               // which kCols-wide column slice this thread owns
     const int64_t grow = (int64_t)blockIdx.x * kRows + row;
 
     if (tid == 0) {
@@ -150,24 +154,25 @@ ya_k_trunk(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out,
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    const uint32_t t_acc = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(half * 128);
+    const uint32_t t_acc = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(half * kCols);
     const uint32_t t_skip = t_acc + 256;
 
-    // first weight image
+    // first weight image + its bias / gamma / beta (one transaction barrier for both)
     if (tid == 0) {
-        mbar_expect_tx(&bars[0], kWBytes);
+        mbar_expect_tx(&bars[0], kWBytes + kParamFloats * 4);
         for (int kb = 0; kb < 4; ++kb) bulk_g2s(w_tile + kb * 32768, wimg + kb * 32768, 32768, &bars[0]);
+        bulk_g2s(prm_all, params, kParamFloats * 4, &bars[0]);
     }
     // prologue: my half row of the input -> swizzled A tile (bf16) and skip connection (float32, TMEM)
     {
-        const uint4* src = reinterpret_cast<const uint4*>(x + grow * kDim + half * 128);
+        const uint4* src = reinterpret_cast<const uint4*>(x + grow * kDim + half * kCols);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {                          // 4 chunks of 32 columns
+        for (int c = 0; c < kChunks; ++c) {                    // chunks of 32 columns
             uint32_t f[32];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 uint4 v = grow < n ? src[c * 4 + q] : make_uint4(0, 0, 0, 0);
-                *reinterpret_cast<uint4*>(a_tile + a_tile_offset(row, half * 16 + c * 4 + q)) = v;
+                *reinterpret_cast<uint4*>(a_tile + a_tile_offset(row, half * (kCols / 8) + c * 4 + q)) = v;
                 const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
                 for (int t = 0; t < 4; ++t) { f[q * 8 + 2 * t] = w[t] << 16; f[q * 8 + 2 * t + 1] = w[t] & 0xFFFF0000u; }
@@ -180,13 +185,12 @@ ya_k_trunk(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out,
     uint32_t w_phase = 0, m_phase = 0;
     for (int l = 0; l < layers; ++l) {
         const int kind = kinds[l];
-        float* prm = prm_all + (l & 1) * kParamFloats;       // slower threads may still read the other buffer (layer l-1)
-        for (int i = tid; i < kParamFloats; i += kThreads) prm[i] = params[(int64_t)l * kParamFloats + i];
+        const float* prm = prm_all + (l & 1) * kParamFloats;  // double-buffered: layer l+1's copy lands in the other half
         proxy_fence();                                        // A tile written through the generic proxy
         tc_fence_before();
         __syncthreads();
+        mbar_wait(&bars[0], w_phase);                         // weights + parameters of layer l have landed (all threads observe it)
         if (tid == 0) {
-            mbar_wait(&bars[0], w_phase);                     // weights of layer l have landed
             tc_fence_after();
             const uint32_t a0 = smem_u32(a_tile), b0 = smem_u32(w_tile);
 #pragma unroll
@@ -202,77 +206,72 @@ ya_k_trunk(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out,
         m_phase ^= 1;
         tc_fence_after();
         if (tid == 0 && l + 1 < layers) {                     // next layer's weights stream in under the epilogue
-            mbar_expect_tx(&bars[0], kWBytes);
+            mbar_expect_tx(&bars[0], kWBytes + kParamFloats * 4);
             const uint8_t* src = wimg + (int64_t)(l + 1) * kWBytes;
             for (int kb = 0; kb < 4; ++kb) bulk_g2s(w_tile + kb * 32768, src + kb * 32768, 32768, &bars[0]);
+            bulk_g2s(prm_all + ((l + 1) & 1) * kParamFloats, params + (int64_t)(l + 1) * kParamFloats, kParamFloats * 4, &bars[0]);
         }
         // ---- pass 1: z + bias -> SiLU, row statistics, values parked back in TMEM
         // (TMEM loads are software-pipelined: chunk c+1 is in flight while chunk c is processed)
         float s = 0.0f, ss = 0.0f;
         {
-            uint32_t buf[2][32];
-            tmem_ld32(t_acc, buf[0]);
+            float ps[4] = {0.0f, 0.0f, 0.0f, 0.0f}, pq[4] = {0.0f, 0.0f, 0.0f, 0.0f};   // 4 independent chains
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 0; c < kChunks; ++c) {
+                uint32_t r[32];
+                tmem_ld32(t_acc + c * 32, r);
                 tmem_ld_wait();
-                if (c + 1 < 4) tmem_ld32(t_acc + (c + 1) * 32, buf[(c + 1) & 1]);
-                uint32_t (&r)[32] = buf[c & 1];
-                const float* bias = prm + half * 128 + c * 32;
+                const float* bias = prm + half * kCols + c * 32;
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
-                    float v = silu(__uint_as_float(r[i]) + bias[i]);
-                    s += v; ss = fmaf(v, v, ss);
+                    float v = silu_from_half(fmaf(__uint_as_float(r[i]), 0.5f, 0.5f * bias[i]));
+                    ps[i & 3] += v; pq[i & 3] = fmaf(v, v, pq[i & 3]);
                     r[i] = __float_as_uint(v);
                 }
                 tmem_st32(t_acc + c * 32, r);
             }
+            s = (ps[0] + ps[1]) + (ps[2] + ps[3]);
+            ss = (pq[0] + pq[1]) + (pq[2] + pq[3]);
         }
         tmem_st_wait();
         xchg[half * kRows + row] = make_float2(s, ss);
         __syncthreads();
-        {
-            float2 o = xchg[(half ^ 1) * kRows + row];
+#pragma unroll
+        for (int p = 1; p < kParts; ++p) {
+            float2 o = xchg[((half + p) % kParts) * kRows + row];
             s += o.x; ss += o.y;
         }
         const float mean = s * (1.0f / kDim);
         const float rstd = rsqrtf(fmaxf(ss * (1.0f / kDim) - mean * mean, 0.0f) + eps);
         // ---- pass 2: LayerNorm (+ skip), bf16 into the next layer's A tile (and to HBM after the last layer)
         const bool last = l + 1 == layers;
-        {
-            uint32_t buf[2][32], skb[2][32];
-            tmem_ld32(t_acc, buf[0]);
-            if (kind == 2) tmem_ld32(t_skip, skb[0]);
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                tmem_ld_wait();
-                if (c + 1 < 4) {
-                    tmem_ld32(t_acc + (c + 1) * 32, buf[(c + 1) & 1]);
-                    if (kind == 2) tmem_ld32(t_skip + (c + 1) * 32, skb[(c + 1) & 1]);
-                }
-                uint32_t (&r)[32] = buf[c & 1];
-                uint32_t (&sk)[32] = skb[c & 1];
-                const float* gamma = prm + kDim + half * 128 + c * 32;
-                const float* beta = prm + 2 * kDim + half * 128 + c * 32;
-                uint32_t packed[16];
+        for (int c = 0; c < kChunks; ++c) {
+            uint32_t r[32], sk[32];
+            tmem_ld32(t_acc + c * 32, r);
+            if (kind == 2) tmem_ld32(t_skip + c * 32, sk);
+            tmem_ld_wait();
+            const float* gamma = prm + kDim + half * kCols + c * 32;
+            const float* beta = prm + 2 * kDim + half * kCols + c * 32;
+            uint32_t packed[16];
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const float ga = rstd * gamma[i];                  // (v - mean) * rstd * gamma + beta as two FMAs
-                    float v = fmaf(__uint_as_float(r[i]), ga, fmaf(-mean, ga, beta[i]));
-                    if (kind == 2) { v += __uint_as_float(sk[i]); sk[i] = __float_as_uint(v); }
-                    r[i] = __float_as_uint(v);
-                }
+            for (int i = 0; i < 32; ++i) {
+                const float ga = rstd * gamma[i];                      // (v - mean) * rstd * gamma + beta as two FMAs
+                float v = fmaf(__uint_as_float(r[i]), ga, fmaf(-mean, ga, beta[i]));
+                if (kind == 2) { v += __uint_as_float(sk[i]); sk[i] = __float_as_uint(v); }
+                r[i] = __float_as_uint(v);
+            }
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    __nv_bfloat162 p = __floats2bfloat162_rn(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
-                    packed[i] = *reinterpret_cast<uint32_t*>(&p);
-                }
-                if (kind == 2) tmem_st32(t_skip + c * 32, sk);
+            for (int i = 0; i < 16; ++i) {
+                __nv_bfloat162 p = __floats2bfloat162_rn(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
+                packed[i] = *reinterpret_cast<uint32_t*>(&p);
+            }
+            if (kind == 2) tmem_st32(t_skip + c * 32, sk);
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    uint4 v = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
-                    *reinterpret_cast<uint4*>(a_tile + a_tile_offset(row, half * 16 + c * 4 + q)) = v;
-                    if (last && grow < n) reinterpret_cast<uint4*>(out + grow * kDim + half * 128)[c * 4 + q] = v;
-                }
+            for (int q = 0; q < 4; ++q) {
+                uint4 v = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+                *reinterpret_cast<uint4*>(a_tile + a_tile_offset(row, half * (kCols / 8) + c * 4 + q)) = v;
+                if (last && grow < n) reinterpret_cast<uint4*>(out + grow * kDim + half * kCols)[c * 4 + q] = v;
             }
         }
         if (kind == 2) tmem_st_wait();
