@@ -567,20 +567,24 @@ ya_k_mcts_expand_logits(ya_mcts_tree tree, const __nv_bfloat16* __restrict__ log
         const float rden = __fdiv_rn(1.0f, den);
         const uint16_t* rc = raw;
         auto pi = [rc, mx, rden](int i) { return __fmul_rn(__expf(__uint_as_float((uint32_t)rc[i] << 16) - mx), rden); };
-        // MCTS.py:88-91: mask, sum in numpy's pairwise order, renormalise (true float32 divisions)
+        // MCTS.py:88-91: mask, sum in numpy's pairwise order, renormalise.  The evaluator's own softmax is not
+        // bit-comparable with any CPU run anyway, so the renormalisation multiplies by 1 / total (<= 1 ulp from
+        // the true quotient) instead of paying an IEEE division per legal action.
         float total = masked_pairwise_sum(pi, desc, lane);
         float* row = reinterpret_cast<float*>(v.arena + node[N_PRIOR]);
         if (total > 0.0f) {
+            const float scale = __fmul_rn(rden, __fdiv_rn(1.0f, total));
+            auto prior = [rc, mx, scale](int i) { return __fmul_rn(__expf(__uint_as_float((uint32_t)rc[i] << 16) - mx), scale); };
             if (desc & 1u) {                                           // bid row: actions 0..201
-                for (int k = lane; k < YA_N_BID; k += 32) row[k] = __fdiv_rn(pi(k), total);
+                for (int k = lane; k < YA_N_BID; k += 32) row[k] = prior(k);
             } else if (desc >> 13) {                                   // ten dice: 252 subsets per open category
                 int k0 = 0;
                 for (uint32_t open = (desc >> 1) & 0xFFFu; open; open &= open - 1, k0 += YA_N_SUBSET) {
                     const int a0 = YA_N_BID + (__ffs(open) - 1) * YA_N_SUBSET;
-                    for (int t = lane; t < YA_N_SUBSET; t += 32) row[k0 + t] = __fdiv_rn(pi(a0 + t), total);
+                    for (int t = lane; t < YA_N_SUBSET; t += 32) row[k0 + t] = prior(a0 + t);
                 }
             } else {                                                   // five dice: subset 0 of every open category
-                for (int k = lane; k < L; k += 32) row[k] = __fdiv_rn(pi(ya_nth_legal(desc, k)), total);
+                for (int k = lane; k < L; k += 32) row[k] = prior(ya_nth_legal(desc, k));
             }
         } else {
             float u = __fdiv_rn(1.0f, (float)L);
