@@ -136,6 +136,16 @@ int ya_mcts_select(const ya_mcts_tree* tree, const uint32_t* states, int64_t str
                    const uint32_t* sim_ptr, float cpuct, const uint8_t* active, float* features, uint8_t* need_eval,
                    uint32_t* leaf_states, int32_t* err_flag, void* stream);
 
+/* The same descent with the dice of in-search transitions supplied by the HOST (the reference rolls them
+ * from the global numpy / random streams through roll_five / tiebreak_uniform, yacht/YachtGame.py:154-159,
+ * so a drop-in MCTS must consume those streams at exactly the same points).  injected[g*12] as in
+ * ya_next_state.  When the chosen transition needs draws that are not marked valid the descent is parked
+ * and need_eval[g] = 0x10 | (1: tie-break needed) | (2: two dice rolls needed); call again with resume = 1
+ * and the draws filled in.  Injected draws are consumed by one transition.  need_eval[g] = 1 / 0 as above. */
+int ya_mcts_select_injected(const ya_mcts_tree* tree, const uint32_t* states, int64_t stride, const int8_t* players,
+                            uint32_t sim, float cpuct, const uint8_t* injected, int resume, float* features,
+                            uint8_t* need_eval, uint32_t* leaf_states, int32_t* err_flag, void* stream);
+
 /* Leaf expansion + backup (MCTS.py:86-115,152-164): pi is float32[n][3226] over ALL actions and
  * value float32[n], as NeuralNet.predict returns them (NeuralNet.py:27-37); with uniform != 0 every
  * leaf gets pi = uniform_p, v = uniform_v without reading memory (BASELINE.json configs[2]).

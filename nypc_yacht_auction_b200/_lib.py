@@ -36,6 +36,7 @@ SIGNATURES = {
     "ya_mcts_node_words": [],
     "ya_mcts_reset": [_vp, _vp, _vp],
     "ya_mcts_select": [_vp, _vp, _i64, _vp, _vp, _vp, _u64, _u64, _u32, _vp, ctypes.c_float, _vp, _vp, _vp, _vp, _vp, _vp],
+    "ya_mcts_select_injected": [_vp, _vp, _i64, _vp, _u32, ctypes.c_float, _vp, _int, _vp, _vp, _vp, _vp, _vp],
     "ya_mcts_expand": [_vp, _vp, _vp, _int, ctypes.c_float, ctypes.c_float, _vp, _vp, _vp],
     "ya_mcts_expand_logits": [_vp, _vp, _i64, _vp, _vp, _vp, _vp],
     "ya_mcts_search_uniform": [_vp, _vp, _i64, _vp, _vp, _vp, _u64, _u64, _int, ctypes.c_float, ctypes.c_float,

@@ -32,8 +32,8 @@ constexpr int kWarpsPerBlock = 4;
 // node words
 enum { N_KEY = 0, N_DESC = 8, N_VISITS = 9, N_PRIOR = 10, N_EDGES = 11, N_NEDGE = 12 };
 // cursor words
-enum { C_LEAF = 0, C_DEPTH = 8, C_KIND = 9, C_NODE = 10, C_PATH = 12 };
-enum { KIND_DONE = 0, KIND_NEED_EVAL = 1, KIND_ERROR = 2 };
+enum { C_LEAF = 0, C_DEPTH = 8, C_KIND = 9, C_NODE = 10, C_PENDING = 11, C_PATH = 12 };
+enum { KIND_DONE = 0, KIND_NEED_EVAL = 1, KIND_ERROR = 2, KIND_NEED_DRAW = 3 };
 // meta words
 enum { M_NODES = 0, M_TOP = 1, M_ROUND = 2 };
 // error bits (OR-ed into err_flag)
@@ -254,7 +254,7 @@ __device__ __forceinline__ bool backup_path(const View& v, int depth, Val ret, u
 
 // ---------------------------------------------------------------- select (MCTS.py:56-150)
 struct Walk {
-    uint32_t node_count, arena_top;
+    uint32_t node_count, arena_top, pending;
     int depth, kind, err, leaf_node;
     Val ret;
     YaState leaf;
@@ -276,50 +276,91 @@ __device__ __forceinline__ void prune_on_new_round(const View& v, const YaState&
 
 // One descent from the canonical root.  On return: kind == KIND_NEED_EVAL (leaf allocated, w.leaf holds its
 // state), KIND_DONE (terminal / dead end: w.ret is the value returned by the deepest call) or KIND_ERROR.
-template <bool FEATURES>
+// Dice for a transition inside search: Philox (batched engine) or injected by the host (drop-in MCTS: the
+// reference rolls in-search dice from the global numpy / random streams, yacht/YachtGame.py:154-159).
+struct DrawSource {
+    const uint8_t* inj;      // NULL = Philox; else {tie, rollA[5], rollB[5], valid bits (1 tie, 2 rolls)}
+    int resume;              // continue the descent paused at a transition that needed draws
+};
+
+// One descent from the canonical root.  On return: kind == KIND_NEED_EVAL (leaf allocated, w.leaf holds its
+// state), KIND_DONE (terminal / dead end: w.ret is the value returned by the deepest call), KIND_NEED_DRAW
+// (injected mode only: the chosen transition needs dice the host has not supplied yet; w.leaf / w.depth /
+// w.pending describe where to resume) or KIND_ERROR.
+template <bool FEATURES, bool INJECT>
 __device__ __forceinline__ void descend(const View& v, YaState cur, Walk& w, uint64_t seed, uint32_t gid, uint32_t ep,
-                                        uint32_t pl, uint32_t sim, float cpuct, float* __restrict__ feat_row, int lane) {
-    w.depth = 0; w.kind = KIND_DONE; w.err = 0; w.leaf_node = -1;
+                                        uint32_t pl, uint32_t sim, float cpuct, float* __restrict__ feat_row, int lane,
+                                        DrawSource src = DrawSource{nullptr, 0}) {
+    w.depth = 0; w.kind = KIND_DONE; w.err = 0; w.leaf_node = -1; w.pending = 0;
     w.ret.d = 0.0; w.ret.is_f32 = false;
-    for (;;) {
-        float es = ya_game_ended(cur, 1);                           // Es[s], MCTS.py:79-83
-        if (es != 0.0f) { w.ret.d = -es_as_double(es); w.ret.is_f32 = false; break; }
-        int free_slot;
-        int idx = ht_find(v, cur, &free_slot);
-        if (idx < 0) {                                               // leaf: MCTS.py:84-115 (evaluation happens outside)
-            uint32_t desc = ya_mask_desc(cur, 1);
-            int L = ya_legal_count(desc);
-            uint32_t row_at = (w.arena_top + 3u) & ~3u;             // 16-byte aligned prior rows
-            if ((int)w.node_count >= v.max_nodes) { w.err = E_NODES_FULL; w.kind = KIND_ERROR; break; }
-            if (row_at + (uint32_t)L > v.arena_words) { w.err = E_ARENA_FULL; w.kind = KIND_ERROR; break; }
-            idx = (int)w.node_count;
-            if (lane == 0) {
-                uint32_t* nd = v.nodes + (int64_t)idx * kNodeWords;
+    bool pending = false;
+    int a = 0;
+    int have = (INJECT && src.inj && src.resume) ? src.inj[11] : 0;  // draws supplied for the paused transition
+    if (INJECT && src.resume) {                                     // pick the paused transition up again
 #pragma unroll
-                for (int i = 0; i < 8; ++i) nd[N_KEY + i] = cur.w[i];
-                nd[N_DESC] = desc; nd[N_VISITS] = 0; nd[N_PRIOR] = row_at; nd[N_EDGES] = 0; nd[N_NEDGE] = 0;
-                v.ht[free_slot] = (uint16_t)(idx + 1);
+        for (int i = 0; i < 8; ++i) cur.w[i] = v.cur[C_LEAF + i];
+        w.depth = (int)v.cur[C_DEPTH];
+        a = (int)(v.cur[C_PENDING] & 0xFFFFu);
+        pending = true;
+    }
+    for (;;) {
+        if (!pending) {
+            float es = ya_game_ended(cur, 1);                       // Es[s], MCTS.py:79-83
+            if (es != 0.0f) { w.ret.d = -es_as_double(es); w.ret.is_f32 = false; break; }
+            int free_slot;
+            int idx = ht_find(v, cur, &free_slot);
+            if (idx < 0) {                                           // leaf: MCTS.py:84-115 (evaluation happens outside)
+                uint32_t desc = ya_mask_desc(cur, 1);
+                int L = ya_legal_count(desc);
+                uint32_t row_at = (w.arena_top + 3u) & ~3u;         // 16-byte aligned prior rows
+                if ((int)w.node_count >= v.max_nodes) { w.err = E_NODES_FULL; w.kind = KIND_ERROR; break; }
+                if (row_at + (uint32_t)L > v.arena_words) { w.err = E_ARENA_FULL; w.kind = KIND_ERROR; break; }
+                idx = (int)w.node_count;
+                if (lane == 0) {
+                    uint32_t* nd = v.nodes + (int64_t)idx * kNodeWords;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) nd[N_KEY + i] = cur.w[i];
+                    nd[N_DESC] = desc; nd[N_VISITS] = 0; nd[N_PRIOR] = row_at; nd[N_EDGES] = 0; nd[N_NEDGE] = 0;
+                    v.ht[free_slot] = (uint16_t)(idx + 1);
+                }
+                w.node_count += 1;
+                w.arena_top = row_at + (uint32_t)L;
+                if (FEATURES)
+                    for (int f = lane; f < YA_N_FEATURE; f += 32) feat_row[f] = ya_feature(cur, f);
+                w.leaf_node = idx;
+                w.kind = KIND_NEED_EVAL;
+                __syncwarp();
+                break;
             }
-            w.node_count += 1;
-            w.arena_top = row_at + (uint32_t)L;
-            if (FEATURES)
-                for (int f = lane; f < YA_N_FEATURE; f += 32) feat_row[f] = ya_feature(cur, f);
-            w.leaf_node = idx;
-            w.kind = KIND_NEED_EVAL;
-            __syncwarp();
-            break;
+            uint32_t* node = v.nodes + (int64_t)idx * kNodeWords;
+            uint32_t desc = node[N_DESC];
+            int L = ya_legal_count(desc);
+            if (L == 0) { w.ret.d = 0.0; w.ret.is_f32 = false; break; }    // MCTS.py:138-147: `return 0`, not negated
+            if (w.depth >= kMaxDepth) { w.err = E_DEPTH; w.kind = KIND_ERROR; break; }
+            int ai = ucb_select(v, node, L, cpuct, lane);
+            a = ya_nth_legal(desc, ai);
+            if (lane == 0) v.cur[C_PATH + w.depth] = (uint32_t)idx | ((uint32_t)ai << 16);
         }
-        uint32_t* node = v.nodes + (int64_t)idx * kNodeWords;
-        uint32_t desc = node[N_DESC];
-        int L = ya_legal_count(desc);
-        if (L == 0) { w.ret.d = 0.0; w.ret.is_f32 = false; break; }    // MCTS.py:138-147: `return 0`, not negated
-        if (w.depth >= kMaxDepth) { w.err = E_DEPTH; w.kind = KIND_ERROR; break; }
-        int ai = ucb_select(v, node, L, cpuct, lane);
-        int a = ya_nth_legal(desc, ai);
-        if (lane == 0) v.cur[C_PATH + w.depth] = (uint32_t)idx | ((uint32_t)ai << 16);
+        pending = false;
         YaDraw d;
         d.roll_a = d.roll_b = d.tie = d.pick = 0;
-        if (ya_draw_needs(cur, 1, a)) d = ya_draw(seed, gid, ep, pl, YA_TAG_SEARCH, (uint32_t)w.depth, sim);
+        const int needs = ya_draw_needs(cur, 1, a);
+        if (needs) {
+            if (!INJECT) {
+                d = ya_draw(seed, gid, ep, pl, YA_TAG_SEARCH, (uint32_t)w.depth, sim);
+            } else {
+                int missing = 0;
+                if ((needs & YA_NEED_TIE) && !(have & 1)) missing |= YA_NEED_TIE;
+                if ((needs & YA_NEED_ROLLS) && !(have & 2)) missing |= YA_NEED_ROLLS;
+                if (missing) { w.kind = KIND_NEED_DRAW; w.pending = (uint32_t)a | ((uint32_t)missing << 16); break; }
+                d.tie = src.inj[0];
+                for (int i = 0; i < 5; ++i) {
+                    d.roll_a |= (uint32_t)src.inj[1 + i] << (3 * i);
+                    d.roll_b |= (uint32_t)src.inj[6 + i] << (3 * i);
+                }
+                have = 0;                                            // injected draws are single use
+            }
+        }
         int st;
         int np = ya_transition(cur, 1, a, d, &st);                   // getNextState(canonicalBoard, 1, a), MCTS.py:149
         if (st != YA_OK) { w.err = E_RULE | (1 << st); w.kind = KIND_ERROR; break; }
@@ -330,13 +371,13 @@ __device__ __forceinline__ void descend(const View& v, YaState cur, Walk& w, uin
     __syncwarp();
 }
 
-template <bool WRITE_LEAF_STATE>
+template <bool WRITE_LEAF_STATE, bool INJECT>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, YA_MCTS_MIN_BLOCKS)
 ya_k_mcts_select(ya_mcts_tree tree, const uint4* __restrict__ states, int64_t stride, const int8_t* __restrict__ players,
                  const int32_t* __restrict__ ply, const uint32_t* __restrict__ episode, uint64_t seed, uint64_t game_base,
                  uint32_t sim, const uint32_t* __restrict__ sim_ptr, float cpuct, const uint8_t* __restrict__ active,
                  float* __restrict__ features, uint8_t* __restrict__ need_eval, uint32_t* __restrict__ leaf_states,
-                 int32_t* __restrict__ err_flag) {
+                 int32_t* __restrict__ err_flag, const uint8_t* __restrict__ injected, int resume) {
     const int lane = threadIdx.x & 31;
     if (sim_ptr) sim = *sim_ptr;                                     // CUDA-graph replay: the counter lives in HBM
     const int64_t g = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
@@ -350,8 +391,9 @@ ya_k_mcts_select(ya_mcts_tree tree, const uint4* __restrict__ states, int64_t st
     Walk w;
     w.node_count = v.meta[M_NODES];
     w.arena_top = v.meta[M_TOP];
-    if (sim == 0) prune_on_new_round(v, root, w, lane);
-    descend<true>(v, root, w, seed, gid, ep, pl, sim, cpuct, features + g * YA_N_FEATURE, lane);
+    if (sim == 0 && !(INJECT && resume)) prune_on_new_round(v, root, w, lane);
+    DrawSource src{INJECT ? injected + g * 12 : nullptr, INJECT ? resume : 0};
+    descend<true, INJECT>(v, root, w, seed, gid, ep, pl, sim, cpuct, features + g * YA_N_FEATURE, lane, src);
     if (w.kind == KIND_DONE) {
         if (!backup_path(v, w.depth, w.ret, w.arena_top, lane)) { w.err = E_ARENA_FULL; w.kind = KIND_ERROR; }
     }
@@ -361,7 +403,14 @@ ya_k_mcts_select(ya_mcts_tree tree, const uint4* __restrict__ states, int64_t st
         v.cur[C_DEPTH] = (uint32_t)w.depth;
         v.cur[C_KIND] = (uint32_t)w.kind;
         v.cur[C_NODE] = (uint32_t)w.leaf_node;
-        need_eval[g] = w.kind == KIND_NEED_EVAL ? 1 : 0;
+        uint8_t code = w.kind == KIND_NEED_EVAL ? 1 : 0;
+        if (INJECT && w.kind == KIND_NEED_DRAW) {                    // park the descent; tell the host what to draw
+            v.cur[C_PENDING] = w.pending;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v.cur[C_LEAF + i] = w.leaf.w[i];
+            code = (uint8_t)(0x10 | (((w.pending >> 16) & YA_NEED_TIE) ? 1 : 0) | (((w.pending >> 16) & YA_NEED_ROLLS) ? 2 : 0));
+        }
+        need_eval[g] = code;
         if (w.err && err_flag) atomicOr(err_flag, w.err);
         if (WRITE_LEAF_STATE && leaf_states && w.kind == KIND_NEED_EVAL) {
             uint4* o = reinterpret_cast<uint4*>(leaf_states);
@@ -628,7 +677,7 @@ ya_k_mcts_search_uniform(ya_mcts_tree tree, const uint4* __restrict__ states, in
     prune_on_new_round(v, root, w, lane);
     int err = 0;
     for (int sim = 0; sim < num_sims; ++sim) {
-        descend<false>(v, root, w, seed, gid, ep, pl, (uint32_t)sim, cpuct, nullptr, lane);
+        descend<false, false>(v, root, w, seed, gid, ep, pl, (uint32_t)sim, cpuct, nullptr, lane);
         if (w.kind == KIND_ERROR) { err = w.err; break; }
         Val ret = w.ret;
         if (w.kind == KIND_NEED_EVAL) {
@@ -775,13 +824,23 @@ int ya_mcts_select(const ya_mcts_tree* tree, const uint32_t* states, int64_t str
                    uint32_t* leaf_states, int32_t* err_flag, void* stream) {
     if (!tree_ok(tree)) return (int)cudaErrorInvalidValue;
     if (leaf_states)
-        ya_k_mcts_select<true><<<warp_blocks(tree->n), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
+        ya_k_mcts_select<true, false><<<warp_blocks(tree->n), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
             *tree, reinterpret_cast<const uint4*>(states), stride, players, ply, episode, seed, game_base, sim, sim_ptr,
-            cpuct, active, features, need_eval, leaf_states, err_flag);
+            cpuct, active, features, need_eval, leaf_states, err_flag, nullptr, 0);
     else
-        ya_k_mcts_select<false><<<warp_blocks(tree->n), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
+        ya_k_mcts_select<false, false><<<warp_blocks(tree->n), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
             *tree, reinterpret_cast<const uint4*>(states), stride, players, ply, episode, seed, game_base, sim, sim_ptr,
-            cpuct, active, features, need_eval, leaf_states, err_flag);
+            cpuct, active, features, need_eval, leaf_states, err_flag, nullptr, 0);
+    return (int)cudaGetLastError();
+}
+
+int ya_mcts_select_injected(const ya_mcts_tree* tree, const uint32_t* states, int64_t stride, const int8_t* players,
+                            uint32_t sim, float cpuct, const uint8_t* injected, int resume, float* features,
+                            uint8_t* need_eval, uint32_t* leaf_states, int32_t* err_flag, void* stream) {
+    if (!tree_ok(tree) || !injected || !leaf_states) return (int)cudaErrorInvalidValue;
+    ya_k_mcts_select<true, true><<<warp_blocks(tree->n), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
+        *tree, reinterpret_cast<const uint4*>(states), stride, players, nullptr, nullptr, 0, 0, sim, nullptr,
+        cpuct, nullptr, features, need_eval, leaf_states, err_flag, injected, resume);
     return (int)cudaGetLastError();
 }
 

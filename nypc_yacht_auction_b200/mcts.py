@@ -415,8 +415,10 @@ class MCTS:
 
     The tree lives on the GPU (one game); ``nnet.predict(canonicalBoard)`` is called on the host for
     every leaf exactly like the reference does (MCTS.py:86), so any evaluator plugs in.  Dice rolled
-    *inside* search come from the engine's Philox stream keyed by (seed, tree id, root index, sim,
-    depth) instead of the global numpy RNG (see DESIGN.md "Randomness")."""
+    *inside* search (quirk Q1) come, by default, from the same hooks and global RNG streams as the
+    reference's (args.search_dice = "hooks"): a seeded Coach.executeEpisode reproduces the reference bit
+    for bit.  args.search_dice = "philox" uses the engine's counter stream keyed by (search_seed,
+    tree_id, root index, sim, depth) instead (see DESIGN.md "Randomness")."""
 
     _next_tree_id = 0
 
@@ -431,6 +433,10 @@ class MCTS:
         sims = int(args.numMCTSSims)
         self.pool = TreePool(1, max(sims, 1), self.device,
                              arena_mb_per_game=_arg(args, "arena_mb_per_game", None), max_nodes=_arg(args, "max_nodes", None))
+        # "hooks" (default): dice rolled inside search come from game.roll_five / game.tiebreak_uniform, i.e. the
+        # global numpy / random streams, consumed exactly like the reference; "philox": the engine's counter stream
+        self.dice = str(_arg(args, "search_dice", "hooks"))
+        assert self.dice in ("hooks", "philox")
         self.seed = int(_arg(args, "search_seed", 0))
         self.tree_id = int(_arg(args, "tree_id", MCTS._next_tree_id))
         MCTS._next_tree_id += 1
@@ -446,6 +452,7 @@ class MCTS:
         self.visits = torch.zeros(1, dtype=torch.int32, device=d)
         self.pi_dev = torch.zeros((1, ACTION_SIZE), dtype=torch.float32, device=d)
         self.v_dev = torch.zeros(1, dtype=torch.float32, device=d)
+        self.d_inj = torch.zeros(12, dtype=torch.uint8, device=d)
         self.root_index = -1          # number of getActionProb calls - 1 = the "ply" of the draw counter
         self.sim_index = 0
         self._root = None
@@ -461,14 +468,40 @@ class MCTS:
         self._load_root(canonicalBoard)
         if self.root_index < 0:
             self.root_index = 0
-        self.ply.fill_(self.root_index)
         s = _lib.current_stream()
-        _lib.check(self.lib.ya_mcts_select(
-            self.pool.ref, _lib.ptr(self.states), 1, _lib.ptr(self.players), _lib.ptr(self.ply), None,
-            self.seed, self.tree_id, self.sim_index, None, float(self.args.cpuct), None, _lib.ptr(self.features),
-            _lib.ptr(self.need_eval), _lib.ptr(self.leaf_states), _lib.ptr(self.err_flag), s), "ya_mcts_select")
+        if self.dice == "philox":
+            self.ply.fill_(self.root_index)
+            _lib.check(self.lib.ya_mcts_select(
+                self.pool.ref, _lib.ptr(self.states), 1, _lib.ptr(self.players), _lib.ptr(self.ply), None,
+                self.seed, self.tree_id, self.sim_index, None, float(self.args.cpuct), None, _lib.ptr(self.features),
+                _lib.ptr(self.need_eval), _lib.ptr(self.leaf_states), _lib.ptr(self.err_flag), s), "ya_mcts_select")
+            code = int(self.need_eval.item())
+        else:
+            # in-search dice through the reference's own hooks, drawn exactly when getNextState would draw them
+            # (tie-break first, then rollA, rollB: yacht/YachtGame.py:287,298-299); the kernel parks the descent
+            # at a transition that needs draws and resumes once they are injected
+            from . import game as game_mod
+            resume = 0
+            while True:
+                _lib.check(self.lib.ya_mcts_select_injected(
+                    self.pool.ref, _lib.ptr(self.states), 1, _lib.ptr(self.players), self.sim_index, float(self.args.cpuct),
+                    _lib.ptr(self.d_inj), resume, _lib.ptr(self.features), _lib.ptr(self.need_eval),
+                    _lib.ptr(self.leaf_states), _lib.ptr(self.err_flag), s), "ya_mcts_select_injected")
+                code = int(self.need_eval.item())
+                if not code & 0x10:
+                    break
+                inj = np.zeros(12, dtype=np.uint8)
+                if code & 1:
+                    inj[0] = int(game_mod.tiebreak_uniform())
+                    inj[11] |= 1
+                if code & 2:
+                    inj[1:6] = [int(x) for x in game_mod.roll_five()]
+                    inj[6:11] = [int(x) for x in game_mod.roll_five()]
+                    inj[11] |= 2
+                self.d_inj.copy_(torch.from_numpy(inj))
+                resume = 1
         self.sim_index += 1
-        if int(self.need_eval.item()):
+        if code == 1:
             leaf = planes_to_boards(self.leaf_states.cpu().numpy().view(np.uint32))[0]
             pi, v = self.nnet.predict(leaf)                                   # MCTS.py:86
             pi = np.ascontiguousarray(np.asarray(pi, dtype=np.float32).reshape(ACTION_SIZE))

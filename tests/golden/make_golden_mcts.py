@@ -185,6 +185,28 @@ def coach_episode_case(mt_seed, sims, cpuct, temp_threshold, search_seed, tree_i
         ref_mod.roll_five, ref_mod.tiebreak_uniform = keep
 
 
+def coach_plain_case(mt_seed, sims, cpuct, temp_threshold):
+    """The reference exactly as shipped: Coach.executeEpisode seeded through YachtGame(seed); every dice roll
+    and tie-break (real moves AND inside MCTS.search) comes from the global numpy / random streams."""
+    import random
+    from Coach import Coach
+
+    class HashedNet:
+        def __init__(self, game=None, args=None):
+            pass
+
+        def predict(self, board):
+            return mcts_oracle.hashed_evaluator(to_oracle_board(board), 9)
+
+    g = YachtGame(seed=mt_seed)
+    coach = Coach(g, HashedNet(), dotdict({"numMCTSSims": sims, "cpuct": cpuct, "tempThreshold": temp_threshold}))
+    examples = coach.executeEpisode()
+    out = [{"key": g.stringRepresentation(b), "v": float(v), "pi": {str(a): float(p).hex() for a, p in enumerate(pi) if p}}
+           for b, pi, v in examples]
+    return {"mt_seed": mt_seed, "sims": sims, "cpuct": cpuct, "temp_threshold": temp_threshold, "examples": out,
+            "rng_after": int(np.random.randint(0, 2 ** 31)), "py_rng_after": random.random().hex()}
+
+
 def main():
     cases = [
         run_case("uniform_s25", mcts_oracle.uniform_evaluator, 25, 1.5, 0, 0, 15),
@@ -194,7 +216,8 @@ def main():
     ]
     coach = [coach_episode_case(0, 20, 1.5, 15, 3, 9), coach_episode_case(4, 12, 1.0, 4, 8, 123)]
     with open(os.path.join(HERE, "mcts_golden.json"), "w") as f:
-        json.dump({"numpy": np.__version__, "cases": cases, "coach": coach}, f, separators=(",", ":"))
+        plain = [coach_plain_case(11, 20, 1.5, 15), coach_plain_case(12, 16, 1.0, 5)]
+        json.dump({"numpy": np.__version__, "cases": cases, "coach": coach, "coach_plain": plain}, f, separators=(",", ":"))
     for c in coach:
         print("coach", c["mt_seed"], len(c["examples"]), "examples", c["examples"][-1]["v"], c["rng_after"])
     for c in cases:

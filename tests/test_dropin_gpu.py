@@ -101,7 +101,7 @@ def test_coach_execute_episode_matches_reference():
     for case in cases:
         g = YachtGame(seed=case["mt_seed"])
         args = Args(numMCTSSims=case["sims"], cpuct=case["cpuct"], tempThreshold=case["temp_threshold"],
-                    search_seed=case["search_seed"], tree_id=case["tree_id"])
+                    search_seed=case["search_seed"], tree_id=case["tree_id"], search_dice="philox")
         coach = Coach(g, HashedNet(), args)
         examples = coach.executeEpisode()
         assert len(examples) == len(case["examples"])
@@ -153,3 +153,33 @@ def test_waves_equal_one_big_batch():
         assert torch.equal(got[w]["features"], ref["features"][:, sl])
     r = ref["result_p1"]
     assert totals == (int((r > 0.5).sum()), int((r < -0.5).sum()), int((r.abs() < 0.5).sum()))
+
+
+def test_seeded_episode_matches_unpatched_reference():
+    """Coach.executeEpisode of the UNPATCHED reference (only YachtGame(seed) set; in-search dice from the global
+    numpy / random streams) vs the drop-in Coach + MCTS + YachtGame in their default mode: identical boards,
+    policies, values and identical RNG states afterwards (both numpy's and random's)."""
+    import random
+    from nypc_yacht_auction_b200.game import YachtGame
+    from nypc_yacht_auction_b200.coach import Coach
+    with open(os.path.join(GOLDEN, "mcts_golden.json")) as f:
+        cases = json.load(f)["coach_plain"]
+
+    class Args(dict):
+        __getattr__ = dict.__getitem__
+
+    class HashedNet:
+        def predict(self, board):
+            return mcts_oracle.hashed_evaluator(to_oracle_board(board), 9)
+
+    for case in cases:
+        g = YachtGame(seed=case["mt_seed"])
+        coach = Coach(g, HashedNet(), Args(numMCTSSims=case["sims"], cpuct=case["cpuct"], tempThreshold=case["temp_threshold"]))
+        examples = coach.executeEpisode()
+        assert len(examples) == len(case["examples"])
+        for (board, pi, v), ref in zip(examples, case["examples"]):
+            assert g.stringRepresentation(board) == ref["key"]
+            assert float(v) == ref["v"]
+            assert {str(a): float(p).hex() for a, p in enumerate(pi) if p} == ref["pi"]
+        assert int(np.random.randint(0, 2 ** 31)) == case["rng_after"]
+        assert random.random().hex() == case["py_rng_after"]

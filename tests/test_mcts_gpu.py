@@ -157,7 +157,7 @@ def test_dropin_mcts_class_matches_reference_trace():
             return mcts_oracle.hashed_evaluator(to_oracle_board(board))
 
     env = _engine(1, case["seed"], case["game"])
-    args = Args(numMCTSSims=case["sims"], cpuct=case["cpuct"], search_seed=case["seed"], tree_id=case["game"])
+    args = Args(numMCTSSims=case["sims"], cpuct=case["cpuct"], search_seed=case["seed"], tree_id=case["game"], search_dice="philox")
     mcts = MCTS(None, Net(), args)
     from nypc_yacht_auction_b200.layout import planes_to_boards
     for ref in case["trace"][:20]:
