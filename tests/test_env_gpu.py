@@ -347,3 +347,67 @@ def test_record_host_abi_matches_device_path():
     assert torch.equal(rec[:, 0:4], st[0]) and torch.equal(rec[:, 4:8], st[1]) and torch.equal(rec[:, 8], dev_env.episode.cpu())
     assert (rec[:, 13] == 2).all() and int(herr.item()) == 0
     lib.ya_host_destroy(h)
+
+
+def test_search_style_walks_match_oracle():
+    """MCTS-style traversal (MCTS.py:149-150: getNextState(canonical, 1, a) then getCanonicalForm) from
+    mid-game roots, including the quirk states real play never reaches (rounds that do not advance, five- and
+    zero-dice positions, bogus round-12 terminals), with in-search Philox draws (tag SEARCH, depth, sim)."""
+    from nypc_yacht_auction_b200.engine import BatchedYacht, TAG_SEARCH
+    from nypc_yacht_auction_b200 import _lib
+    from nypc_yacht_auction_b200.layout import string_key
+    from conftest import to_oracle_board
+    rng = np.random.default_rng(5)
+    n, seed, base = 160, 77, 4000
+    env = BatchedYacht(n, seed=seed, game_base=base)
+    start_ply = rng.integers(0, 47, size=n)
+    for t in range(47):                                   # bring game g to a random ply
+        acts = env.random_actions()
+        keep = torch.from_numpy((start_ply > t)).cuda()
+        st_before, pl_before, ply_before = env.states.clone(), env.players.clone(), env.ply.clone()
+        env.next_state(acts)
+        env.states[:, ~keep] = st_before[:, ~keep]
+        env.players[~keep] = pl_before[~keep]
+        env.ply[~keep] = ply_before[~keep]
+    canon = env.canonical()
+    env.states.copy_(canon)
+    env.players.fill_(1)
+    boards = [to_oracle_board(b) for b in env.boards()]
+    lib = env.lib
+    ended_seen = dead_seen = 0
+    for depth in range(7):
+        masks = env.valid_moves().cpu().numpy()
+        ended = env.game_ended().cpu().numpy()
+        acts = np.zeros(n, dtype=np.int32)
+        live = np.zeros(n, dtype=bool)
+        for g in range(n):
+            assert (masks[g] == yr.legal_mask(boards[g], 1)).all()
+            assert ended[g] == np.float32(yr.outcome(boards[g], 1))
+            legal = np.flatnonzero(masks[g])
+            if ended[g] != 0:
+                ended_seen += 1
+            elif len(legal) == 0:
+                dead_seen += 1
+            else:
+                acts[g] = int(legal[rng.integers(0, len(legal))])
+                live[g] = True
+        depth_sim = torch.full((n,), depth | (3 << 8), dtype=torch.int32, device="cuda")       # depth, sim = 3
+        a_dev = torch.from_numpy(acts).cuda()
+        out = torch.empty_like(env.states)
+        nxt = torch.empty_like(env.players)
+        _lib.check(lib.ya_next_state(_lib.ptr(env.states), n, _lib.ptr(env.players), _lib.ptr(a_dev), _lib.ptr(out), n,
+                                     _lib.ptr(nxt), _lib.ptr(env.status), n, 0, None, seed, base, _lib.ptr(env.episode),
+                                     _lib.ptr(env.ply), TAG_SEARCH, _lib.ptr(depth_sim), _lib.current_stream()), "next")
+        live_t = torch.from_numpy(live).cuda()
+        env.states[:, live_t] = out[:, live_t]
+        env.players[live_t] = nxt[live_t]
+        env.states.copy_(env.canonical())
+        env.players.fill_(1)
+        ply_host = env.ply.cpu().numpy()
+        for g in range(n):
+            if live[g]:
+                d = philox.Draw(seed, base + g, 0, int(ply_host[g]), philox.TAG_SEARCH, depth, 3)
+                nb, who = yr.next_state(boards[g], 1, int(acts[g]), d)
+                boards[g] = yr.canonical(nb, who)
+        assert _keys(env) == [yr.key(b) for b in boards], depth
+    assert dead_seen > 0 and ended_seen > 0        # the walk did reach dead ends and (bogus) terminals
