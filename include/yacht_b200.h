@@ -173,6 +173,12 @@ int ya_mcts_search_uniform(const ya_mcts_tree* tree, const uint32_t* states, int
 int ya_mcts_root_counts(const ya_mcts_tree* tree, const uint32_t* states, int64_t stride, const int8_t* players,
                         int32_t* counts, int32_t* visits, double* qvals, uint8_t* qkind, void* stream);
 
+/* The same statistics in canonical sparse form for training examples (Coach.py:60-63): the visited root
+ * edges as (action int16, Nsa int32) pairs in ascending action order, zero padded to k per game;
+ * overflow[g] (may be NULL) = number of visited edges if they exceed k, -1 if the root is unknown, else 0. */
+int ya_mcts_root_sparse(const ya_mcts_tree* tree, const uint32_t* states, int64_t stride, const int8_t* players,
+                        int k, int16_t* actions, int32_t* counts, int32_t* overflow, void* stream);
+
 /* Move selection from visit counts (Coach.py:56-65, MCTS.py:44-54): temp = (ply+1 < temp_threshold);
  * temp 1 samples proportionally to the counts, temp 0 picks uniformly among the arg-max actions;
  * randomness = Philox word of tag ACTION. */

@@ -42,6 +42,7 @@ SIGNATURES = {
     "ya_mcts_search_uniform": [_vp, _vp, _i64, _vp, _vp, _vp, _u64, _u64, _int, ctypes.c_float, ctypes.c_float,
                                ctypes.c_float, _vp, _vp, _vp],
     "ya_mcts_root_counts": [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp],
+    "ya_mcts_root_sparse": [_vp, _vp, _i64, _vp, _int, _vp, _vp, _vp, _vp],
     "ya_mcts_pick_action": [_vp, _vp, _vp, _i64, _u64, _u64, _int, _vp, _vp],
     "ya_nn_ln_act": [_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, ctypes.c_float, _vp],
     "ya_nn_trunk": [_vp, _vp, _vp, _vp, _vp, _int, _i64, _i64, ctypes.c_float, _vp],

@@ -68,6 +68,7 @@ class BatchedSelfPlay:
             self.ex_actions = torch.zeros((self.PLIES, n, self.k), dtype=torch.int16, device=d)
             self.ex_counts = torch.zeros((self.PLIES, n, self.k), dtype=torch.int32, device=d)
             self.ex_players = torch.zeros((self.PLIES, n), dtype=torch.int8, device=d)
+            self.ex_overflow = torch.zeros(n, dtype=torch.int32, device=d)
 
     def play_ply(self, t):
         env, m = self.env, self.mcts
@@ -75,11 +76,9 @@ class BatchedSelfPlay:
             env.features(out=self.ex_features[t])                    # state_to_vec of the canonical root
             self.ex_players[t].copy_(env.players)
         m.search()
-        counts, _ = m.root_counts()
-        if self.record:
-            vals, idx = torch.topk(counts, self.k, dim=1)            # the <= k visited root edges
-            self.ex_counts[t].copy_(vals)
-            self.ex_actions[t].copy_(idx.to(torch.int16))
+        m.root_counts()
+        if self.record:                                              # the visited root edges, sorted by action
+            m.root_sparse(self.ex_actions[t], self.ex_counts[t], self.ex_overflow)
         actions = m.pick_actions()
         env.next_state(actions, check=False)
         return actions

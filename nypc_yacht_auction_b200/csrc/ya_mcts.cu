@@ -740,6 +740,47 @@ ya_k_mcts_root_counts(ya_mcts_tree tree, const uint4* __restrict__ states, int64
     }
 }
 
+// ---------------------------------------------------------------- sparse root policy (training examples)
+// The visited root edges as (action, Nsa) pairs in ascending action order, zero padded to k entries: the
+// canonical sparse form of the pi vector Coach.executeEpisode records (Coach.py:60-63).  overflow[g] = number
+// of visited edges when they do not fit k (the row then holds the k lowest actions).
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+ya_k_mcts_root_sparse(ya_mcts_tree tree, const uint4* __restrict__ states, int64_t stride, const int8_t* __restrict__ players,
+                      int k, int16_t* __restrict__ actions, int32_t* __restrict__ counts, int32_t* __restrict__ overflow) {
+    const int lane = threadIdx.x & 31;
+    const int64_t g = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    if (g >= tree.n) return;
+    View v = make_view(tree, g);
+    YaState cur = ya_load(states, stride, g);
+    if (players[g] != 1) cur = ya_flip(cur);
+    int16_t* arow = actions + g * k;
+    int32_t* crow = counts + g * k;
+    for (int i = lane; i < k; i += 32) { arow[i] = 0; crow[i] = 0; }
+    __syncwarp();
+    int free_slot;
+    int idx = ht_find(v, cur, &free_slot);
+    if (idx < 0) { if (lane == 0 && overflow) overflow[g] = -1; return; }
+    const uint32_t* node = v.nodes + (int64_t)idx * kNodeWords;
+    const int n_edges = (int)node[N_NEDGE];
+    if (lane == 0 && overflow) overflow[g] = n_edges > k ? n_edges : 0;
+    // legal indices ascend with actions, so the rank of an edge = number of edges with a smaller legal index
+    for (int e = lane; e < n_edges; e += 32) {
+        uint32_t off = node[N_EDGES];
+        for (int c = 0; c < e / kChunkEdges; ++c) off = v.arena[off];
+        const uint32_t* ch = v.arena + off;
+        const int my = reinterpret_cast<const uint16_t*>(ch + 2)[e % kChunkEdges];
+        const uint32_t nsa = ch[18 + e % kChunkEdges] & 0x7FFFFFFFu;
+        int rank = 0;
+        uint32_t o = node[N_EDGES];
+        for (int base = 0; base < n_edges; base += kChunkEdges, o = v.arena[o]) {
+            const uint16_t* ids = reinterpret_cast<const uint16_t*>(v.arena + o + 2);
+            const int cnt = min(kChunkEdges, n_edges - base);
+            for (int j = 0; j < cnt; ++j) rank += ids[j] < my;
+        }
+        if (rank < k) { arow[rank] = (int16_t)ya_nth_legal(node[N_DESC], my); crow[rank] = (int32_t)nsa; }
+    }
+}
+
 // ---------------------------------------------------------------- action from visit counts
 // temp = 1 (Coach.py:56-65): inverse CDF over the integer counts, r = (word * total) >> 32.
 // temp = 0 (MCTS.py:44-49): uniformly among the arg-max actions, k = (word * ties) >> 32.
@@ -882,6 +923,14 @@ int ya_mcts_root_counts(const ya_mcts_tree* tree, const uint32_t* states, int64_
     if (!tree_ok(tree)) return (int)cudaErrorInvalidValue;
     ya_k_mcts_root_counts<<<warp_blocks(tree->n), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
         *tree, reinterpret_cast<const uint4*>(states), stride, players, counts, visits, qvals, qkind);
+    return (int)cudaGetLastError();
+}
+
+int ya_mcts_root_sparse(const ya_mcts_tree* tree, const uint32_t* states, int64_t stride, const int8_t* players,
+                        int k, int16_t* actions, int32_t* counts, int32_t* overflow, void* stream) {
+    if (!tree_ok(tree) || k <= 0) return (int)cudaErrorInvalidValue;
+    ya_k_mcts_root_sparse<<<warp_blocks(tree->n), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
+        *tree, reinterpret_cast<const uint4*>(states), stride, players, k, actions, counts, overflow);
     return (int)cudaGetLastError();
 }
 

@@ -44,8 +44,11 @@ def allgather_examples(examples, group=None):
         pad_shape[game_dim] = n_max
         buf = t.new_zeros(pad_shape)
         buf.narrow(game_dim, 0, t.shape[game_dim]).copy_(t)
-        parts = [torch.empty_like(buf) for _ in range(world)]
-        dist.all_gather(parts, buf.contiguous(), group=group)
+        # NCCL has no int16 / bool collectives: every tensor travels as raw bytes and is viewed back
+        wire = buf.contiguous().view(torch.uint8) if buf.dim() > 0 else buf
+        parts = [torch.empty_like(wire) for _ in range(world)]
+        dist.all_gather(parts, wire, group=group)
+        parts = [p.view(t.dtype).view(pad_shape) for p in parts]
         out[name] = torch.cat([p.narrow(game_dim, 0, s) for p, s in zip(parts, sizes)], dim=game_dim)
     return out
 

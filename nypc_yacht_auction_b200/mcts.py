@@ -387,6 +387,13 @@ class BatchedMCTS:
             _lib.ptr(q), _lib.ptr(kind), _lib.current_stream()), "ya_mcts_root_counts")
         return (self.counts, self.visits, q, kind) if with_q else (self.counts, self.visits)
 
+    def root_sparse(self, actions_out, counts_out, overflow=None):
+        """Visited root edges as sorted (action, count) pairs, zero padded (canonical sparse pi)."""
+        env = self.env
+        _lib.check(self.lib.ya_mcts_root_sparse(
+            self.pool.ref, _lib.ptr(env.states), env.n, _lib.ptr(env.players), actions_out.shape[-1], _lib.ptr(actions_out),
+            _lib.ptr(counts_out), _lib.ptr(overflow), _lib.current_stream()), "ya_mcts_root_sparse")
+
     def pick_actions(self):
         env = self.env
         _lib.check(self.lib.ya_mcts_pick_action(

@@ -40,11 +40,13 @@ def _worker(rank, world, port, total):
         ex = {
             "features": (ids.float().view(1, n, 1) + torch.arange(3).float().view(3, 1, 1)).expand(3, n, 59).contiguous(),
             "counts": ids.int().view(1, n, 1).expand(3, n, 4).contiguous(),
+            "actions": ids.to(torch.int16).view(1, n, 1).expand(3, n, 4).contiguous(),      # NCCL has no int16: sent as bytes
             "result_p1": ids.float(),
         }
         full = allgather_examples(ex)
         assert full["features"].shape == (3, total, 59)
         assert torch.equal(full["counts"][0, :, 0], torch.arange(total, dtype=torch.int32))
+        assert full["actions"].dtype == torch.int16 and torch.equal(full["actions"][1, :, 3], torch.arange(total, dtype=torch.int16))
         assert torch.equal(full["result_p1"], torch.arange(total, dtype=torch.float32))
         assert torch.equal(full["features"][2, :, 5], torch.arange(total).float() + 2)
         torch.manual_seed(rank)
