@@ -202,6 +202,17 @@ int ya_nn_ln_act(int mode, const void* x, const void* gamma, const void* beta, c
 int ya_nn_trunk(const void* x, void* out, const void* weight_images, const float* params, const int32_t* kinds,
                 int layers, int64_t n, int64_t hidden, float eps, void* stream);
 
+/* The whole YachtNNet.forward (yacht/pytorch/YachtNNet.py:62-70) for a wave of leaves as one persistent
+ * tcgen05 kernel: features float32 [n][59] (state_to_vec rows) -> logits bf16 [n][3232] (columns >= 3226 are
+ * padding) and values float32 [n] (tanh).  weight_blob / param_blob are built once on the host
+ * (mcts.FusedYachtEvaluator): 128-byte-swizzled K-major images of W_in (K padded to 64), the 2*nblocks trunk
+ * weights, the value head's first Linear and 26 policy-head tiles of 128 columns; biases and LayerNorm
+ * parameters as float32.  offsets (HOST pointer, int64[9]) = byte offsets {w_in, w_trunk, w_v, w_pi} and float
+ * offsets {p_in, p_trunk, p_v, p_pi_ln, p_pi_bias}.  hidden width 256 only.  Rows are independent of the
+ * batch they sit in (batch-invariant evaluator). */
+int ya_nn_forward(const float* features, void* logits_bf16, float* values, const void* weight_blob,
+                  const float* param_blob, const int64_t* offsets, int nblocks, int64_t n, float eps, void* stream);
+
 /* ---- host-buffer variants (end-to-end path for callers that keep boards in host memory) ----
  * ya_host_create allocates the device mirror for n games once (no allocation per call);
  * ya_host_play_ply copies the packed states and side arrays host->device, runs ya_play_ply,

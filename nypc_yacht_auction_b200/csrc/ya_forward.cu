@@ -1,0 +1,379 @@
+// Yacht-Auction B200 engine -- the WHOLE leaf-evaluator forward (YachtNNet.forward,
+// yacht/pytorch/YachtNNet.py:62-70) as one persistent tcgen05 kernel: state_to_vec features in, bf16 policy
+// logits (padded to 3232 columns) and tanh values out.  A CTA owns 128 leaves from the first Linear to the
+// last: activations stay in shared memory (bf16, 128-byte-swizzled K-major A operand), the skip connection
+// and the accumulators live in TMEM, every weight matrix arrives as a pre-swizzled image through
+// cp.async.bulk while the previous stage's epilogue runs, and all bias / SiLU / LayerNorm / residual / tanh
+// work happens in the tcgen05.ld epilogues.  Stages:
+//   input   Linear(59->256) + LN + SiLU                         (1 K-block of 64, N = 256)
+//   trunk   nblocks x [LN(SiLU(fc1)), skip + LN(SiLU(fc2))]     (4 K-blocks, N = 256)
+//   value   SiLU(LN_v(h)) -> Linear(256->128) + SiLU -> dot(w2) + b2 -> tanh      (N = 128)
+//   policy  SiLU(LN_pi(h)) -> 26 tiles of Linear(256->128 columns) + bias -> bf16 logits
+// Every row is computed independently of the batch it sits in (fixed tile shapes, fixed accumulation order),
+// so the evaluator is batch-invariant: sharding leaves over GPUs or waves cannot change a single bit.
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cstdint>
+#include "../../include/yacht_b200.h"
+#include "ya_tc.cuh"
+
+namespace {
+
+using namespace ya_tc;
+
+constexpr int kRows = 128, kDim = 256, kThreads = 512, kParts = 4;
+constexpr int kFeat = 59;
+constexpr int kPolicyCols = 3232, kPolicyTile = 128, kPolicyTiles = 26;        // 26 * 128 = 3328 >= 3232
+constexpr int kABytes = kRows * kDim * 2;            // 64 KB
+constexpr int kWBytes = kDim * kDim * 2;             // 128 KB (two 64 KB halves for the N = 128 stages)
+constexpr int kPrmFloats = 776;                      // largest parameter block (value head), 16-byte multiple
+constexpr int kSmemBytes = 1024 + kABytes + kWBytes + 2 * kPrmFloats * 4 + kRows * kParts * 8 + 64;
+
+struct Blob {                                        // byte / float offsets of the host-built blobs (see mcts.py)
+    int64_t w_in, w_trunk, w_v, w_pi;
+    int64_t p_in, p_trunk, p_v, p_pi_ln, p_pi_bias;
+};
+
+__device__ __forceinline__ uint32_t a_tile_offset(int r, int c8) {
+    int kb = c8 >> 3, chunk = c8 & 7;
+    return (uint32_t)(kb * (kRows * 128) + r * 128 + ((chunk ^ (r & 7)) << 4));
+}
+
+__device__ __forceinline__ void pack_store_a(uint8_t* a_tile, int row, int c8_first, const uint32_t (&r)[32]) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        uint32_t p[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(r[q * 8 + 2 * i]), __uint_as_float(r[q * 8 + 2 * i + 1]));
+            p[i] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        *reinterpret_cast<uint4*>(a_tile + a_tile_offset(row, c8_first + q)) = make_uint4(p[0], p[1], p[2], p[3]);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+ya_k_forward(const float* __restrict__ features, __nv_bfloat16* __restrict__ logits, float* __restrict__ values,
+             const uint8_t* __restrict__ wblob, const float* __restrict__ pblob, Blob off, int nblocks, int64_t n, float eps) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* a_tile = base;
+    uint8_t* w_tile = base + kABytes;
+    float* prm_all = reinterpret_cast<float*>(w_tile + kWBytes);
+    float2* xchg = reinterpret_cast<float2*>(prm_all + 2 * kPrmFloats);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(xchg + kParts * kRows);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int row = (warp & 3) * 32 + lane;
+    const int part = warp >> 2;
+    const int64_t grow = (int64_t)blockIdx.x * kRows + row;
+
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t t_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    const uint32_t t_acc64 = t_lane + (uint32_t)(part * 64);          // my 64 columns of an N = 256 accumulator
+    const uint32_t t_skip = t_lane + 256 + (uint32_t)(part * 64);     // my 64 columns of the float32 skip connection
+    uint32_t w_phase = 0, m_phase = 0;
+    int stage = 0;                                                    // parameter double buffer index = stage & 1
+
+    // one weight image + one parameter block per stage, on one transaction barrier
+    auto load_stage = [&](uint8_t* w_dst, int64_t w_src, uint32_t w_bytes, int buf, int64_t p_src, uint32_t p_floats) {
+        mbar_expect_tx(&bars[0], w_bytes + p_floats * 4);
+        for (uint32_t o = 0; o < w_bytes; o += 32768) bulk_g2s(w_dst + o, wblob + w_src + o, min(32768u, w_bytes - o), &bars[0]);
+        if (p_floats) bulk_g2s(prm_all + buf * kPrmFloats, pblob + p_src, p_floats * 4, &bars[0]);
+    };
+    // MMA of one stage: A tile (n_kb K-blocks of 64) x weight image at w_src (rows = n_cols) -> TMEM column d_col
+    auto run_mma = [&](const uint8_t* w_src, int n_kb, int n_cols, uint32_t d_col) {
+        proxy_fence();                                                // A tile written through the generic proxy
+        tc_fence_before();
+        __syncthreads();
+        mbar_wait(&bars[0], w_phase);                                 // weights + parameters landed
+        w_phase ^= 1;
+        if (tid == 0) {
+            tc_fence_after();
+            const uint32_t a0 = smem_u32(a_tile), b0 = smem_u32(w_src);
+            const uint32_t idesc = umma_idesc(n_cols);
+            for (int kb = 0; kb < n_kb; ++kb)
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    umma(tmem + d_col, umma_desc(a0 + kb * (kRows * 128) + k * 32), umma_desc(b0 + kb * (n_cols * 128) + k * 32),
+                         (uint32_t)((kb | k) != 0), idesc);
+            umma_commit(&bars[1]);
+        }
+        mbar_wait(&bars[1], m_phase);                                 // accumulator ready; A tile and this weight buffer free
+        m_phase ^= 1;
+        tc_fence_after();
+    };
+    auto row_stats = [&](float s, float ss, float& mean, float& rstd) {  // LayerNorm statistics over the 4 threads of a row
+        xchg[part * kRows + row] = make_float2(s, ss);
+        __syncthreads();
+#pragma unroll
+        for (int p = 1; p < kParts; ++p) {
+            float2 o = xchg[((part + p) % kParts) * kRows + row];
+            s += o.x; ss += o.y;
+        }
+        mean = s * (1.0f / kDim);
+        rstd = rsqrtf(fmaxf(ss * (1.0f / kDim) - mean * mean, 0.0f) + eps);
+        __syncthreads();                                              // xchg may be rewritten by the next stage
+    };
+
+    // ---------------------------------------------------------------- input stage
+    if (tid == 0) load_stage(w_tile, off.w_in, 256 * 128, 0, off.p_in, 3 * kDim);
+    {   // features (float32 [n][59]) -> bf16, K padded to 64: this thread fills chunks 2*part, 2*part+1 of K-block 0
+        uint32_t f[32];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            int c = part * 16 + i;
+            f[i] = (grow < n && c < kFeat) ? __float_as_uint(features[grow * kFeat + c]) : 0u;
+        }
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            uint32_t p[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(f[q * 8 + 2 * i]), __uint_as_float(f[q * 8 + 2 * i + 1]));
+                p[i] = *reinterpret_cast<uint32_t*>(&h);
+            }
+            *reinterpret_cast<uint4*>(a_tile + a_tile_offset(row, part * 2 + q)) = make_uint4(p[0], p[1], p[2], p[3]);
+        }
+    }
+    run_mma(w_tile, 1, kDim, 0);
+    if (tid == 0) load_stage(w_tile, off.w_trunk, kWBytes, 1, off.p_trunk, 3 * kDim);      // first trunk layer streams in
+    {   // h = SiLU(LN(z + b)): Linear -> LayerNorm -> SiLU (YachtNNet.py:25-30); also the first skip connection
+        const float* prm = prm_all;
+        float ps[4] = {0, 0, 0, 0}, pq[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            uint32_t r[32];
+            tmem_ld32(t_acc64 + c * 32, r);
+            tmem_ld_wait();
+            const float* bias = prm + part * 64 + c * 32;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                float v = __uint_as_float(r[i]) + bias[i];
+                ps[i & 3] += v; pq[i & 3] = fmaf(v, v, pq[i & 3]);
+                r[i] = __float_as_uint(v);
+            }
+            tmem_st32(t_acc64 + c * 32, r);
+        }
+        tmem_st_wait();
+        float mean, rstd;
+        row_stats((ps[0] + ps[1]) + (ps[2] + ps[3]), (pq[0] + pq[1]) + (pq[2] + pq[3]), mean, rstd);
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            uint32_t r[32];
+            tmem_ld32(t_acc64 + c * 32, r);
+            tmem_ld_wait();
+            const float* gamma = prm + kDim + part * 64 + c * 32;
+            const float* beta = prm + 2 * kDim + part * 64 + c * 32;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const float ga = rstd * gamma[i];
+                float y = fmaf(__uint_as_float(r[i]), ga, fmaf(-mean, ga, beta[i]));
+                r[i] = __float_as_uint(silu_from_half(0.5f * y));
+            }
+            tmem_st32(t_skip + c * 32, r);
+            pack_store_a(a_tile, row, part * 8 + c * 4, r);
+        }
+        tmem_st_wait();
+    }
+    stage = 1;
+
+    // ---------------------------------------------------------------- residual trunk
+    const int layers = 2 * nblocks;
+    for (int l = 0; l < layers; ++l, ++stage) {
+        const float* prm = prm_all + (stage & 1) * kPrmFloats;
+        const bool second = l & 1;                                    // fc2: add the skip connection
+        run_mma(w_tile, 4, kDim, 0);
+        if (tid == 0) {                                               // next stage's weights under this epilogue
+            if (l + 1 < layers) load_stage(w_tile, off.w_trunk + (int64_t)(l + 1) * kWBytes, kWBytes, (stage + 1) & 1,
+                                           off.p_trunk + (int64_t)(l + 1) * 3 * kDim, 3 * kDim);
+            else load_stage(w_tile, off.w_v, 128 * 512, (stage + 1) & 1, off.p_v, 772);
+        }
+        float ps[4] = {0, 0, 0, 0}, pq[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            uint32_t r[32];
+            tmem_ld32(t_acc64 + c * 32, r);
+            tmem_ld_wait();
+            const float* bias = prm + part * 64 + c * 32;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                float v = silu_from_half(fmaf(__uint_as_float(r[i]), 0.5f, 0.5f * bias[i]));
+                ps[i & 3] += v; pq[i & 3] = fmaf(v, v, pq[i & 3]);
+                r[i] = __float_as_uint(v);
+            }
+            tmem_st32(t_acc64 + c * 32, r);
+        }
+        tmem_st_wait();
+        float mean, rstd;
+        row_stats((ps[0] + ps[1]) + (ps[2] + ps[3]), (pq[0] + pq[1]) + (pq[2] + pq[3]), mean, rstd);
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            uint32_t r[32], sk[32];
+            tmem_ld32(t_acc64 + c * 32, r);
+            if (second) tmem_ld32(t_skip + c * 32, sk);
+            tmem_ld_wait();
+            const float* gamma = prm + kDim + part * 64 + c * 32;
+            const float* beta = prm + 2 * kDim + part * 64 + c * 32;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const float ga = rstd * gamma[i];
+                float v = fmaf(__uint_as_float(r[i]), ga, fmaf(-mean, ga, beta[i]));
+                if (second) { v += __uint_as_float(sk[i]); }
+                r[i] = __float_as_uint(v);
+            }
+            if (second) tmem_st32(t_skip + c * 32, r);
+            pack_store_a(a_tile, row, part * 8 + c * 4, r);
+        }
+        if (second) tmem_st_wait();
+    }
+
+    // ---------------------------------------------------------------- heads: a = SiLU(LN(h; gamma, beta)) from the skip
+    auto head_prep = [&](const float* gamma_all, const float* beta_all) {
+        float ps[4] = {0, 0, 0, 0}, pq[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            uint32_t r[32];
+            tmem_ld32(t_skip + c * 32, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) { float v = __uint_as_float(r[i]); ps[i & 3] += v; pq[i & 3] = fmaf(v, v, pq[i & 3]); }
+        }
+        float mean, rstd;
+        row_stats((ps[0] + ps[1]) + (ps[2] + ps[3]), (pq[0] + pq[1]) + (pq[2] + pq[3]), mean, rstd);
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            uint32_t r[32];
+            tmem_ld32(t_skip + c * 32, r);
+            tmem_ld_wait();
+            const float* gamma = gamma_all + part * 64 + c * 32;
+            const float* beta = beta_all + part * 64 + c * 32;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const float ga = rstd * gamma[i];
+                float y = fmaf(__uint_as_float(r[i]), ga, fmaf(-mean, ga, beta[i]));
+                r[i] = __float_as_uint(silu_from_half(0.5f * y));
+            }
+            pack_store_a(a_tile, row, part * 8 + c * 4, r);
+        }
+    };
+
+    // value head (YachtNNet.py:44-50): LN -> SiLU -> Linear(256,128) -> SiLU -> Linear(128,1) -> tanh
+    {
+        const float* prm = prm_all + (stage & 1) * kPrmFloats;       // gamma_v | beta_v | b1[128] | w2[128] | b2
+        mbar_wait(&bars[0], w_phase);                                 // the LayerNorm parameters travel with the weights
+        head_prep(prm, prm + kDim);
+        run_mma(w_tile, 4, 128, 0);                                   // (re-waits the same completed phase, then flips it)
+        if (tid == 0) load_stage(w_tile + 65536, off.w_pi, 65536, (stage + 1) & 1, off.p_pi_ln, 2 * kDim + kPolicyTile);
+        uint32_t r[32];
+        tmem_ld32(t_lane + part * 32, r);
+        tmem_ld_wait();
+        const float* b1 = prm + 2 * kDim + part * 32;
+        const float* w2 = prm + 2 * kDim + 128 + part * 32;
+        float acc[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            float t = silu_from_half(fmaf(__uint_as_float(r[i]), 0.5f, 0.5f * b1[i]));
+            acc[i & 3] = fmaf(t, w2[i], acc[i & 3]);
+        }
+        float dot = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+        xchg[part * kRows + row] = make_float2(dot, 0.0f);
+        __syncthreads();
+        if (part == 0 && grow < n) {
+            float s = dot + xchg[1 * kRows + row].x + xchg[2 * kRows + row].x + xchg[3 * kRows + row].x + prm[2 * kDim + 256];
+            float th;
+            asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(s));
+            values[grow] = th;
+        }
+        __syncthreads();
+        ++stage;
+    }
+
+    // policy head (YachtNNet.py:38-42): LN -> SiLU -> Linear(256, 3226), 26 tiles of 128 columns, weight tiles
+    // ping-pong between the two 64 KB halves of the weight region
+    {
+        const float* prm0 = prm_all + (stage & 1) * kPrmFloats;      // gamma_pi | beta_pi | bias of tile 0
+        mbar_wait(&bars[0], w_phase);
+        head_prep(prm0, prm0 + kDim);
+        for (int j = 0; j < kPolicyTiles; ++j, ++stage) {
+            const float* bias = prm_all + (stage & 1) * kPrmFloats + (j == 0 ? 2 * kDim : 0);
+            uint8_t* wj = w_tile + ((j + 1) & 1) * 65536;             // tile 0 went to the upper half
+            proxy_fence();
+            tc_fence_before();
+            __syncthreads();
+            mbar_wait(&bars[0], w_phase);
+            w_phase ^= 1;
+            if (tid == 0) {
+                tc_fence_after();
+                if (j + 1 < kPolicyTiles)                             // next tile into the other half (its last reader finished)
+                    load_stage(w_tile + (j & 1) * 65536, off.w_pi + (int64_t)(j + 1) * 65536, 65536, (stage + 1) & 1,
+                               off.p_pi_bias + (int64_t)(j + 1) * kPolicyTile, kPolicyTile);
+                const uint32_t a0 = smem_u32(a_tile), b0 = smem_u32(wj);
+                const uint32_t idesc = umma_idesc(kPolicyTile);
+#pragma unroll
+                for (int kb = 0; kb < 4; ++kb)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma(tmem, umma_desc(a0 + kb * (kRows * 128) + k * 32), umma_desc(b0 + kb * (kPolicyTile * 128) + k * 32),
+                             (uint32_t)((kb | k) != 0), idesc);
+                umma_commit(&bars[1]);
+            }
+            mbar_wait(&bars[1], m_phase);
+            m_phase ^= 1;
+            tc_fence_after();
+            uint32_t r[32];
+            tmem_ld32(t_lane + part * 32, r);
+            tmem_ld_wait();
+            const int col0 = j * kPolicyTile + part * 32;
+            if (grow < n && col0 < kPolicyCols) {
+                uint32_t p[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(r[2 * i]) + bias[part * 32 + 2 * i],
+                                                             __uint_as_float(r[2 * i + 1]) + bias[part * 32 + 2 * i + 1]);
+                    p[i] = *reinterpret_cast<uint32_t*>(&h);
+                }
+                uint4* dst = reinterpret_cast<uint4*>(logits + grow * kPolicyCols + col0);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) dst[q] = make_uint4(p[4 * q], p[4 * q + 1], p[4 * q + 2], p[4 * q + 3]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+}
+
+}  // namespace
+
+extern "C" int ya_nn_forward(const float* features, void* logits_bf16, float* values, const void* weight_blob,
+                             const float* param_blob, const int64_t* offsets, int nblocks, int64_t n, float eps, void* stream) {
+    if (n <= 0) return 0;
+    if ((reinterpret_cast<uintptr_t>(logits_bf16) | reinterpret_cast<uintptr_t>(weight_blob) |
+         reinterpret_cast<uintptr_t>(param_blob)) & 15u) return (int)cudaErrorMisalignedAddress;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(ya_k_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        if (e != cudaSuccess) return (int)e;
+        configured = true;
+    }
+    Blob off{offsets[0], offsets[1], offsets[2], offsets[3], offsets[4], offsets[5], offsets[6], offsets[7], offsets[8]};
+    int blocks = (int)((n + kRows - 1) / kRows);
+    ya_k_forward<<<blocks, kThreads, kSmemBytes, (cudaStream_t)stream>>>(
+        features, static_cast<__nv_bfloat16*>(logits_bf16), values, static_cast<const uint8_t*>(weight_blob), param_blob, off,
+        nblocks, n, eps);
+    return (int)cudaGetLastError();
+}

@@ -125,7 +125,7 @@ class FusedYachtEvaluator:
     returns_logits = True
     PADDED = 3232
 
-    def __init__(self, net, max_batch, trunk_kernel=True):
+    def __init__(self, net, max_batch, trunk_kernel=True, whole_forward=True):
         sd = {k: v.detach() for k, v in net.state_dict().items()}
         dev = next(net.parameters()).device
         bf = lambda t: t.to(device=dev, dtype=torch.bfloat16).contiguous()
@@ -169,6 +169,46 @@ class FusedYachtEvaluator:
             self.trunk_p = torch.stack(params).to(dev).contiguous()
             self.trunk_kinds = torch.tensor(kinds, dtype=torch.int32, device=dev)
 
+        # everything (input layer, trunk, both heads) for the single-kernel forward (csrc/ya_forward.cu)
+        self.whole_forward = bool(whole_forward) and self.trunk_kernel and sd["v_head.2.weight"].shape[0] == 128 \
+            and sd["pi_head.2.weight"].shape[0] <= self.PADDED and sd["inp.0.weight"].shape[1] <= 64
+        if self.whole_forward:
+            f32 = lambda t: t.to(device=dev, dtype=torch.float32).reshape(-1)
+            w_in = torch.zeros((256, 64), dtype=torch.bfloat16, device=dev)
+            w_in[:, :sd["inp.0.weight"].shape[1]].copy_(sd["inp.0.weight"])
+            w_pi = torch.zeros((26 * 128, 256), dtype=torch.bfloat16, device=dev)
+            w_pi[:a].copy_(sd["pi_head.2.weight"])
+            b_pi = torch.zeros(26 * 128, dtype=torch.float32, device=dev)
+            b_pi[:a].copy_(sd["pi_head.2.bias"])
+            wparts = [self.swizzled_image(w_in), self.trunk_w, self.swizzled_image(sd["v_head.2.weight"].to(dev))] + \
+                     [self.swizzled_image(w_pi[128 * j:128 * (j + 1)]) for j in range(26)]
+            pparts = [f32(sd["inp.0.bias"]), f32(sd["inp.1.weight"]), f32(sd["inp.1.bias"]), self.trunk_p.reshape(-1),
+                      f32(sd["v_head.0.weight"]), f32(sd["v_head.0.bias"]), f32(sd["v_head.2.bias"]), f32(sd["v_head.4.weight"]),
+                      torch.cat([f32(sd["v_head.4.bias"]), torch.zeros(3, device=dev)]),
+                      f32(sd["pi_head.0.weight"]), f32(sd["pi_head.0.bias"]), b_pi]
+            wsizes = [p.numel() for p in wparts]
+            psizes = [p.numel() for p in pparts]
+            self.fw_w = torch.cat(wparts).contiguous()
+            self.fw_p = torch.cat(pparts).contiguous()
+            w_off = [0, wsizes[0], wsizes[0] + wsizes[1], wsizes[0] + wsizes[1] + wsizes[2]]
+            p_in, p_trunk = 0, sum(psizes[:3])
+            p_v = p_trunk + psizes[3]
+            p_pi_ln = p_v + sum(psizes[4:9])
+            self.fw_off = (ctypes.c_int64 * 9)(*w_off, p_in, p_trunk, p_v, p_pi_ln, p_pi_ln + 512)
+            assert sum(psizes[4:9]) == 772 and psizes[3] == 768 * 2 * self.nblocks
+            self.values = torch.empty(int(max_batch), dtype=torch.float32, device=dev)
+
+    @staticmethod
+    def swizzled_image(w):
+        """[rows][K] weight (K a multiple of 64) -> shared-memory image for tcgen05.mma: K-blocks of [rows][64 bf16],
+        16-byte chunk c of row r stored at chunk c ^ (r & 7) (128-byte swizzle)."""
+        rows, k = w.shape
+        w = w.to(torch.bfloat16).contiguous().view(rows, k // 64, 8, 8)
+        r = torch.arange(rows, device=w.device).view(rows, 1, 1)
+        src_chunk = (torch.arange(8, device=w.device).view(1, 1, 8) ^ (r & 7)).expand(rows, k // 64, 8)
+        img = torch.gather(w, 2, src_chunk.unsqueeze(-1).expand(rows, k // 64, 8, 8))
+        return img.permute(1, 0, 2, 3).contiguous().view(torch.uint8).reshape(-1)
+
     @staticmethod
     def swizzled_weight_image(w):
         """[256 out][256 in] weight -> the 128 KB shared-memory image tcgen05.mma reads: 4 K-blocks of
@@ -190,6 +230,8 @@ class FusedYachtEvaluator:
         import copy
         other = copy.copy(self)
         other._alloc(int(max_batch), self.w_in.device)
+        if self.whole_forward:
+            other.values = torch.empty(int(max_batch), dtype=torch.float32, device=self.w_in.device)
         return other
 
     def _ln(self, mode, x, ln, out, residual=None, ln2=None, out2=None):
@@ -201,6 +243,12 @@ class FusedYachtEvaluator:
     @torch.no_grad()
     def __call__(self, features, need_eval=None, leaf_states=None):
         n = features.shape[0]
+        if self.whole_forward:                                            # one tcgen05 kernel: features -> logits, values
+            logits, values = self.logits[:n], self.values[:n]
+            _lib.check(self.lib.ya_nn_forward(_lib.ptr(features), _lib.ptr(logits), _lib.ptr(values), _lib.ptr(self.fw_w),
+                                              _lib.ptr(self.fw_p), self.fw_off, self.nblocks, n, self.eps,
+                                              _lib.current_stream()), "ya_nn_forward")
+            return logits, values
         z, h, a, p, q = self.z[:n], self.h[:n], self.a[:n], self.p[:n], self.q[:n]
         x = features.to(torch.bfloat16)
         torch.addmm(self.b_in, x, self.w_in, out=z)

@@ -370,7 +370,7 @@ def test_tcgen05_trunk_kernel_matches_layerwise_path():
     for _ in range(9):
         env.play_ply(masks=None, auto_reset=False)
     x = env.features()
-    fast = FusedYachtEvaluator(net, max_batch=n, trunk_kernel=True)
+    fast = FusedYachtEvaluator(net, max_batch=n, trunk_kernel=True, whole_forward=False)
     slow = FusedYachtEvaluator(net, max_batch=n, trunk_kernel=False)
     lf, vf = fast(x)
     lf, vf = lf.clone(), vf.clone()
@@ -382,3 +382,42 @@ def test_tcgen05_trunk_kernel_matches_layerwise_path():
     assert err_fast <= 1.25 * err_slow + 0.01, (err_fast, err_slow)
     assert (vf - ref_v.reshape(-1)).abs().max().item() <= 1.25 * (vs - ref_v.reshape(-1)).abs().max().item() + 0.01
     assert (lf[:, :3226].float() - ls[:, :3226].float()).abs().max().item() < 0.02 * ref_logits.abs().max().item()
+
+
+def test_whole_forward_kernel():
+    """csrc/ya_forward.cu: features -> logits / values in one tcgen05 kernel, against the layer-by-layer path and
+    the fp32 module (same yardstick as the other evaluator tests), and batch invariance: a row evaluated alone,
+    in a small batch or in a large one gives bit-identical logits and value."""
+    from nypc_yacht_auction_b200.mcts import FusedYachtEvaluator
+    from nypc_yacht_auction_b200.nnet import YachtPolicyValueNet
+    torch.manual_seed(3)
+    net = YachtPolicyValueNet().cuda().eval()
+    with torch.no_grad():
+        for p in net.parameters():
+            if p.ndim == 1:
+                p.add_(0.1 * torch.randn_like(p))
+    n = 777
+    env = _engine(n, 6, 6)
+    for _ in range(11):
+        env.play_ply(masks=None, auto_reset=False)
+    x = env.features()
+    one = FusedYachtEvaluator(net, max_batch=n)
+    assert one.whole_forward
+    slow = FusedYachtEvaluator(net, max_batch=n, trunk_kernel=False, whole_forward=False)
+    lf, vf = one(x)
+    lf, vf = lf.clone(), vf.clone()
+    ls, vs = slow(x)
+    with torch.no_grad():
+        ref_logits, ref_v = net(x)
+    err_fast = (lf[:, :3226].float() - ref_logits).abs().max().item()
+    err_slow = (ls[:, :3226].float() - ref_logits).abs().max().item()
+    assert err_fast <= 1.25 * err_slow + 0.01, (err_fast, err_slow)
+    v_fast = (vf - ref_v.reshape(-1)).abs().max().item()
+    v_slow = (vs - ref_v.reshape(-1)).abs().max().item()
+    assert v_fast <= 1.25 * v_slow + 0.01, (v_fast, v_slow)
+    tv = 0.5 * (torch.softmax(lf[:, :3226].float(), 1) - torch.softmax(ref_logits, 1)).abs().sum(1).max().item()
+    assert tv < 0.02, tv
+    # batch invariance (bitwise)
+    for lo, hi in ((0, 1), (5, 6), (100, 229), (640, 777)):
+        l2, v2 = one(x[lo:hi].contiguous())
+        assert torch.equal(l2[:, :3226], lf[lo:hi, :3226]) and torch.equal(v2, vf[lo:hi])
