@@ -154,11 +154,13 @@ int ya_mcts_expand(const ya_mcts_tree* tree, const float* pi, const float* value
                    float uniform_v, uint32_t* sim_counter, int32_t* err_flag, void* stream);
 
 /* Same as ya_mcts_expand, fed with the raw policy-head output: bf16 logits [n][ld] (ld >= 3232 and a multiple of 8,
- * e.g. the head padded to 3232 columns for an aligned GEMM; base 16-byte aligned).  pi = exp(l - max) / sum(exp(l - max)) in float32
- * (the softmax of NNetWrapper.predict, yacht/NNet.py:193), masking and renormalisation are fused in
- * the kernel, so neither float32 logits nor pi are ever written to HBM. */
-int ya_mcts_expand_logits(const ya_mcts_tree* tree, const void* logits_bf16, int64_t ld, const float* value,
-                          uint32_t* sim_counter, int32_t* err_flag, void* stream);
+ * e.g. the head padded to 3232 columns; base 16-byte aligned).  The softmax of NNetWrapper.predict
+ * (yacht/NNet.py:193), masking and renormalisation (MCTS.py:88-101) are fused:
+ * P[a] = exp(l[a] - max) / sum over legal a' of exp(l[a'] - max), float32, max taken over all 3,226 logits;
+ * only the legal logits are read, neither float32 logits nor pi are ever written to HBM.
+ * row_max float32[n] = that per-row maximum (written by ya_nn_forward), or NULL: the kernel scans the row. */
+int ya_mcts_expand_logits(const ya_mcts_tree* tree, const void* logits_bf16, int64_t ld, const float* row_max,
+                          const float* value, uint32_t* sim_counter, int32_t* err_flag, void* stream);
 
 /* getActionProb's whole simulation loop (MCTS.py:37-38) in ONE launch for the uniform evaluator
  * (pi = uniform_p, v = uniform_v; BASELINE.json configs[2]): num_sims x (descent, expansion, backup) per
@@ -209,8 +211,9 @@ int ya_nn_trunk(const void* x, void* out, const void* weight_images, const float
  * weights, the value head's first Linear and 26 policy-head tiles of 128 columns; biases and LayerNorm
  * parameters as float32.  offsets (HOST pointer, int64[9]) = byte offsets {w_in, w_trunk, w_v, w_pi} and float
  * offsets {p_in, p_trunk, p_v, p_pi_ln, p_pi_bias}.  hidden width 256 only.  Rows are independent of the
- * batch they sit in (batch-invariant evaluator). */
-int ya_nn_forward(const float* features, void* logits_bf16, float* values, const void* weight_blob,
+ * batch they sit in (batch-invariant evaluator).  row_max float32[n] (may be NULL) receives each row's largest
+ * logit over the 3,226 real columns, for ya_mcts_expand_logits. */
+int ya_nn_forward(const float* features, void* logits_bf16, float* values, float* row_max, const void* weight_blob,
                   const float* param_blob, const int64_t* offsets, int nblocks, int64_t n, float eps, void* stream);
 
 /* ---- host-buffer variants (end-to-end path for callers that keep boards in host memory) ----

@@ -27,7 +27,9 @@ constexpr int kPolicyCols = 3232, kPolicyTile = 128, kPolicyTiles = 26;        /
 constexpr int kABytes = kRows * kDim * 2;            // 64 KB
 constexpr int kWBytes = kDim * kDim * 2;             // 128 KB (two 64 KB halves for the N = 128 stages)
 constexpr int kPrmFloats = 776;                      // largest parameter block (value head), 16-byte multiple
-constexpr int kSmemBytes = 1024 + kABytes + kWBytes + 2 * kPrmFloats * 4 + kRows * kParts * 8 + 64;
+constexpr int kPiPrmFloats = 2 * kDim + kPolicyTiles * kPolicyTile;            // gamma_pi | beta_pi | bias of all 3,328 columns
+constexpr int kActions = 3226;
+constexpr int kSmemBytes = 1024 + kABytes + kWBytes + 2 * kPrmFloats * 4 + kPiPrmFloats * 4 + kRows * kParts * 8 + 64;
 
 struct Blob {                                        // byte / float offsets of the host-built blobs (see mcts.py)
     int64_t w_in, w_trunk, w_v, w_pi;
@@ -54,15 +56,16 @@ __device__ __forceinline__ void pack_store_a(uint8_t* a_tile, int row, int c8_fi
 
 __global__ void __launch_bounds__(kThreads, 1)
 ya_k_forward(const float* __restrict__ features, __nv_bfloat16* __restrict__ logits, float* __restrict__ values,
-             const uint8_t* __restrict__ wblob, const float* __restrict__ pblob, Blob off, int nblocks, int64_t n, float eps) {
+             float* __restrict__ row_max, const uint8_t* __restrict__ wblob, const float* __restrict__ pblob, Blob off, int nblocks, int64_t n, float eps) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* a_tile = base;
     uint8_t* w_tile = base + kABytes;
     float* prm_all = reinterpret_cast<float*>(w_tile + kWBytes);
-    float2* xchg = reinterpret_cast<float2*>(prm_all + 2 * kPrmFloats);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(xchg + kParts * kRows);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+    float* pi_prm = prm_all + 2 * kPrmFloats;
+    float2* xchg = reinterpret_cast<float2*>(pi_prm + kPiPrmFloats);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(xchg + kParts * kRows);     // [0] weights landed, [1] / [2] MMA done
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int row = (warp & 3) * 32 + lane;
@@ -72,6 +75,7 @@ ya_k_forward(const float* __restrict__ features, __nv_bfloat16* __restrict__ log
     if (tid == 0) {
         mbar_init(&bars[0], 1);
         mbar_init(&bars[1], 1);
+        mbar_init(&bars[2], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -89,11 +93,12 @@ ya_k_forward(const float* __restrict__ features, __nv_bfloat16* __restrict__ log
     int stage = 0;                                                    // parameter double buffer index = stage & 1
 
     // one weight image + one parameter block per stage, on one transaction barrier
-    auto load_stage = [&](uint8_t* w_dst, int64_t w_src, uint32_t w_bytes, int buf, int64_t p_src, uint32_t p_floats) {
+    auto load_stage = [&](uint8_t* w_dst, int64_t w_src, uint32_t w_bytes, float* p_dst, int64_t p_src, uint32_t p_floats) {
         mbar_expect_tx(&bars[0], w_bytes + p_floats * 4);
         for (uint32_t o = 0; o < w_bytes; o += 32768) bulk_g2s(w_dst + o, wblob + w_src + o, min(32768u, w_bytes - o), &bars[0]);
-        if (p_floats) bulk_g2s(prm_all + buf * kPrmFloats, pblob + p_src, p_floats * 4, &bars[0]);
+        if (p_floats) bulk_g2s(p_dst, pblob + p_src, p_floats * 4, &bars[0]);
     };
+    auto prm_buf = [&](int buf) { return prm_all + (buf & 1) * kPrmFloats; };
     // MMA of one stage: A tile (n_kb K-blocks of 64) x weight image at w_src (rows = n_cols) -> TMEM column d_col
     auto run_mma = [&](const uint8_t* w_src, int n_kb, int n_cols, uint32_t d_col) {
         proxy_fence();                                                // A tile written through the generic proxy
@@ -130,7 +135,7 @@ ya_k_forward(const float* __restrict__ features, __nv_bfloat16* __restrict__ log
     };
 
     // ---------------------------------------------------------------- input stage
-    if (tid == 0) load_stage(w_tile, off.w_in, 256 * 128, 0, off.p_in, 3 * kDim);
+    if (tid == 0) load_stage(w_tile, off.w_in, 256 * 128, prm_buf(0), off.p_in, 3 * kDim);
     {   // features (float32 [n][59]) -> bf16, K padded to 64: this thread fills chunks 2*part, 2*part+1 of K-block 0
         uint32_t f[32];
 #pragma unroll
@@ -150,7 +155,7 @@ ya_k_forward(const float* __restrict__ features, __nv_bfloat16* __restrict__ log
         }
     }
     run_mma(w_tile, 1, kDim, 0);
-    if (tid == 0) load_stage(w_tile, off.w_trunk, kWBytes, 1, off.p_trunk, 3 * kDim);      // first trunk layer streams in
+    if (tid == 0) load_stage(w_tile, off.w_trunk, kWBytes, prm_buf(1), off.p_trunk, 3 * kDim);      // first trunk layer streams in
     {   // h = SiLU(LN(z + b)): Linear -> LayerNorm -> SiLU (YachtNNet.py:25-30); also the first skip connection
         const float* prm = prm_all;
         float ps[4] = {0, 0, 0, 0}, pq[4] = {0, 0, 0, 0};
@@ -198,9 +203,9 @@ ya_k_forward(const float* __restrict__ features, __nv_bfloat16* __restrict__ log
         const bool second = l & 1;                                    // fc2: add the skip connection
         run_mma(w_tile, 4, kDim, 0);
         if (tid == 0) {                                               // next stage's weights under this epilogue
-            if (l + 1 < layers) load_stage(w_tile, off.w_trunk + (int64_t)(l + 1) * kWBytes, kWBytes, (stage + 1) & 1,
+            if (l + 1 < layers) load_stage(w_tile, off.w_trunk + (int64_t)(l + 1) * kWBytes, kWBytes, prm_buf(stage + 1),
                                            off.p_trunk + (int64_t)(l + 1) * 3 * kDim, 3 * kDim);
-            else load_stage(w_tile, off.w_v, 128 * 512, (stage + 1) & 1, off.p_v, 772);
+            else load_stage(w_tile, off.w_v, 128 * 512, prm_buf(stage + 1), off.p_v, 772);
         }
         float ps[4] = {0, 0, 0, 0}, pq[4] = {0, 0, 0, 0};
 #pragma unroll
@@ -277,7 +282,7 @@ ya_k_forward(const float* __restrict__ features, __nv_bfloat16* __restrict__ log
         mbar_wait(&bars[0], w_phase);                                 // the LayerNorm parameters travel with the weights
         head_prep(prm, prm + kDim);
         run_mma(w_tile, 4, 128, 0);                                   // (re-waits the same completed phase, then flips it)
-        if (tid == 0) load_stage(w_tile + 65536, off.w_pi, 65536, (stage + 1) & 1, off.p_pi_ln, 2 * kDim + kPolicyTile);
+        if (tid == 0) load_stage(w_tile + 65536, off.w_pi, 65536, pi_prm, off.p_pi_ln, kPiPrmFloats);
         uint32_t r[32];
         tmem_ld32(t_lane + part * 32, r);
         tmem_ld_wait();
@@ -302,54 +307,84 @@ ya_k_forward(const float* __restrict__ features, __nv_bfloat16* __restrict__ log
         ++stage;
     }
 
-    // policy head (YachtNNet.py:38-42): LN -> SiLU -> Linear(256, 3226), 26 tiles of 128 columns, weight tiles
-    // ping-pong between the two 64 KB halves of the weight region
+    // policy head (YachtNNet.py:38-42): LN -> SiLU -> Linear(256, 3226) as 26 tiles of 128 columns.  Weight tiles
+    // ping-pong between the two 64 KB halves of the weight region and accumulators between TMEM columns 0 and 128,
+    // so the MMA of tile j + 1 and the load of tile j + 2 run under the epilogue of tile j.
     {
-        const float* prm0 = prm_all + (stage & 1) * kPrmFloats;      // gamma_pi | beta_pi | bias of tile 0
-        mbar_wait(&bars[0], w_phase);
-        head_prep(prm0, prm0 + kDim);
-        for (int j = 0; j < kPolicyTiles; ++j, ++stage) {
-            const float* bias = prm_all + (stage & 1) * kPrmFloats + (j == 0 ? 2 * kDim : 0);
-            uint8_t* wj = w_tile + ((j + 1) & 1) * 65536;             // tile 0 went to the upper half
-            proxy_fence();
-            tc_fence_before();
-            __syncthreads();
-            mbar_wait(&bars[0], w_phase);
-            w_phase ^= 1;
-            if (tid == 0) {
-                tc_fence_after();
-                if (j + 1 < kPolicyTiles)                             // next tile into the other half (its last reader finished)
-                    load_stage(w_tile + (j & 1) * 65536, off.w_pi + (int64_t)(j + 1) * 65536, 65536, (stage + 1) & 1,
-                               off.p_pi_bias + (int64_t)(j + 1) * kPolicyTile, kPolicyTile);
-                const uint32_t a0 = smem_u32(a_tile), b0 = smem_u32(wj);
-                const uint32_t idesc = umma_idesc(kPolicyTile);
+        mbar_wait(&bars[0], w_phase);                                 // tile 0, gamma_pi | beta_pi and every bias landed
+        w_phase ^= 1;
+        head_prep(pi_prm, pi_prm + kDim);
+        const float* bias_all = pi_prm + 2 * kDim;
+        uint32_t m2_phase = 0;
+        auto issue_tile = [&](int j) {                                // thread 0: tile j's 16 MMAs
+            const uint32_t a0 = smem_u32(a_tile), b0 = smem_u32(w_tile + ((j + 1) & 1) * 65536);   // tile 0 sits in the upper half
+            const uint32_t idesc = umma_idesc(kPolicyTile);
 #pragma unroll
-                for (int kb = 0; kb < 4; ++kb)
+            for (int kb = 0; kb < 4; ++kb)
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        umma(tmem, umma_desc(a0 + kb * (kRows * 128) + k * 32), umma_desc(b0 + kb * (kPolicyTile * 128) + k * 32),
-                             (uint32_t)((kb | k) != 0), idesc);
-                umma_commit(&bars[1]);
-            }
-            mbar_wait(&bars[1], m_phase);
-            m_phase ^= 1;
+                for (int k = 0; k < 4; ++k)
+                    umma(tmem + (j & 1) * kPolicyTile, umma_desc(a0 + kb * (kRows * 128) + k * 32),
+                         umma_desc(b0 + kb * (kPolicyTile * 128) + k * 32), (uint32_t)((kb | k) != 0), idesc);
+            umma_commit(&bars[1 + (j & 1)]);
+        };
+        proxy_fence();
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
             tc_fence_after();
+            load_stage(w_tile, off.w_pi + 65536, 65536, nullptr, 0, 0);           // tile 1 -> lower half (value head is done with it)
+            issue_tile(0);
+        }
+        float row_mx = -3.0e38f;
+        for (int j = 0; j < kPolicyTiles; ++j) {
+            tc_fence_before();
+            __syncthreads();                                          // every thread has drained tile j - 1's accumulator
+            if (tid == 0 && j + 1 < kPolicyTiles) {
+                tc_fence_after();
+                mbar_wait(&bars[0], w_phase);                         // tile j + 1 landed
+                issue_tile(j + 1);
+            }
+            if (j + 1 < kPolicyTiles) w_phase ^= 1;
+            if (j & 1) { mbar_wait(&bars[2], m2_phase); m2_phase ^= 1; }
+            else { mbar_wait(&bars[1], m_phase); m_phase ^= 1; }
+            tc_fence_after();
+            if (tid == 0 && j + 2 < kPolicyTiles)                     // tile j's half is free again
+                load_stage(w_tile + ((j + 1) & 1) * 65536, off.w_pi + (int64_t)(j + 2) * 65536, 65536, nullptr, 0, 0);
             uint32_t r[32];
-            tmem_ld32(t_lane + part * 32, r);
+            tmem_ld32(t_lane + (j & 1) * kPolicyTile + part * 32, r);
             tmem_ld_wait();
             const int col0 = j * kPolicyTile + part * 32;
-            if (grow < n && col0 < kPolicyCols) {
-                uint32_t p[16];
+            if (col0 < kPolicyCols) {
+                const float* bias = bias_all + col0;
+                float f[32];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(r[2 * i]) + bias[part * 32 + 2 * i],
-                                                             __uint_as_float(r[2 * i + 1]) + bias[part * 32 + 2 * i + 1]);
-                    p[i] = *reinterpret_cast<uint32_t*>(&h);
+                for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(r[i]) + bias[i];
+                if (col0 + 32 <= kActions) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) row_mx = fmaxf(row_mx, f[i]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) if (col0 + i < kActions) row_mx = fmaxf(row_mx, f[i]);
                 }
-                uint4* dst = reinterpret_cast<uint4*>(logits + grow * kPolicyCols + col0);
+                if (grow < n) {
+                    uint32_t p[16];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) dst[q] = make_uint4(p[4 * q], p[4 * q + 1], p[4 * q + 2], p[4 * q + 3]);
+                    for (int i = 0; i < 16; ++i) {
+                        __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+                        p[i] = *reinterpret_cast<uint32_t*>(&h);
+                    }
+                    uint4* dst = reinterpret_cast<uint4*>(logits + grow * kPolicyCols + col0);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) dst[q] = make_uint4(p[4 * q], p[4 * q + 1], p[4 * q + 2], p[4 * q + 3]);
+                }
             }
+        }
+        // the row's largest logit as the expand kernel will see it (bf16 rounding is monotone)
+        xchg[part * kRows + row].x = row_mx;
+        __syncthreads();
+        if (part == 0 && grow < n && row_max) {
+            float m = fmaxf(fmaxf(row_mx, xchg[1 * kRows + row].x), fmaxf(xchg[2 * kRows + row].x, xchg[3 * kRows + row].x));
+            row_max[grow] = __bfloat162float(__float2bfloat16_rn(m));
         }
     }
     tc_fence_before();
@@ -359,7 +394,7 @@ ya_k_forward(const float* __restrict__ features, __nv_bfloat16* __restrict__ log
 
 }  // namespace
 
-extern "C" int ya_nn_forward(const float* features, void* logits_bf16, float* values, const void* weight_blob,
+extern "C" int ya_nn_forward(const float* features, void* logits_bf16, float* values, float* row_max, const void* weight_blob,
                              const float* param_blob, const int64_t* offsets, int nblocks, int64_t n, float eps, void* stream) {
     if (n <= 0) return 0;
     if ((reinterpret_cast<uintptr_t>(logits_bf16) | reinterpret_cast<uintptr_t>(weight_blob) |
@@ -373,7 +408,7 @@ extern "C" int ya_nn_forward(const float* features, void* logits_bf16, float* va
     Blob off{offsets[0], offsets[1], offsets[2], offsets[3], offsets[4], offsets[5], offsets[6], offsets[7], offsets[8]};
     int blocks = (int)((n + kRows - 1) / kRows);
     ya_k_forward<<<blocks, kThreads, kSmemBytes, (cudaStream_t)stream>>>(
-        features, static_cast<__nv_bfloat16*>(logits_bf16), values, static_cast<const uint8_t*>(weight_blob), param_blob, off,
+        features, static_cast<__nv_bfloat16*>(logits_bf16), values, row_max, static_cast<const uint8_t*>(weight_blob), param_blob, off,
         nblocks, n, eps);
     return (int)cudaGetLastError();
 }

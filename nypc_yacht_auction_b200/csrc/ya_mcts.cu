@@ -62,6 +62,22 @@ __device__ __forceinline__ View make_view(const ya_mcts_tree& t, int64_t g) {
     return v;
 }
 
+// A node's prior block in the arena: L float32 priors (sign bit = child visited), padded to a multiple of four
+// words, then one word per 32 priors holding 1 + the bit pattern of the largest UNVISITED prior of that group
+// (0 = none left).  UCB for an unvisited child, cpuct * P * sqrt(Ns + EPS), is monotone in P, so the argmax over
+// up to 3,024 unvisited children is: best group from <= 95 words, then the 32 priors of that one group.
+__device__ __forceinline__ int row_words(int L) { return ((L + 3) & ~3) + ((L + 31) >> 5); }
+__device__ __forceinline__ int group_max_at(int L) { return (L + 3) & ~3; }
+
+// writes priors [k0, k0 + 32) of a fresh row (one per lane; lanes with k >= L idle) and the group's maximum
+__device__ __forceinline__ void store_prior_group(float* __restrict__ row, int L, int k0, float p, int lane) {
+    const int k = k0 + lane;
+    uint32_t e = 0;
+    if (k < L) { row[k] = p; e = __float_as_uint(p) + 1u; }
+    e = __reduce_max_sync(0xFFFFFFFFu, e);
+    if (lane == 0) reinterpret_cast<uint32_t*>(row)[group_max_at(L) + (k0 >> 5)] = e;
+}
+
 // A value travelling up the tree with the numeric type Python would give it.
 struct Val {
     double d;        // value (exact float32 value when is_f32)
@@ -124,37 +140,34 @@ __device__ __forceinline__ int ucb_select(const View& v, const uint32_t* node, i
         off = ch[0];
         remaining -= cnt;
     }
-    // unvisited edges: u = cpuct * P * sqrt(Ns + EPS).  Rows start 16-byte aligned: four priors per load.
+    // unvisited edges: u = cpuct * P * sqrt(Ns + EPS), float32.  u is monotone (non-strictly) in P, so the
+    // lowest-index maximiser lives in the lowest group whose largest unvisited prior reaches the maximal u.
     {
-        const uint4* row4 = reinterpret_cast<const uint4*>(row);
-        const int nvec = L >> 2;
-        constexpr int kBatch = 6;                                   // 6 x 16 B in flight per lane before first use
-        for (int j0 = lane; j0 < nvec; j0 += 32 * kBatch) {
-            uint4 q[kBatch];
-#pragma unroll
-            for (int b = 0; b < kBatch; ++b) {
-                int j = j0 + 32 * b;
-                q[b] = j < nvec ? row4[j] : make_uint4(0x80000000u, 0x80000000u, 0x80000000u, 0x80000000u);
-            }
-#pragma unroll
-            for (int b = 0; b < kBatch; ++b) {
-                const uint32_t bits[4] = {q[b].x, q[b].y, q[b].z, q[b].w};
-                const int base = 4 * (j0 + 32 * b);
-#pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    if (bits[t] >> 31) continue;                    // visited (or padding)
-                    float u = __fmul_rn(__fmul_rn(cpuct, __uint_as_float(bits[t])), sq_new);
-                    int i = base + t;
-                    if (u > best || (u == best && i < besti)) { best = u; besti = i; }
-                }
+        const uint32_t* gmax = row + group_max_at(L);
+        const int ngroups = (L + 31) >> 5;
+        float gu = -CUDART_INF_F;
+        int gb = 0x7FFFFFFF;
+        for (int b = lane; b < ngroups; b += 32) {                  // <= 3 words per lane
+            uint32_t e = gmax[b];
+            if (e) {
+                float u = __fmul_rn(__fmul_rn(cpuct, __uint_as_float(e - 1u)), sq_new);
+                if (u > gu) { gu = u; gb = b; }                     // b ascends: ties keep the lower group
             }
         }
-        int i = (nvec << 2) + lane;
-        if (i < L) {
-            uint32_t b = row[i];
-            if (!(b >> 31)) {
-                float u = __fmul_rn(__fmul_rn(cpuct, __uint_as_float(b)), sq_new);
-                if (u > best || (u == best && i < besti)) { best = u; besti = i; }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            float ou = __shfl_xor_sync(0xFFFFFFFFu, gu, o);
+            int ob = __shfl_xor_sync(0xFFFFFFFFu, gb, o);
+            if (ou > gu || (ou == gu && ob < gb)) { gu = ou; gb = ob; }
+        }
+        if (gb != 0x7FFFFFFF) {
+            int i = (gb << 5) + lane;
+            if (i < L) {
+                uint32_t bits = row[i];
+                if (!(bits >> 31)) {
+                    float u = __fmul_rn(__fmul_rn(cpuct, __uint_as_float(bits)), sq_new);
+                    if (u > best || (u == best && i < besti)) { best = u; besti = i; }
+                }
             }
         }
     }
@@ -170,7 +183,7 @@ __device__ __forceinline__ int ucb_select(const View& v, const uint32_t* node, i
 // ---------------------------------------------------------------- backup (MCTS.py:152-164)
 // Returns false if the arena overflowed.
 __device__ __forceinline__ bool backup_edge(const View& v, uint32_t* node, int ai, const Val& val, uint32_t& arena_top, int lane) {
-    int failed = 0;
+    int failed = 0, fresh = 0;
     // locate the edge
     uint32_t off = node[N_EDGES];
     int n_edges = (int)node[N_NEDGE];
@@ -230,6 +243,7 @@ __device__ __forceinline__ bool backup_edge(const View& v, uint32_t* node, int a
                 reinterpret_cast<double*>(ch + 50)[slot] = val.d;
                 node[N_NEDGE] = (uint32_t)(n_edges + 1);
                 v.arena[node[N_PRIOR] + ai] |= 0x80000000u;                 // mark the prior entry as visited
+                fresh = 1;
             } else {
                 failed = 1;
             }
@@ -238,7 +252,18 @@ __device__ __forceinline__ bool backup_edge(const View& v, uint32_t* node, int a
     }
     arena_top = __shfl_sync(0xFFFFFFFFu, arena_top, 0);
     failed = __shfl_sync(0xFFFFFFFFu, failed, 0);
+    fresh = __shfl_sync(0xFFFFFFFFu, fresh, 0);
     __syncwarp();
+    if (fresh) {                                                     // the child's group lost an unvisited prior
+        const int L = ya_legal_count(node[N_DESC]);
+        uint32_t* row = v.arena + node[N_PRIOR];
+        const int i = (ai & ~31) + lane;
+        uint32_t e = 0;
+        if (i < L) { uint32_t b = row[i]; if (!(b >> 31)) e = b + 1u; }
+        e = __reduce_max_sync(0xFFFFFFFFu, e);
+        if (lane == 0) row[group_max_at(L) + (ai >> 5)] = e;
+        __syncwarp();
+    }
     return !failed;
 }
 
@@ -314,7 +339,7 @@ __device__ __forceinline__ void descend(const View& v, YaState cur, Walk& w, uin
                 int L = ya_legal_count(desc);
                 uint32_t row_at = (w.arena_top + 3u) & ~3u;         // 16-byte aligned prior rows
                 if ((int)w.node_count >= v.max_nodes) { w.err = E_NODES_FULL; w.kind = KIND_ERROR; break; }
-                if (row_at + (uint32_t)L > v.arena_words) { w.err = E_ARENA_FULL; w.kind = KIND_ERROR; break; }
+                if (row_at + (uint32_t)row_words(L) > v.arena_words) { w.err = E_ARENA_FULL; w.kind = KIND_ERROR; break; }
                 idx = (int)w.node_count;
                 if (lane == 0) {
                     uint32_t* nd = v.nodes + (int64_t)idx * kNodeWords;
@@ -324,7 +349,7 @@ __device__ __forceinline__ void descend(const View& v, YaState cur, Walk& w, uin
                     v.ht[free_slot] = (uint16_t)(idx + 1);
                 }
                 w.node_count += 1;
-                w.arena_top = row_at + (uint32_t)L;
+                w.arena_top = row_at + (uint32_t)row_words(L);
                 if (FEATURES)
                     for (int f = lane; f < YA_N_FEATURE; f += 32) feat_row[f] = ya_feature(cur, f);
                 w.leaf_node = idx;
@@ -509,17 +534,20 @@ __device__ __forceinline__ void write_prior_row(float* __restrict__ row, uint32_
     if (MODE == 0) {
         total = masked_pairwise_sum([pi](int i) { return pi[i]; }, desc, lane);
         if (total > 0.0f)                                            // Ps /= sum, MCTS.py:90-91
-            for (int k = lane; k < L; k += 32) row[k] = __fdiv_rn(pi[ya_nth_legal(desc, k)], total);
+            for (int k0 = 0; k0 < L; k0 += 32) {
+                const int k = k0 + lane;
+                store_prior_group(row, L, k0, k < L ? __fdiv_rn(pi[ya_nth_legal(desc, k)], total) : 0.0f, lane);
+            }
     } else {
         total = masked_pairwise_sum([uniform_p](int) { return uniform_p; }, desc, lane);
         if (total > 0.0f) {
             float p = __fdiv_rn(uniform_p, total);
-            for (int k = lane; k < L; k += 32) row[k] = p;
+            for (int k0 = 0; k0 < L; k0 += 32) store_prior_group(row, L, k0, p, lane);
         }
     }
     if (!(total > 0.0f)) {                                           // all legal moves masked: uniform over legal, :97-101
         float u = __fdiv_rn(1.0f, (float)L);
-        for (int k = lane; k < L; k += 32) row[k] = u;
+        for (int k0 = 0; k0 < L; k0 += 32) store_prior_group(row, L, k0, u, lane);
     }
 }
 
@@ -552,18 +580,23 @@ ya_k_mcts_expand(ya_mcts_tree tree, const float* __restrict__ pi_all, const floa
     }
 }
 
-// bf16 logits [n][ld] straight from the policy-head GEMM: softmax (float32: exp(l - max) / sum), mask and
-// renormalisation fused, so neither float32 logits nor pi ever touch HBM.  The raw bf16 row is staged once
-// in shared memory (6.3 KB per warp -> 32 resident warps per SM); exp() is two instructions and is simply
-// re-evaluated by each pass (sum, pairwise sum, row write) with the identical expression.
+// bf16 logits [n][ld] straight from the policy head: softmax, mask and renormalisation fused (MCTS.py:86-101 after
+// NNetWrapper.predict's softmax, yacht/NNet.py:193), so neither float32 logits nor pi ever touch HBM:
+//     P[a] = exp(l[a] - max_all) / sum over legal a' of exp(l[a'] - max_all)
+// which is softmax -> mask -> divide by the masked sum with the softmax denominator cancelled.  Only the LEGAL
+// logits are read (202 of 3,226 on a bid ply, 252 per open category on a score ply): asynchronous 4-byte copies
+// compact them into shared memory in row order.  max_all (over all 3,226 logits: it decides when every legal
+// exp underflows and the reference falls back to the uniform row) comes from the forward kernel's epilogue
+// (row_max) or, for other evaluators, from one pass over the row.
 constexpr int kLogitWarps = 4;
-constexpr int kLogitCols = 3232;                                       // 404 vectors of 8 bf16
+constexpr int kLogitCols = 3232;
 __global__ void __launch_bounds__(kLogitWarps * 32)
 ya_k_mcts_expand_logits(ya_mcts_tree tree, const __nv_bfloat16* __restrict__ logits_all, int64_t ld,
-                        const float* __restrict__ value, uint32_t* __restrict__ sim_counter, int32_t* __restrict__ err_flag) {
-    __shared__ __align__(16) uint16_t raw_all[kLogitWarps][kLogitCols];
+                        const float* __restrict__ row_max, const float* __restrict__ value,
+                        uint32_t* __restrict__ sim_counter, int32_t* __restrict__ err_flag) {
+    __shared__ __align__(16) uint32_t raw_all[kLogitWarps][kLogitCols / 2];
     const int lane = threadIdx.x & 31;
-    uint16_t* raw = raw_all[threadIdx.x >> 5];
+    uint32_t* raw = raw_all[threadIdx.x >> 5];
     const int64_t g = (int64_t)blockIdx.x * kLogitWarps + (threadIdx.x >> 5);
     if (sim_counter && blockIdx.x == 0 && threadIdx.x == 0) *sim_counter += 1;
     if (g >= tree.n) return;
@@ -573,71 +606,52 @@ ya_k_mcts_expand_logits(ya_mcts_tree tree, const __nv_bfloat16* __restrict__ log
     const uint32_t desc = node[N_DESC];
     const int L = ya_legal_count(desc);
     if (L > 0) {
-        const uint4* lg4 = reinterpret_cast<const uint4*>(logits_all + g * ld);   // ld % 8 == 0, base 16-byte aligned
-        uint4* raw4 = reinterpret_cast<uint4*>(raw);
-        constexpr int kVec = kLogitCols / 8;                           // 404; vector 403 holds actions 3224, 3225 + padding
-        constexpr int kRounds = (kVec + 31) / 32;
-        float mx = -CUDART_INF_F;
-        {
-            uint4 q[kRounds];
-#pragma unroll
-            for (int r = 0; r < kRounds; ++r) { int j = lane + 32 * r; if (j < kVec) q[r] = lg4[j]; }   // whole row in flight
-#pragma unroll
-            for (int r = 0; r < kRounds; ++r) {
-                int j = lane + 32 * r;
-                if (j < kVec) {
-                    raw4[j] = q[r];
-                    const uint32_t w[4] = {q[r].x, q[r].y, q[r].z, q[r].w};
-#pragma unroll
-                    for (int t = 0; t < 4; ++t) {
-                        if (8 * j + 2 * t < YA_N_ACTION) {             // both halves valid or both padding (3226 is even)
-                            mx = fmaxf(mx, fmaxf(__uint_as_float(w[t] << 16), __uint_as_float(w[t] & 0xFFFF0000u)));
-                        }
-                    }
-                }
+        const uint32_t* lg = reinterpret_cast<const uint32_t*>(logits_all + g * ld);   // two logits per word (ld is even)
+        const uint32_t raw_s = (uint32_t)__cvta_generic_to_shared(raw);
+        auto copy_word = [&](int dst_word, int src_word) {
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(raw_s + 4u * (uint32_t)dst_word), "l"(lg + src_word) : "memory");
+        };
+        if (desc & 1u) {                                               // bid row: actions 0..201
+            for (int j = lane; j < YA_N_BID / 2; j += 32) copy_word(j, j);
+        } else if (desc >> 13) {                                       // ten dice: 252 subsets per open category
+            int k0 = 0;
+            for (uint32_t open = (desc >> 1) & 0xFFFu; open; open &= open - 1, k0 += YA_N_SUBSET / 2) {
+                const int a0 = (YA_N_BID + (__ffs(open) - 1) * YA_N_SUBSET) / 2;
+                for (int t = lane; t < YA_N_SUBSET / 2; t += 32) copy_word(k0 + t, a0 + t);
             }
+        } else {                                                       // five dice: subset 0 of every open category
+            if (lane < L) reinterpret_cast<uint16_t*>(raw)[lane] = reinterpret_cast<const uint16_t*>(lg)[ya_nth_legal(desc, lane)];
         }
+        float mx;
+        if (row_max) {
+            mx = row_max[g];
+        } else {
+            mx = -CUDART_INF_F;
+            for (int j = lane; j < YA_N_ACTION / 2; j += 32) {
+                uint32_t w = lg[j];
+                mx = fmaxf(mx, fmaxf(__uint_as_float(w << 16), __uint_as_float(w & 0xFFFF0000u)));
+            }
 #pragma unroll
-        for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, o));
+            for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, o));
+        }
+        asm volatile("cp.async.wait_all;" ::: "memory");
         __syncwarp();
-        // softmax of the evaluator (NNetWrapper.predict, yacht/NNet.py:193): pi = exp(l - max) / sum
-        float den = 0.0f;
-        for (int j = lane; j < kVec; j += 32) {
-            uint4 q = raw4[j];
-            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+        const uint16_t* rc = reinterpret_cast<const uint16_t*>(raw);
+        auto ex = [rc, mx](int k) { return __expf(__uint_as_float((uint32_t)rc[k] << 16) - mx); };
+        float total = 0.0f;
+        for (int k = lane; k < L; k += 32) total += ex(k);
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                if (8 * j + 2 * t < YA_N_ACTION)
-                    den += __expf(__uint_as_float(w[t] << 16) - mx) + __expf(__uint_as_float(w[t] & 0xFFFF0000u) - mx);
-            }
-        }
-#pragma unroll
-        for (int o = 16; o; o >>= 1) den += __shfl_xor_sync(0xFFFFFFFFu, den, o);
-        const float rden = __fdiv_rn(1.0f, den);
-        const uint16_t* rc = raw;
-        auto pi = [rc, mx, rden](int i) { return __fmul_rn(__expf(__uint_as_float((uint32_t)rc[i] << 16) - mx), rden); };
-        // MCTS.py:88-91: mask, sum in numpy's pairwise order, renormalise.  The evaluator's own softmax is not
-        // bit-comparable with any CPU run anyway, so the renormalisation multiplies by 1 / total (<= 1 ulp from
-        // the true quotient) instead of paying an IEEE division per legal action.
-        float total = masked_pairwise_sum(pi, desc, lane);
+        for (int o = 16; o; o >>= 1) total += __shfl_xor_sync(0xFFFFFFFFu, total, o);
         float* row = reinterpret_cast<float*>(v.arena + node[N_PRIOR]);
         if (total > 0.0f) {
-            const float scale = __fmul_rn(rden, __fdiv_rn(1.0f, total));
-            auto prior = [rc, mx, scale](int i) { return __fmul_rn(__expf(__uint_as_float((uint32_t)rc[i] << 16) - mx), scale); };
-            if (desc & 1u) {                                           // bid row: actions 0..201
-                for (int k = lane; k < YA_N_BID; k += 32) row[k] = prior(k);
-            } else if (desc >> 13) {                                   // ten dice: 252 subsets per open category
-                int k0 = 0;
-                for (uint32_t open = (desc >> 1) & 0xFFFu; open; open &= open - 1, k0 += YA_N_SUBSET) {
-                    const int a0 = YA_N_BID + (__ffs(open) - 1) * YA_N_SUBSET;
-                    for (int t = lane; t < YA_N_SUBSET; t += 32) row[k0 + t] = prior(a0 + t);
-                }
-            } else {                                                   // five dice: subset 0 of every open category
-                for (int k = lane; k < L; k += 32) row[k] = prior(ya_nth_legal(desc, k));
+            const float scale = __fdiv_rn(1.0f, total);
+            for (int k0 = 0; k0 < L; k0 += 32) {
+                const int k = k0 + lane;
+                store_prior_group(row, L, k0, k < L ? __fmul_rn(ex(k), scale) : 0.0f, lane);
             }
-        } else {
-            float u = __fdiv_rn(1.0f, (float)L);
-            for (int k = lane; k < L; k += 32) row[k] = u;
+        } else {                                                       // every legal move underflowed: MCTS.py:97-101
+            const float u = __fdiv_rn(1.0f, (float)L);
+            for (int k0 = 0; k0 < L; k0 += 32) store_prior_group(row, L, k0, u, lane);
         }
     }
     __syncwarp();
@@ -897,13 +911,13 @@ int ya_mcts_expand(const ya_mcts_tree* tree, const float* pi, const float* value
     return (int)cudaGetLastError();
 }
 
-int ya_mcts_expand_logits(const ya_mcts_tree* tree, const void* logits_bf16, int64_t ld, const float* value,
-                          uint32_t* sim_counter, int32_t* err_flag, void* stream) {
+int ya_mcts_expand_logits(const ya_mcts_tree* tree, const void* logits_bf16, int64_t ld, const float* row_max,
+                          const float* value, uint32_t* sim_counter, int32_t* err_flag, void* stream) {
     if (!tree_ok(tree) || ld < kLogitCols || (ld % 8) != 0 || (reinterpret_cast<uintptr_t>(logits_bf16) & 15u))
         return (int)cudaErrorInvalidValue;
     int blocks = (int)((tree->n + kLogitWarps - 1) / kLogitWarps);
     ya_k_mcts_expand_logits<<<blocks, kLogitWarps * 32, 0, (cudaStream_t)stream>>>(
-        *tree, static_cast<const __nv_bfloat16*>(logits_bf16), ld, value, sim_counter, err_flag);
+        *tree, static_cast<const __nv_bfloat16*>(logits_bf16), ld, row_max, value, sim_counter, err_flag);
     return (int)cudaGetLastError();
 }
 

@@ -126,6 +126,7 @@ class FusedYachtEvaluator:
     PADDED = 3232
 
     def __init__(self, net, max_batch, trunk_kernel=True, whole_forward=True):
+        self.last_row_max = None
         sd = {k: v.detach() for k, v in net.state_dict().items()}
         dev = next(net.parameters()).device
         bf = lambda t: t.to(device=dev, dtype=torch.bfloat16).contiguous()
@@ -197,6 +198,7 @@ class FusedYachtEvaluator:
             self.fw_off = (ctypes.c_int64 * 9)(*w_off, p_in, p_trunk, p_v, p_pi_ln, p_pi_ln + 512)
             assert sum(psizes[4:9]) == 772 and psizes[3] == 768 * 2 * self.nblocks
             self.values = torch.empty(int(max_batch), dtype=torch.float32, device=dev)
+            self.row_max = torch.empty(int(max_batch), dtype=torch.float32, device=dev)
 
     @staticmethod
     def swizzled_image(w):
@@ -232,6 +234,7 @@ class FusedYachtEvaluator:
         other._alloc(int(max_batch), self.w_in.device)
         if self.whole_forward:
             other.values = torch.empty(int(max_batch), dtype=torch.float32, device=self.w_in.device)
+            other.row_max = torch.empty(int(max_batch), dtype=torch.float32, device=self.w_in.device)
         return other
 
     def _ln(self, mode, x, ln, out, residual=None, ln2=None, out2=None):
@@ -245,7 +248,9 @@ class FusedYachtEvaluator:
         n = features.shape[0]
         if self.whole_forward:                                            # one tcgen05 kernel: features -> logits, values
             logits, values = self.logits[:n], self.values[:n]
-            _lib.check(self.lib.ya_nn_forward(_lib.ptr(features), _lib.ptr(logits), _lib.ptr(values), _lib.ptr(self.fw_w),
+            self.last_row_max = self.row_max[:n]                          # consumed by ya_mcts_expand_logits
+            _lib.check(self.lib.ya_nn_forward(_lib.ptr(features), _lib.ptr(logits), _lib.ptr(values),
+                                              _lib.ptr(self.last_row_max), _lib.ptr(self.fw_w),
                                               _lib.ptr(self.fw_p), self.fw_off, self.nblocks, n, self.eps,
                                               _lib.current_stream()), "ya_nn_forward")
             return logits, values
@@ -377,8 +382,10 @@ class BatchedMCTS:
         assert v.dtype == torch.float32 and v.is_contiguous() and v.shape == (grp.n,)
         if getattr(ev, "returns_logits", False):
             assert pi.dtype == torch.bfloat16 and pi.is_contiguous() and pi.shape[0] == grp.n
-            _lib.check(self.lib.ya_mcts_expand_logits(grp.ref, _lib.ptr(pi), pi.shape[1], _lib.ptr(v), counter,
-                                                      _lib.ptr(self.err_flag), s), "ya_mcts_expand_logits")
+            row_max = getattr(ev, "last_row_max", None)               # per-row max logit, if the evaluator has it
+            assert row_max is None or (row_max.dtype == torch.float32 and row_max.shape == (grp.n,))
+            _lib.check(self.lib.ya_mcts_expand_logits(grp.ref, _lib.ptr(pi), pi.shape[1], _lib.ptr(row_max), _lib.ptr(v),
+                                                      counter, _lib.ptr(self.err_flag), s), "ya_mcts_expand_logits")
             return
         assert pi.dtype == torch.float32 and pi.is_contiguous() and pi.shape == (grp.n, ACTION_SIZE)
         _lib.check(self.lib.ya_mcts_expand(grp.ref, _lib.ptr(pi), _lib.ptr(v), 0, 0.0, 0.0, counter,

@@ -417,6 +417,7 @@ def test_whole_forward_kernel():
     assert v_fast <= 1.25 * v_slow + 0.01, (v_fast, v_slow)
     tv = 0.5 * (torch.softmax(lf[:, :3226].float(), 1) - torch.softmax(ref_logits, 1)).abs().sum(1).max().item()
     assert tv < 0.02, tv
+    assert torch.equal(one.last_row_max, lf[:, :3226].float().max(dim=1).values)     # epilogue by-product for expand
     # batch invariance (bitwise)
     for lo, hi in ((0, 1), (5, 6), (100, 229), (640, 777)):
         l2, v2 = one(x[lo:hi].contiguous())
