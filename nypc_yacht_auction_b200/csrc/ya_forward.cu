@@ -21,7 +21,10 @@ namespace {
 
 using namespace ya_tc;
 
-constexpr int kRows = 128, kDim = 256, kThreads = 512, kParts = 4;
+constexpr int kRows = 128, kDim = 256, kParts = 4;
+constexpr int kWorkers = 512;                       // 16 epilogue warps: warp w owns TMEM lanes 32 (w % 4).., column part w / 4
+constexpr int kProducer = kWorkers;                  // lane 0 of a 17th warp issues every bulk copy and every MMA
+constexpr int kThreads = kWorkers + 32;
 constexpr int kFeat = 59;
 constexpr int kPolicyCols = 3232, kPolicyTile = 128, kPolicyTiles = 26;        // 26 * 128 = 3328 >= 3232
 constexpr int kABytes = kRows * kDim * 2;            // 64 KB
@@ -29,12 +32,27 @@ constexpr int kWBytes = kDim * kDim * 2;             // 128 KB (two 64 KB halves
 constexpr int kPrmFloats = 776;                      // largest parameter block (value head), 16-byte multiple
 constexpr int kPiPrmFloats = 2 * kDim + kPolicyTiles * kPolicyTile;            // gamma_pi | beta_pi | bias of all 3,328 columns
 constexpr int kActions = 3226;
+#ifndef YA_FWD_BULK_CHUNK
+#define YA_FWD_BULK_CHUNK 32768
+#endif
+constexpr int kBulkChunk = YA_FWD_BULK_CHUNK;        // bytes per cp.async.bulk request
 constexpr int kSmemBytes = 1024 + kABytes + kWBytes + 2 * kPrmFloats * 4 + kPiPrmFloats * 4 + kRows * kParts * 8 + 64;
 
 struct Blob {                                        // byte / float offsets of the host-built blobs (see mcts.py)
     int64_t w_in, w_trunk, w_v, w_pi;
     int64_t p_in, p_trunk, p_v, p_pi_ln, p_pi_bias;
 };
+
+#ifdef YA_FWD_TIMELINE                                 // profiling build only (profiles/tools/forward_timeline.py)
+__device__ unsigned long long g_timeline[1024];
+#define YA_STAMP() do { if (blockIdx.x == 0 && tid == 0 && tl_n < 1024) { unsigned long long t_; \
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); g_timeline[tl_n++] = t_; } } while (0)
+#define YA_STAMP2() do { if (blockIdx.x == 0 && tl_n < 512) { unsigned long long t_; \
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); g_timeline[512 + tl_n++] = t_; } } while (0)
+#else
+#define YA_STAMP() do { } while (0)
+#define YA_STAMP2() do { } while (0)
+#endif
 
 __device__ __forceinline__ uint32_t a_tile_offset(int r, int c8) {
     int kb = c8 >> 3, chunk = c8 & 7;
@@ -64,18 +82,24 @@ ya_k_forward(const float* __restrict__ features, __nv_bfloat16* __restrict__ log
     float* prm_all = reinterpret_cast<float*>(w_tile + kWBytes);
     float* pi_prm = prm_all + 2 * kPrmFloats;
     float2* xchg = reinterpret_cast<float2*>(pi_prm + kPiPrmFloats);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(xchg + kParts * kRows);     // [0] weights landed, [1] / [2] MMA done
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(xchg + kParts * kRows);     // [0] weights landed, [1] / [2] MMA done,
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);             // [3] / [4] policy weight halves landed,
+                                                                             // [5] / [6] policy accumulator drained
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int row = (warp & 3) * 32 + lane;
     const int part = warp >> 2;
     const int64_t grow = (int64_t)blockIdx.x * kRows + row;
+    const bool worker = warp < kWorkers / 32;                         // the producer warp only keeps the barriers company
 
     if (tid == 0) {
         mbar_init(&bars[0], 1);
         mbar_init(&bars[1], 1);
         mbar_init(&bars[2], 1);
+        mbar_init(&bars[3], 1);
+        mbar_init(&bars[4], 1);
+        mbar_init(&bars[5], kWorkers / 32);
+        mbar_init(&bars[6], kWorkers / 32);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -90,6 +114,7 @@ ya_k_forward(const float* __restrict__ features, __nv_bfloat16* __restrict__ log
     const uint32_t t_acc64 = t_lane + (uint32_t)(part * 64);          // my 64 columns of an N = 256 accumulator
     const uint32_t t_skip = t_lane + 256 + (uint32_t)(part * 64);     // my 64 columns of the float32 skip connection
     uint32_t w_phase = 0, m_phase = 0;
+    int tl_n = 0; (void)tl_n;
     int stage = 0;                                                    // parameter double buffer index = stage & 1
 
     // one weight image + one parameter block per stage, on one transaction barrier
@@ -104,9 +129,11 @@ ya_k_forward(const float* __restrict__ features, __nv_bfloat16* __restrict__ log
         proxy_fence();                                                // A tile written through the generic proxy
         tc_fence_before();
         __syncthreads();
+        YA_STAMP();                                                   // [3k] epilogue of the previous stage done
         mbar_wait(&bars[0], w_phase);                                 // weights + parameters landed
         w_phase ^= 1;
-        if (tid == 0) {
+        YA_STAMP();                                                   // [3k+1] weights landed
+        if (tid == kProducer) {
             tc_fence_after();
             const uint32_t a0 = smem_u32(a_tile), b0 = smem_u32(w_src);
             const uint32_t idesc = umma_idesc(n_cols);
@@ -120,10 +147,12 @@ ya_k_forward(const float* __restrict__ features, __nv_bfloat16* __restrict__ log
         mbar_wait(&bars[1], m_phase);                                 // accumulator ready; A tile and this weight buffer free
         m_phase ^= 1;
         tc_fence_after();
+        YA_STAMP();                                                   // [3k+2] MMA done
     };
+    auto worker_sync = [] { asm volatile("bar.sync 1, %0;" ::"n"(kWorkers) : "memory"); };   // the 16 epilogue warps only
     auto row_stats = [&](float s, float ss, float& mean, float& rstd) {  // LayerNorm statistics over the 4 threads of a row
         xchg[part * kRows + row] = make_float2(s, ss);
-        __syncthreads();
+        worker_sync();
 #pragma unroll
         for (int p = 1; p < kParts; ++p) {
             float2 o = xchg[((part + p) % kParts) * kRows + row];
@@ -131,12 +160,12 @@ ya_k_forward(const float* __restrict__ features, __nv_bfloat16* __restrict__ log
         }
         mean = s * (1.0f / kDim);
         rstd = rsqrtf(fmaxf(ss * (1.0f / kDim) - mean * mean, 0.0f) + eps);
-        __syncthreads();                                              // xchg may be rewritten by the next stage
+        worker_sync();                                                // xchg may be rewritten by the next stage
     };
 
     // ---------------------------------------------------------------- input stage
-    if (tid == 0) load_stage(w_tile, off.w_in, 256 * 128, prm_buf(0), off.p_in, 3 * kDim);
-    {   // features (float32 [n][59]) -> bf16, K padded to 64: this thread fills chunks 2*part, 2*part+1 of K-block 0
+    if (tid == kProducer) load_stage(w_tile, off.w_in, 256 * 128, prm_buf(0), off.p_in, 3 * kDim);
+    if (worker) {   // features (float32 [n][59]) -> bf16, K padded to 64: this thread fills chunks 2*part, 2*part+1 of K-block 0
         uint32_t f[32];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
@@ -155,8 +184,8 @@ ya_k_forward(const float* __restrict__ features, __nv_bfloat16* __restrict__ log
         }
     }
     run_mma(w_tile, 1, kDim, 0);
-    if (tid == 0) load_stage(w_tile, off.w_trunk, kWBytes, prm_buf(1), off.p_trunk, 3 * kDim);      // first trunk layer streams in
-    {   // h = SiLU(LN(z + b)): Linear -> LayerNorm -> SiLU (YachtNNet.py:25-30); also the first skip connection
+    if (tid == kProducer) load_stage(w_tile, off.w_trunk, kWBytes, prm_buf(1), off.p_trunk, 3 * kDim);      // first trunk layer streams in
+    if (worker) {   // h = SiLU(LN(z + b)): Linear -> LayerNorm -> SiLU (YachtNNet.py:25-30); also the first skip connection
         const float* prm = prm_all;
         float ps[4] = {0, 0, 0, 0}, pq[4] = {0, 0, 0, 0};
 #pragma unroll
@@ -202,11 +231,12 @@ ya_k_forward(const float* __restrict__ features, __nv_bfloat16* __restrict__ log
         const float* prm = prm_all + (stage & 1) * kPrmFloats;
         const bool second = l & 1;                                    // fc2: add the skip connection
         run_mma(w_tile, 4, kDim, 0);
-        if (tid == 0) {                                               // next stage's weights under this epilogue
+        if (tid == kProducer) {                                       // next stage's weights under this epilogue
             if (l + 1 < layers) load_stage(w_tile, off.w_trunk + (int64_t)(l + 1) * kWBytes, kWBytes, prm_buf(stage + 1),
                                            off.p_trunk + (int64_t)(l + 1) * 3 * kDim, 3 * kDim);
             else load_stage(w_tile, off.w_v, 128 * 512, prm_buf(stage + 1), off.p_v, 772);
         }
+        if (!worker) continue;
         float ps[4] = {0, 0, 0, 0}, pq[4] = {0, 0, 0, 0};
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
@@ -247,7 +277,9 @@ ya_k_forward(const float* __restrict__ features, __nv_bfloat16* __restrict__ log
     }
 
     // ---------------------------------------------------------------- heads: a = SiLU(LN(h; gamma, beta)) from the skip
-    auto head_prep = [&](const float* gamma_all, const float* beta_all) {
+    // to_tmem: the activations go to tensor-memory columns [0, 128) as packed bf16 pairs (A operand read from TMEM)
+    auto head_prep = [&](const float* gamma_all, const float* beta_all, bool to_tmem) {
+        if (!worker) return;
         float ps[4] = {0, 0, 0, 0}, pq[4] = {0, 0, 0, 0};
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
@@ -272,32 +304,46 @@ ya_k_forward(const float* __restrict__ features, __nv_bfloat16* __restrict__ log
                 float y = fmaf(__uint_as_float(r[i]), ga, fmaf(-mean, ga, beta[i]));
                 r[i] = __float_as_uint(silu_from_half(0.5f * y));
             }
-            pack_store_a(a_tile, row, part * 8 + c * 4, r);
+            if (to_tmem) {
+                uint32_t pk[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
+                    pk[i] = *reinterpret_cast<uint32_t*>(&h);
+                }
+                tmem_st16(t_lane + (uint32_t)(part * 32 + c * 16), pk);
+            } else {
+                pack_store_a(a_tile, row, part * 8 + c * 4, r);
+            }
         }
+        if (to_tmem) tmem_st_wait();
     };
 
     // value head (YachtNNet.py:44-50): LN -> SiLU -> Linear(256,128) -> SiLU -> Linear(128,1) -> tanh
     {
         const float* prm = prm_all + (stage & 1) * kPrmFloats;       // gamma_v | beta_v | b1[128] | w2[128] | b2
         mbar_wait(&bars[0], w_phase);                                 // the LayerNorm parameters travel with the weights
-        head_prep(prm, prm + kDim);
+        head_prep(prm, prm + kDim, false);
         run_mma(w_tile, 4, 128, 0);                                   // (re-waits the same completed phase, then flips it)
-        if (tid == 0) load_stage(w_tile + 65536, off.w_pi, 65536, pi_prm, off.p_pi_ln, kPiPrmFloats);
-        uint32_t r[32];
-        tmem_ld32(t_lane + part * 32, r);
-        tmem_ld_wait();
-        const float* b1 = prm + 2 * kDim + part * 32;
-        const float* w2 = prm + 2 * kDim + 128 + part * 32;
-        float acc[4] = {0, 0, 0, 0};
+        if (tid == kProducer) load_stage(w_tile + 65536, off.w_pi, 65536, pi_prm, off.p_pi_ln, kPiPrmFloats);
+        float dot = 0.0f;
+        if (worker) {
+            uint32_t r[32];
+            tmem_ld32(t_lane + part * 32, r);
+            tmem_ld_wait();
+            const float* b1 = prm + 2 * kDim + part * 32;
+            const float* w2 = prm + 2 * kDim + 128 + part * 32;
+            float acc[4] = {0, 0, 0, 0};
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-            float t = silu_from_half(fmaf(__uint_as_float(r[i]), 0.5f, 0.5f * b1[i]));
-            acc[i & 3] = fmaf(t, w2[i], acc[i & 3]);
+            for (int i = 0; i < 32; ++i) {
+                float t = silu_from_half(fmaf(__uint_as_float(r[i]), 0.5f, 0.5f * b1[i]));
+                acc[i & 3] = fmaf(t, w2[i], acc[i & 3]);
+            }
+            dot = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+            xchg[part * kRows + row] = make_float2(dot, 0.0f);
         }
-        float dot = (acc[0] + acc[1]) + (acc[2] + acc[3]);
-        xchg[part * kRows + row] = make_float2(dot, 0.0f);
         __syncthreads();
-        if (part == 0 && grow < n) {
+        if (worker && part == 0 && grow < n) {
             float s = dot + xchg[1 * kRows + row].x + xchg[2 * kRows + row].x + xchg[3 * kRows + row].x + prm[2 * kDim + 256];
             float th;
             asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(s));
@@ -308,81 +354,119 @@ ya_k_forward(const float* __restrict__ features, __nv_bfloat16* __restrict__ log
     }
 
     // policy head (YachtNNet.py:38-42): LN -> SiLU -> Linear(256, 3226) as 26 tiles of 128 columns.  Weight tiles
-    // ping-pong between the two 64 KB halves of the weight region and accumulators between TMEM columns 0 and 128,
-    // so the MMA of tile j + 1 and the load of tile j + 2 run under the epilogue of tile j.
+    // ping-pong between the two 64 KB halves of the weight region (one transaction barrier per half) and
+    // accumulators between TMEM columns 0 and 128: as soon as tile j's MMAs retire, tile j + 2 starts streaming
+    // into the half they read and tile j + 1's MMAs are issued, all under the epilogue of tile j.
     {
         mbar_wait(&bars[0], w_phase);                                 // tile 0, gamma_pi | beta_pi and every bias landed
         w_phase ^= 1;
-        head_prep(pi_prm, pi_prm + kDim);
+        head_prep(pi_prm, pi_prm + kDim, true);
         const float* bias_all = pi_prm + 2 * kDim;
-        uint32_t m2_phase = 0;
-        auto issue_tile = [&](int j) {                                // thread 0: tile j's 16 MMAs
-            const uint32_t a0 = smem_u32(a_tile), b0 = smem_u32(w_tile + ((j + 1) & 1) * 65536);   // tile 0 sits in the upper half
+        auto tile_half = [&](int j) { return w_tile + ((j + 1) & 1) * 65536; };     // tile 0 sits in the upper half
+        auto load_tile = [&](int j) {                                 // producer thread, j >= 1
+            uint64_t* bar = &bars[3 + (j & 1)];
+#ifdef YA_FWD_EXP_NOLOAD
+            mbar_expect_tx(bar, 1024);
+            bulk_g2s(tile_half(j), wblob + off.w_pi + (int64_t)j * 65536, 1024, bar);
+#else
+            mbar_expect_tx(bar, 65536);
+#pragma unroll
+            for (int o = 0; o < 65536; o += kBulkChunk) bulk_g2s(tile_half(j) + o, wblob + off.w_pi + (int64_t)j * 65536 + o, kBulkChunk, bar);
+#endif
+        };
+        auto issue_tile = [&](int j) {                                // producer thread: tile j's 16 MMAs
+            const uint32_t b0 = smem_u32(tile_half(j));
             const uint32_t idesc = umma_idesc(kPolicyTile);
 #pragma unroll
             for (int kb = 0; kb < 4; ++kb)
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                    umma(tmem + (j & 1) * kPolicyTile, umma_desc(a0 + kb * (kRows * 128) + k * 32),
-                         umma_desc(b0 + kb * (kPolicyTile * 128) + k * 32), (uint32_t)((kb | k) != 0), idesc);
+                    umma_ts(tmem + kPolicyTile + (j & 1) * kPolicyTile, tmem + kb * 32 + k * 8,
+                            umma_desc(b0 + kb * (kPolicyTile * 128) + k * 32), (uint32_t)((kb | k) != 0), idesc);
             umma_commit(&bars[1 + (j & 1)]);
         };
         proxy_fence();
         tc_fence_before();
-        __syncthreads();
-        if (tid == 0) {
-            tc_fence_after();
-            load_stage(w_tile, off.w_pi + 65536, 65536, nullptr, 0, 0);           // tile 1 -> lower half (value head is done with it)
-            issue_tile(0);
-        }
+        __syncthreads();                                              // the A tile (p) is complete
+        tc_fence_after();
+        const uint32_t m1_base = m_phase;                             // parity of bars[1] for policy tile 0
+        auto mma_parity = [&](int j) { return (j & 1) ? (uint32_t)((j >> 1) & 1) : (m1_base ^ (uint32_t)((j >> 1) & 1)); };
         float row_mx = -3.0e38f;
-        for (int j = 0; j < kPolicyTiles; ++j) {
-            tc_fence_before();
-            __syncthreads();                                          // every thread has drained tile j - 1's accumulator
-            if (tid == 0 && j + 1 < kPolicyTiles) {
+        if (tid == kProducer) {
+            // Producer: keeps the tensor pipe fed.  Tile j needs its weights (landed), and its accumulator half
+            // drained by the epilogue of tile j - 2; tile j + 1's weights go where tile j - 1's were as soon as
+            // tile j - 1's MMAs have retired -- by then tile j's MMAs are already queued behind them.
+            load_tile(1);                                             // lower half: the value head is done with it
+            for (int j = 0; j < kPolicyTiles; ++j) {
+                YA_STAMP2();                                          // [5j] loop top
+                if (j >= 1) mbar_wait(&bars[3 + (j & 1)], (uint32_t)(((j - 1) >> 1) & 1));
+                YA_STAMP2();                                          // [5j+1] weights landed
+                if (j >= 2) mbar_wait(&bars[5 + (j & 1)], (uint32_t)(((j - 2) >> 1) & 1));
+                YA_STAMP2();                                          // [5j+2] accumulator drained
                 tc_fence_after();
-                mbar_wait(&bars[0], w_phase);                         // tile j + 1 landed
-                issue_tile(j + 1);
-            }
-            if (j + 1 < kPolicyTiles) w_phase ^= 1;
-            if (j & 1) { mbar_wait(&bars[2], m2_phase); m2_phase ^= 1; }
-            else { mbar_wait(&bars[1], m_phase); m_phase ^= 1; }
-            tc_fence_after();
-            if (tid == 0 && j + 2 < kPolicyTiles)                     // tile j's half is free again
-                load_stage(w_tile + ((j + 1) & 1) * 65536, off.w_pi + (int64_t)(j + 2) * 65536, 65536, nullptr, 0, 0);
-            uint32_t r[32];
-            tmem_ld32(t_lane + (j & 1) * kPolicyTile + part * 32, r);
-            tmem_ld_wait();
-            const int col0 = j * kPolicyTile + part * 32;
-            if (col0 < kPolicyCols) {
-                const float* bias = bias_all + col0;
-                float f[32];
-#pragma unroll
-                for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(r[i]) + bias[i];
-                if (col0 + 32 <= kActions) {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) row_mx = fmaxf(row_mx, f[i]);
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) if (col0 + i < kActions) row_mx = fmaxf(row_mx, f[i]);
+                issue_tile(j);
+                YA_STAMP2();                                          // [5j+3] MMAs issued
+                if (j >= 1 && j + 1 < kPolicyTiles) {
+                    mbar_wait(&bars[1 + ((j - 1) & 1)], mma_parity(j - 1));
+                    load_tile(j + 1);
                 }
-                if (grow < n) {
-                    uint32_t p[16];
+                YA_STAMP2();                                          // [5j+4] previous tile retired, next load issued
+            }
+        } else if (worker) {
+            for (int j = 0; j < kPolicyTiles; ++j) {
+                mbar_wait(&bars[1 + (j & 1)], mma_parity(j));
+                tc_fence_after();
+                YA_STAMP();                                           // policy tile j: accumulator ready
+                uint32_t r[32];
+#ifdef YA_FWD_EXP_NOTMEMLD
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
-                        p[i] = *reinterpret_cast<uint32_t*>(&h);
+                for (int i = 0; i < 32; ++i) r[i] = (uint32_t)(j + i);
+#else
+                tmem_ld32(t_lane + kPolicyTile + (j & 1) * kPolicyTile + part * 32, r);
+                tmem_ld_wait();
+#endif
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars[5 + (j & 1)]);       // this warp's share of the accumulator is in registers
+                const int col0 = j * kPolicyTile + part * 32;
+                if (col0 < kPolicyCols) {
+                    const float* bias = bias_all + col0;
+                    float f[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(r[i]) + bias[i];
+                    if (col0 + 32 <= kActions) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) row_mx = fmaxf(row_mx, f[i]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) if (col0 + i < kActions) row_mx = fmaxf(row_mx, f[i]);
                     }
-                    uint4* dst = reinterpret_cast<uint4*>(logits + grow * kPolicyCols + col0);
+                    if (grow < n) {
+                        uint32_t p[16];
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) dst[q] = make_uint4(p[4 * q], p[4 * q + 1], p[4 * q + 2], p[4 * q + 3]);
+                        for (int i = 0; i < 16; ++i) {
+                            __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+                            p[i] = *reinterpret_cast<uint32_t*>(&h);
+                        }
+                        __nv_bfloat16* dst = logits + grow * kPolicyCols + col0;    // 64 bytes, 32-byte aligned
+#ifndef YA_FWD_EXP_NOSTORE
+#pragma unroll
+                        for (int q = 0; q < 2; ++q)                   // 256-bit stores: half the LSU work of 4 x 16 bytes
+                            asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + 16 * q),
+                                         "r"(p[8 * q]), "r"(p[8 * q + 1]), "r"(p[8 * q + 2]), "r"(p[8 * q + 3]), "r"(p[8 * q + 4]),
+                                         "r"(p[8 * q + 5]), "r"(p[8 * q + 6]), "r"(p[8 * q + 7]) : "memory");
+#else
+                        if (p[0] == 0x12345678u && p[5] == 0x9abcdef0u) *reinterpret_cast<uint4*>(dst) = make_uint4(p[1] ^ p[9], p[2] ^ p[10], p[3] ^ p[11], p[4] ^ p[15]);
+#endif
+                    }
                 }
             }
         }
+        YA_STAMP();
         // the row's largest logit as the expand kernel will see it (bf16 rounding is monotone)
-        xchg[part * kRows + row].x = row_mx;
+        if (worker) xchg[part * kRows + row].x = row_mx;
         __syncthreads();
-        if (part == 0 && grow < n && row_max) {
+        if (worker && part == 0 && grow < n && row_max) {
             float m = fmaxf(fmaxf(row_mx, xchg[1 * kRows + row].x), fmaxf(xchg[2 * kRows + row].x, xchg[3 * kRows + row].x));
             row_max[grow] = __bfloat162float(__float2bfloat16_rn(m));
         }
@@ -394,11 +478,17 @@ ya_k_forward(const float* __restrict__ features, __nv_bfloat16* __restrict__ log
 
 }  // namespace
 
+#ifdef YA_FWD_TIMELINE
+extern "C" int ya_debug_forward_timeline(unsigned long long* host_out) {
+    return (int)cudaMemcpyFromSymbol(host_out, g_timeline, sizeof(unsigned long long) * 1024);
+}
+#endif
+
 extern "C" int ya_nn_forward(const float* features, void* logits_bf16, float* values, float* row_max, const void* weight_blob,
                              const float* param_blob, const int64_t* offsets, int nblocks, int64_t n, float eps, void* stream) {
     if (n <= 0) return 0;
     if ((reinterpret_cast<uintptr_t>(logits_bf16) | reinterpret_cast<uintptr_t>(weight_blob) |
-         reinterpret_cast<uintptr_t>(param_blob)) & 15u) return (int)cudaErrorMisalignedAddress;
+         reinterpret_cast<uintptr_t>(param_blob)) & 31u) return (int)cudaErrorMisalignedAddress;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(ya_k_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
