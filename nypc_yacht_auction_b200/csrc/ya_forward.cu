@@ -22,9 +22,8 @@ namespace {
 using namespace ya_tc;
 
 constexpr int kRows = 128, kDim = 256, kParts = 4;
-constexpr int kWorkers = 512;                       // 16 epilogue warps: warp w owns TMEM lanes 32 (w % 4).., column part w / 4
-constexpr int kProducer = kWorkers;                  // lane 0 of a 17th warp issues every bulk copy and every MMA
-constexpr int kThreads = kWorkers + 32;
+constexpr int kThreads = 512;                       // 16 warps: warp w owns TMEM lanes 32 (w % 4).., column part w / 4
+constexpr int kIssuerWarp = 15;                     // its elected lane issues every bulk copy and every MMA
 constexpr int kFeat = 59;
 constexpr int kPolicyCols = 3232, kPolicyTile = 128, kPolicyTiles = 26;        // 26 * 128 = 3328 >= 3232
 constexpr int kABytes = kRows * kDim * 2;            // 64 KB
@@ -32,11 +31,7 @@ constexpr int kWBytes = kDim * kDim * 2;             // 128 KB (two 64 KB halves
 constexpr int kPrmFloats = 776;                      // largest parameter block (value head), 16-byte multiple
 constexpr int kPiPrmFloats = 2 * kDim + kPolicyTiles * kPolicyTile;            // gamma_pi | beta_pi | bias of all 3,328 columns
 constexpr int kActions = 3226;
-#ifndef YA_FWD_BULK_CHUNK
-#define YA_FWD_BULK_CHUNK 32768
-#endif
-constexpr int kBulkChunk = YA_FWD_BULK_CHUNK;        // bytes per cp.async.bulk request
-constexpr int kSmemBytes = 1024 + kABytes + kWBytes + 2 * kPrmFloats * 4 + kPiPrmFloats * 4 + kRows * kParts * 8 + 64;
+constexpr int kSmemBytes = 1024 + kABytes + kWBytes + 2 * kPrmFloats * 4 + kPiPrmFloats * 4 + kRows * kParts * 8 + 128;
 
 struct Blob {                                        // byte / float offsets of the host-built blobs (see mcts.py)
     int64_t w_in, w_trunk, w_v, w_pi;
@@ -83,14 +78,15 @@ ya_k_forward(const float* __restrict__ features, __nv_bfloat16* __restrict__ log
     float* pi_prm = prm_all + 2 * kPrmFloats;
     float2* xchg = reinterpret_cast<float2*>(pi_prm + kPiPrmFloats);
     uint64_t* bars = reinterpret_cast<uint64_t*>(xchg + kParts * kRows);     // [0] weights landed, [1] / [2] MMA done,
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);             // [3] / [4] policy weight halves landed,
-                                                                             // [5] / [6] policy accumulator drained
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);            // policy head: [3..5] weight slot landed,
+                                                                             // [6..8] accumulator ready, [9..11] drained
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int row = (warp & 3) * 32 + lane;
     const int part = warp >> 2;
     const int64_t grow = (int64_t)blockIdx.x * kRows + row;
-    const bool worker = warp < kWorkers / 32;                         // the producer warp only keeps the barriers company
+    const bool producer = warp == kIssuerWarp;                        // also an epilogue warp, except in the policy head
+    constexpr bool worker = true;
 
     if (tid == 0) {
         mbar_init(&bars[0], 1);
@@ -98,8 +94,8 @@ ya_k_forward(const float* __restrict__ features, __nv_bfloat16* __restrict__ log
         mbar_init(&bars[2], 1);
         mbar_init(&bars[3], 1);
         mbar_init(&bars[4], 1);
-        mbar_init(&bars[5], kWorkers / 32);
-        mbar_init(&bars[6], kWorkers / 32);
+        for (int i = 5; i < 9; ++i) mbar_init(&bars[i], 1);
+        for (int i = 9; i < 12; ++i) mbar_init(&bars[i], 15);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -124,6 +120,7 @@ ya_k_forward(const float* __restrict__ features, __nv_bfloat16* __restrict__ log
         if (p_floats) bulk_g2s(p_dst, pblob + p_src, p_floats * 4, &bars[0]);
     };
     auto prm_buf = [&](int buf) { return prm_all + (buf & 1) * kPrmFloats; };
+    auto policy_slot = [](int j) { return (2 + 2 * j) % 3; };          // tile j -> 64 KB slot: 2, 1, 0, 2, 1, 0, ...
     // MMA of one stage: A tile (n_kb K-blocks of 64) x weight image at w_src (rows = n_cols) -> TMEM column d_col
     auto run_mma = [&](const uint8_t* w_src, int n_kb, int n_cols, uint32_t d_col) {
         proxy_fence();                                                // A tile written through the generic proxy
@@ -133,23 +130,27 @@ ya_k_forward(const float* __restrict__ features, __nv_bfloat16* __restrict__ log
         mbar_wait(&bars[0], w_phase);                                 // weights + parameters landed
         w_phase ^= 1;
         YA_STAMP();                                                   // [3k+1] weights landed
-        if (tid == kProducer) {
+        if (producer) {
             tc_fence_after();
-            const uint32_t a0 = smem_u32(a_tile), b0 = smem_u32(w_src);
+            const uint64_t da = umma_desc(smem_u32(a_tile)), db = umma_desc(smem_u32(w_src));
             const uint32_t idesc = umma_idesc(n_cols);
-            for (int kb = 0; kb < n_kb; ++kb)
+            if (elect_one()) {
+                for (int kb = 0; kb < n_kb; ++kb)
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    umma(tmem + d_col, umma_desc(a0 + kb * (kRows * 128) + k * 32), umma_desc(b0 + kb * (n_cols * 128) + k * 32),
-                         (uint32_t)((kb | k) != 0), idesc);
-            umma_commit(&bars[1]);
+                    for (int k = 0; k < 4; ++k)
+                        umma(tmem + d_col, umma_desc_advance(da, kb * (kRows * 128) + k * 32),
+                             umma_desc_advance(db, kb * (n_cols * 128) + k * 32), (uint32_t)((kb | k) != 0), idesc);
+                umma_commit(&bars[1]);
+            }
+            __syncwarp();
         }
         mbar_wait(&bars[1], m_phase);                                 // accumulator ready; A tile and this weight buffer free
         m_phase ^= 1;
         tc_fence_after();
         YA_STAMP();                                                   // [3k+2] MMA done
     };
-    auto worker_sync = [] { asm volatile("bar.sync 1, %0;" ::"n"(kWorkers) : "memory"); };   // the 16 epilogue warps only
+    // the four warps that share a TMEM lane quarter (same 32 rows, different column parts) exchange row statistics
+    auto worker_sync = [&] { asm volatile("bar.sync %0, 128;" ::"r"(1 + (warp & 3)) : "memory"); };
     auto row_stats = [&](float s, float ss, float& mean, float& rstd) {  // LayerNorm statistics over the 4 threads of a row
         xchg[part * kRows + row] = make_float2(s, ss);
         worker_sync();
@@ -164,7 +165,7 @@ ya_k_forward(const float* __restrict__ features, __nv_bfloat16* __restrict__ log
     };
 
     // ---------------------------------------------------------------- input stage
-    if (tid == kProducer) load_stage(w_tile, off.w_in, 256 * 128, prm_buf(0), off.p_in, 3 * kDim);
+    if (producer && elect_one()) load_stage(w_tile, off.w_in, 256 * 128, prm_buf(0), off.p_in, 3 * kDim);
     if (worker) {   // features (float32 [n][59]) -> bf16, K padded to 64: this thread fills chunks 2*part, 2*part+1 of K-block 0
         uint32_t f[32];
 #pragma unroll
@@ -184,7 +185,7 @@ ya_k_forward(const float* __restrict__ features, __nv_bfloat16* __restrict__ log
         }
     }
     run_mma(w_tile, 1, kDim, 0);
-    if (tid == kProducer) load_stage(w_tile, off.w_trunk, kWBytes, prm_buf(1), off.p_trunk, 3 * kDim);      // first trunk layer streams in
+    if (producer && elect_one()) load_stage(w_tile, off.w_trunk, kWBytes, prm_buf(1), off.p_trunk, 3 * kDim);      // first trunk layer streams in
     if (worker) {   // h = SiLU(LN(z + b)): Linear -> LayerNorm -> SiLU (YachtNNet.py:25-30); also the first skip connection
         const float* prm = prm_all;
         float ps[4] = {0, 0, 0, 0}, pq[4] = {0, 0, 0, 0};
@@ -231,49 +232,64 @@ ya_k_forward(const float* __restrict__ features, __nv_bfloat16* __restrict__ log
         const float* prm = prm_all + (stage & 1) * kPrmFloats;
         const bool second = l & 1;                                    // fc2: add the skip connection
         run_mma(w_tile, 4, kDim, 0);
-        if (tid == kProducer) {                                       // next stage's weights under this epilogue
+        if (producer && elect_one()) {                                // next stage's weights under this epilogue
             if (l + 1 < layers) load_stage(w_tile, off.w_trunk + (int64_t)(l + 1) * kWBytes, kWBytes, prm_buf(stage + 1),
                                            off.p_trunk + (int64_t)(l + 1) * 3 * kDim, 3 * kDim);
             else load_stage(w_tile, off.w_v, 128 * 512, prm_buf(stage + 1), off.p_v, 772);
         }
         if (!worker) continue;
+        // This thread's 64 activations stay in registers across the statistics exchange (no TMEM round trip).
+        // prm = bias / 2 | gamma | beta (the host halves the bias: SiLU(x) = t + t * tanh(t), t = x / 2).
+        uint32_t v0[32], v1[32];
+        tmem_ld32(t_acc64, v0);
+        tmem_ld32(t_acc64 + 32, v1);
+        tmem_ld_wait();
         float ps[4] = {0, 0, 0, 0}, pq[4] = {0, 0, 0, 0};
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-            uint32_t r[32];
-            tmem_ld32(t_acc64 + c * 32, r);
-            tmem_ld_wait();
-            const float* bias = prm + part * 64 + c * 32;
+        {
+            const float* hb = prm + part * 64;
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
-                float v = silu_from_half(fmaf(__uint_as_float(r[i]), 0.5f, 0.5f * bias[i]));
-                ps[i & 3] += v; pq[i & 3] = fmaf(v, v, pq[i & 3]);
-                r[i] = __float_as_uint(v);
+                float x = silu_from_half(fmaf(__uint_as_float(v0[i]), 0.5f, hb[i]));
+                ps[i & 3] += x; pq[i & 3] = fmaf(x, x, pq[i & 3]);
+                v0[i] = __float_as_uint(x);
             }
-            tmem_st32(t_acc64 + c * 32, r);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                float x = silu_from_half(fmaf(__uint_as_float(v1[i]), 0.5f, hb[32 + i]));
+                ps[i & 3] += x; pq[i & 3] = fmaf(x, x, pq[i & 3]);
+                v1[i] = __float_as_uint(x);
+            }
         }
-        tmem_st_wait();
         float mean, rstd;
         row_stats((ps[0] + ps[1]) + (ps[2] + ps[3]), (pq[0] + pq[1]) + (pq[2] + pq[3]), mean, rstd);
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-            uint32_t r[32], sk[32];
-            tmem_ld32(t_acc64 + c * 32, r);
-            if (second) tmem_ld32(t_skip + c * 32, sk);
+        const float nm = -mean * rstd;
+        const float* gamma = prm + kDim + part * 64;
+        const float* beta = prm + 2 * kDim + part * 64;
+        if (second) {                                                 // h += LN(SiLU(fc2(..))); the sum is the next skip
+            uint32_t sk[32];
+            tmem_ld32(t_skip, sk);
             tmem_ld_wait();
-            const float* gamma = prm + kDim + part * 64 + c * 32;
-            const float* beta = prm + 2 * kDim + part * 64 + c * 32;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                const float ga = rstd * gamma[i];
-                float v = fmaf(__uint_as_float(r[i]), ga, fmaf(-mean, ga, beta[i]));
-                if (second) { v += __uint_as_float(sk[i]); }
-                r[i] = __float_as_uint(v);
-            }
-            if (second) tmem_st32(t_skip + c * 32, r);
-            pack_store_a(a_tile, row, part * 8 + c * 4, r);
+            for (int i = 0; i < 32; ++i)
+                v0[i] = __float_as_uint(fmaf(fmaf(__uint_as_float(v0[i]), rstd, nm), gamma[i], beta[i]) + __uint_as_float(sk[i]));
+            tmem_st32(t_skip, v0);
+            pack_store_a(a_tile, row, part * 8, v0);
+            tmem_ld32(t_skip + 32, sk);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+                v1[i] = __float_as_uint(fmaf(fmaf(__uint_as_float(v1[i]), rstd, nm), gamma[32 + i], beta[32 + i]) + __uint_as_float(sk[i]));
+            tmem_st32(t_skip + 32, v1);
+            pack_store_a(a_tile, row, part * 8 + 4, v1);
+            tmem_st_wait();
+        } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v0[i] = __float_as_uint(fmaf(fmaf(__uint_as_float(v0[i]), rstd, nm), gamma[i], beta[i]));
+            pack_store_a(a_tile, row, part * 8, v0);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v1[i] = __float_as_uint(fmaf(fmaf(__uint_as_float(v1[i]), rstd, nm), gamma[32 + i], beta[32 + i]));
+            pack_store_a(a_tile, row, part * 8 + 4, v1);
         }
-        if (second) tmem_st_wait();
     }
 
     // ---------------------------------------------------------------- heads: a = SiLU(LN(h; gamma, beta)) from the skip
@@ -325,7 +341,17 @@ ya_k_forward(const float* __restrict__ features, __nv_bfloat16* __restrict__ log
         mbar_wait(&bars[0], w_phase);                                 // the LayerNorm parameters travel with the weights
         head_prep(prm, prm + kDim, false);
         run_mma(w_tile, 4, 128, 0);                                   // (re-waits the same completed phase, then flips it)
-        if (tid == kProducer) load_stage(w_tile + 65536, off.w_pi, 65536, pi_prm, off.p_pi_ln, kPiPrmFloats);
+        if (producer && elect_one()) {
+            // The policy head reads its activations from tensor memory, so all 192 KB of operand space (A tile +
+            // weight region) become three 64 KB weight slots; tiles 0..2 start streaming now.
+            for (int j = 0; j < 3; ++j) {
+                uint64_t* bar = &bars[3 + policy_slot(j)];
+                mbar_expect_tx(bar, 65536 + (j == 0 ? kPiPrmFloats * 4 : 0));
+                bulk_g2s(base + policy_slot(j) * 65536, wblob + off.w_pi + (int64_t)j * 65536, 32768, bar);
+                bulk_g2s(base + policy_slot(j) * 65536 + 32768, wblob + off.w_pi + (int64_t)j * 65536 + 32768, 32768, bar);
+                if (j == 0) bulk_g2s(pi_prm, pblob + off.p_pi_ln, kPiPrmFloats * 4, bar);
+            }
+        }
         float dot = 0.0f;
         if (worker) {
             uint32_t r[32];
@@ -358,116 +384,126 @@ ya_k_forward(const float* __restrict__ features, __nv_bfloat16* __restrict__ log
     // accumulators between TMEM columns 0 and 128: as soon as tile j's MMAs retire, tile j + 2 starts streaming
     // into the half they read and tile j + 1's MMAs are issued, all under the epilogue of tile j.
     {
-        mbar_wait(&bars[0], w_phase);                                 // tile 0, gamma_pi | beta_pi and every bias landed
-        w_phase ^= 1;
+        mbar_wait(&bars[3 + policy_slot(0)], 0);                      // tile 0, gamma_pi | beta_pi and every bias landed
         head_prep(pi_prm, pi_prm + kDim, true);
         const float* bias_all = pi_prm + 2 * kDim;
-        auto tile_half = [&](int j) { return w_tile + ((j + 1) & 1) * 65536; };     // tile 0 sits in the upper half
-        auto load_tile = [&](int j) {                                 // producer thread, j >= 1
-            uint64_t* bar = &bars[3 + (j & 1)];
-#ifdef YA_FWD_EXP_NOLOAD
-            mbar_expect_tx(bar, 1024);
-            bulk_g2s(tile_half(j), wblob + off.w_pi + (int64_t)j * 65536, 1024, bar);
-#else
+        auto load_tile = [&](int j) {                                 // producer thread, j >= 3
+            uint64_t* bar = &bars[3 + policy_slot(j)];
+            uint8_t* dst = base + policy_slot(j) * 65536;
             mbar_expect_tx(bar, 65536);
-#pragma unroll
-            for (int o = 0; o < 65536; o += kBulkChunk) bulk_g2s(tile_half(j) + o, wblob + off.w_pi + (int64_t)j * 65536 + o, kBulkChunk, bar);
-#endif
+            bulk_g2s(dst, wblob + off.w_pi + (int64_t)j * 65536, 32768, bar);
+            bulk_g2s(dst + 32768, wblob + off.w_pi + (int64_t)j * 65536 + 32768, 32768, bar);
         };
         auto issue_tile = [&](int j) {                                // producer thread: tile j's 16 MMAs
-            const uint32_t b0 = smem_u32(tile_half(j));
+            const uint64_t db = umma_desc(smem_u32(base + policy_slot(j) * 65536));
             const uint32_t idesc = umma_idesc(kPolicyTile);
 #pragma unroll
             for (int kb = 0; kb < 4; ++kb)
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                    umma_ts(tmem + kPolicyTile + (j & 1) * kPolicyTile, tmem + kb * 32 + k * 8,
-                            umma_desc(b0 + kb * (kPolicyTile * 128) + k * 32), (uint32_t)((kb | k) != 0), idesc);
-            umma_commit(&bars[1 + (j & 1)]);
+                    umma_ts(tmem + kPolicyTile + (j % 3) * kPolicyTile, tmem + kb * 32 + k * 8,
+                            umma_desc_advance(db, kb * (kPolicyTile * 128) + k * 32), (uint32_t)((kb | k) != 0), idesc);
+#ifdef YA_FWD_EXP_DOUBLE_MMA
+#pragma unroll
+            for (int kb = 0; kb < 4; ++kb)
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    umma_ts(tmem + kPolicyTile + (j % 3) * kPolicyTile, tmem + kb * 32 + k * 8,
+                            umma_desc_advance(db, kb * (kPolicyTile * 128) + k * 32), 1u, idesc);
+#endif
+            umma_commit(&bars[6 + j % 3]);
         };
         proxy_fence();
         tc_fence_before();
         __syncthreads();                                              // the A tile (p) is complete
         tc_fence_after();
-        const uint32_t m1_base = m_phase;                             // parity of bars[1] for policy tile 0
-        auto mma_parity = [&](int j) { return (j & 1) ? (uint32_t)((j >> 1) & 1) : (m1_base ^ (uint32_t)((j >> 1) & 1)); };
-        float row_mx = -3.0e38f;
-        if (tid == kProducer) {
-            // Producer: keeps the tensor pipe fed.  Tile j needs its weights (landed), and its accumulator half
-            // drained by the epilogue of tile j - 2; tile j + 1's weights go where tile j - 1's were as soon as
-            // tile j - 1's MMAs have retired -- by then tile j's MMAs are already queued behind them.
-            load_tile(1);                                             // lower half: the value head is done with it
+        float row_mx[2] = {-3.0e38f, -3.0e38f};
+        if (producer) {
+            // Producer: keeps the tensor pipe fed.  Weight slots, accumulators (TMEM columns 128 / 256 / 384) and their
+            // barriers all cycle with period 3: tile j needs its weights (requested two tiles ago) and the accumulator
+            // drained by the epilogue of tile j - 3; once tile j is queued, tile j - 1 has retired and tile j + 2
+            // streams into its slot.
             for (int j = 0; j < kPolicyTiles; ++j) {
-                YA_STAMP2();                                          // [5j] loop top
-                if (j >= 1) mbar_wait(&bars[3 + (j & 1)], (uint32_t)(((j - 1) >> 1) & 1));
-                YA_STAMP2();                                          // [5j+1] weights landed
-                if (j >= 2) mbar_wait(&bars[5 + (j & 1)], (uint32_t)(((j - 2) >> 1) & 1));
-                YA_STAMP2();                                          // [5j+2] accumulator drained
+                const uint32_t par = (uint32_t)((j / 3) & 1);
+#ifndef YA_FWD_EXP_NOLOAD
+                mbar_wait(&bars[3 + policy_slot(j)], par);
+#else
+                if (j < 3) mbar_wait(&bars[3 + policy_slot(j)], par);
+#endif
+#ifndef YA_FWD_EXP_NODRAINWAIT
+                if (j >= 3) mbar_wait(&bars[9 + j % 3], par ^ 1u);
+#endif
                 tc_fence_after();
-                issue_tile(j);
-                YA_STAMP2();                                          // [5j+3] MMAs issued
-                if (j >= 1 && j + 1 < kPolicyTiles) {
-                    mbar_wait(&bars[1 + ((j - 1) & 1)], mma_parity(j - 1));
-                    load_tile(j + 1);
+                if (elect_one()) issue_tile(j);
+                __syncwarp();
+#ifndef YA_FWD_EXP_NOLOAD
+                if (j >= 1 && j + 2 < kPolicyTiles) {
+                    mbar_wait(&bars[6 + (j - 1) % 3], (uint32_t)(((j - 1) / 3) & 1));
+                    if (elect_one()) load_tile(j + 2);
+                    __syncwarp();
                 }
-                YA_STAMP2();                                          // [5j+4] previous tile retired, next load issued
+#endif
             }
-        } else if (worker) {
+        } else {
+            // 15 epilogue warps: the issuer warp's share (rows 96..127, column part 3) goes to warp 11 on top of its own
+            const int n_my = (warp == kIssuerWarp - 4) ? 2 : 1;
             for (int j = 0; j < kPolicyTiles; ++j) {
-                mbar_wait(&bars[1 + (j & 1)], mma_parity(j));
+                mbar_wait(&bars[6 + j % 3], (uint32_t)((j / 3) & 1));
                 tc_fence_after();
                 YA_STAMP();                                           // policy tile j: accumulator ready
-                uint32_t r[32];
-#ifdef YA_FWD_EXP_NOTMEMLD
-#pragma unroll
-                for (int i = 0; i < 32; ++i) r[i] = (uint32_t)(j + i);
-#else
-                tmem_ld32(t_lane + kPolicyTile + (j & 1) * kPolicyTile + part * 32, r);
-                tmem_ld_wait();
-#endif
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&bars[5 + (j & 1)]);       // this warp's share of the accumulator is in registers
-                const int col0 = j * kPolicyTile + part * 32;
-                if (col0 < kPolicyCols) {
-                    const float* bias = bias_all + col0;
-                    float f[32];
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(r[i]) + bias[i];
-                    if (col0 + 32 <= kActions) {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) row_mx = fmaxf(row_mx, f[i]);
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) if (col0 + i < kActions) row_mx = fmaxf(row_mx, f[i]);
+                for (int q = 0; q < n_my; ++q) {
+                    const int pp = part + q;
+                    uint32_t r[32];
+                    tmem_ld32(t_lane + kPolicyTile + (j % 3) * kPolicyTile + pp * 32, r);
+                    tmem_ld_wait();
+                    if (q == n_my - 1) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&bars[9 + j % 3]); // this warp's share of the accumulator is in registers
                     }
-                    if (grow < n) {
-                        uint32_t p[16];
+                    const int col0 = j * kPolicyTile + pp * 32;
+                    if (col0 < kPolicyCols) {
+                        const float* bias = bias_all + col0;
+                        float f[32];
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
-                            p[i] = *reinterpret_cast<uint32_t*>(&h);
+                        for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(r[i]) + bias[i];
+                        float m = row_mx[q];
+                        if (col0 + 32 <= kActions) {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) m = fmaxf(m, f[i]);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) if (col0 + i < kActions) m = fmaxf(m, f[i]);
                         }
-                        __nv_bfloat16* dst = logits + grow * kPolicyCols + col0;    // 64 bytes, 32-byte aligned
+                        row_mx[q] = m;
+                        if (grow < n) {
+                            uint32_t p[16];
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) {
+                                __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+                                p[i] = *reinterpret_cast<uint32_t*>(&h);
+                            }
+                            __nv_bfloat16* dst = logits + grow * kPolicyCols + col0;    // 64 bytes, 32-byte aligned
 #ifndef YA_FWD_EXP_NOSTORE
 #pragma unroll
-                        for (int q = 0; q < 2; ++q)                   // 256-bit stores: half the LSU work of 4 x 16 bytes
-                            asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + 16 * q),
-                                         "r"(p[8 * q]), "r"(p[8 * q + 1]), "r"(p[8 * q + 2]), "r"(p[8 * q + 3]), "r"(p[8 * q + 4]),
-                                         "r"(p[8 * q + 5]), "r"(p[8 * q + 6]), "r"(p[8 * q + 7]) : "memory");
+                            for (int h2 = 0; h2 < 2; ++h2)            // 256-bit stores: half the LSU work of 4 x 16 bytes
+                                asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + 16 * h2),
+                                             "r"(p[8 * h2]), "r"(p[8 * h2 + 1]), "r"(p[8 * h2 + 2]), "r"(p[8 * h2 + 3]),
+                                             "r"(p[8 * h2 + 4]), "r"(p[8 * h2 + 5]), "r"(p[8 * h2 + 6]), "r"(p[8 * h2 + 7]) : "memory");
 #else
-                        if (p[0] == 0x12345678u && p[5] == 0x9abcdef0u) *reinterpret_cast<uint4*>(dst) = make_uint4(p[1] ^ p[9], p[2] ^ p[10], p[3] ^ p[11], p[4] ^ p[15]);
+                            if (p[0] == 0x12345678u && p[5] == 0x9abcdef0u) *reinterpret_cast<uint4*>(dst) = make_uint4(p[1] ^ p[9], p[2] ^ p[10], p[3] ^ p[11], p[4] ^ p[15]);
 #endif
+                        }
                     }
                 }
             }
+            for (int q = 0; q < n_my; ++q) xchg[(part + q) * kRows + row].x = row_mx[q];
         }
         YA_STAMP();
         // the row's largest logit as the expand kernel will see it (bf16 rounding is monotone)
-        if (worker) xchg[part * kRows + row].x = row_mx;
         __syncthreads();
-        if (worker && part == 0 && grow < n && row_max) {
-            float m = fmaxf(fmaxf(row_mx, xchg[1 * kRows + row].x), fmaxf(xchg[2 * kRows + row].x, xchg[3 * kRows + row].x));
+        if (part == 0 && grow < n && row_max) {
+            float m = fmaxf(fmaxf(row_mx[0], xchg[1 * kRows + row].x), fmaxf(xchg[2 * kRows + row].x, xchg[3 * kRows + row].x));
             row_max[grow] = __bfloat162float(__float2bfloat16_rn(m));
         }
     }

@@ -34,6 +34,15 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// One lane of a fully converged warp.  Code guarded by this predicate is known to run in exactly one thread, so
+// the single-thread tcgen05 / bulk-copy instructions inside are emitted straight-line (a plain `tid == x` test
+// makes the compiler wrap every one of them in a loop over the possibly-many active lanes).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xFFFFFFFF;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 // shared-memory matrix descriptor: K-major, 128-byte swizzle, rows 128 B apart, 8-row groups 1024 B apart
 __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
     uint64_t d = 0;
@@ -44,6 +53,9 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
     d |= (uint64_t)2 << 61;                               // SWIZZLE_128B
     return d;
 }
+
+// descriptor of the same tile `bytes` further on (same swizzle atom row: K steps of 32 bytes, K-blocks, halves)
+__device__ __forceinline__ uint64_t umma_desc_advance(uint64_t desc, uint32_t bytes) { return desc + (uint64_t)(bytes >> 4); }
 
 // instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=n_cols
 __host__ __device__ constexpr uint32_t umma_idesc(int n_cols) {

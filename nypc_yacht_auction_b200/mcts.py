@@ -183,7 +183,9 @@ class FusedYachtEvaluator:
             b_pi[:a].copy_(sd["pi_head.2.bias"])
             wparts = [self.swizzled_image(w_in), self.trunk_w, self.swizzled_image(sd["v_head.2.weight"].to(dev))] + \
                      [self.swizzled_image(w_pi[128 * j:128 * (j + 1)]) for j in range(26)]
-            pparts = [f32(sd["inp.0.bias"]), f32(sd["inp.1.weight"]), f32(sd["inp.1.bias"]), self.trunk_p.reshape(-1),
+            trunk_p = self.trunk_p.clone()                              # [layer][bias | gamma | beta][256]
+            trunk_p[:, 0] *= 0.5                                        # the kernel's SiLU works on (z + b) / 2
+            pparts = [f32(sd["inp.0.bias"]), f32(sd["inp.1.weight"]), f32(sd["inp.1.bias"]), trunk_p.reshape(-1),
                       f32(sd["v_head.0.weight"]), f32(sd["v_head.0.bias"]), f32(sd["v_head.2.bias"]), f32(sd["v_head.4.weight"]),
                       torch.cat([f32(sd["v_head.4.bias"]), torch.zeros(3, device=dev)]),
                       f32(sd["pi_head.0.weight"]), f32(sd["pi_head.0.bias"]), b_pi]
