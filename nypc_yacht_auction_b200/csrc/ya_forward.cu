@@ -107,9 +107,11 @@ ya_k_forward(const float* __restrict__ features, __nv_bfloat16* __restrict__ log
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
     const uint32_t t_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-    const uint32_t t_acc64 = t_lane + (uint32_t)(part * 64);          // my 64 columns of an N = 256 accumulator
-    const uint32_t t_skip = t_lane + 256 + (uint32_t)(part * 64);     // my 64 columns of the float32 skip connection
-    uint32_t w_phase = 0, m_phase = 0;
+    // This thread's 64 of a row's 256 columns: 32 from each half, so that the epilogue can start on the first
+    // N = 128 half of a trunk layer while the tensor core is still on the second.
+    const int colv[2] = {part * 32, 128 + part * 32};
+    const uint32_t t_skip = t_lane + 256;                             // float32 skip connection: TMEM columns 256..511
+    uint32_t w_phase = 0, m_phase = 0, m2_phase = 0;
     int tl_n = 0; (void)tl_n;
     int stage = 0;                                                    // parameter double buffer index = stage & 1
 
@@ -192,16 +194,16 @@ ya_k_forward(const float* __restrict__ features, __nv_bfloat16* __restrict__ log
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
             uint32_t r[32];
-            tmem_ld32(t_acc64 + c * 32, r);
+            tmem_ld32(t_lane + colv[c], r);
             tmem_ld_wait();
-            const float* bias = prm + part * 64 + c * 32;
+            const float* bias = prm + colv[c];
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
                 float v = __uint_as_float(r[i]) + bias[i];
                 ps[i & 3] += v; pq[i & 3] = fmaf(v, v, pq[i & 3]);
                 r[i] = __float_as_uint(v);
             }
-            tmem_st32(t_acc64 + c * 32, r);
+            tmem_st32(t_lane + colv[c], r);
         }
         tmem_st_wait();
         float mean, rstd;
@@ -209,18 +211,18 @@ ya_k_forward(const float* __restrict__ features, __nv_bfloat16* __restrict__ log
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
             uint32_t r[32];
-            tmem_ld32(t_acc64 + c * 32, r);
+            tmem_ld32(t_lane + colv[c], r);
             tmem_ld_wait();
-            const float* gamma = prm + kDim + part * 64 + c * 32;
-            const float* beta = prm + 2 * kDim + part * 64 + c * 32;
+            const float* gamma = prm + kDim + colv[c];
+            const float* beta = prm + 2 * kDim + colv[c];
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
                 const float ga = rstd * gamma[i];
                 float y = fmaf(__uint_as_float(r[i]), ga, fmaf(-mean, ga, beta[i]));
                 r[i] = __float_as_uint(silu_from_half(0.5f * y));
             }
-            tmem_st32(t_skip + c * 32, r);
-            pack_store_a(a_tile, row, part * 8 + c * 4, r);
+            tmem_st32(t_skip + colv[c], r);
+            pack_store_a(a_tile, row, colv[c] / 8, r);
         }
         tmem_st_wait();
     }
@@ -231,64 +233,95 @@ ya_k_forward(const float* __restrict__ features, __nv_bfloat16* __restrict__ log
     for (int l = 0; l < layers; ++l, ++stage) {
         const float* prm = prm_all + (stage & 1) * kPrmFloats;
         const bool second = l & 1;                                    // fc2: add the skip connection
-        run_mma(w_tile, 4, kDim, 0);
-        if (producer && elect_one()) {                                // next stage's weights under this epilogue
+        // Two N = 128 halves, each with its own completion barrier: the epilogue's first pass over columns
+        // 0..127 runs while the tensor core works on columns 128..255.
+        proxy_fence();
+        tc_fence_before();
+        __syncthreads();
+        YA_STAMP();
+        mbar_wait(&bars[0], w_phase);
+        w_phase ^= 1;
+        YA_STAMP();
+        if (producer) {
+            tc_fence_after();
+            const uint64_t da = umma_desc(smem_u32(a_tile)), db = umma_desc(smem_u32(w_tile));
+            const uint32_t idesc = umma_idesc(128);
+            if (elect_one()) {
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+#pragma unroll
+                    for (int kb = 0; kb < 4; ++kb)
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            umma(tmem + half * 128, umma_desc_advance(da, kb * (kRows * 128) + k * 32),
+                                 umma_desc_advance(db, kb * (kDim * 128) + half * (128 * 128) + k * 32), (uint32_t)((kb | k) != 0), idesc);
+                    umma_commit(&bars[1 + half]);
+                }
+            }
+            __syncwarp();
+        }
+        // prm = bias / 2 | gamma | beta (the host halves the bias: SiLU(x) = t + t * tanh(t), t = x / 2).  The 64
+        // activations stay in registers across the statistics exchange (no TMEM round trip).
+        uint32_t v0[32], v1[32];
+        float ps[4] = {0, 0, 0, 0}, pq[4] = {0, 0, 0, 0};
+        mbar_wait(&bars[1], m_phase);
+        m_phase ^= 1;
+        tc_fence_after();
+        tmem_ld32(t_lane + colv[0], v0);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            float x = silu_from_half(fmaf(__uint_as_float(v0[i]), 0.5f, prm[colv[0] + i]));
+            ps[i & 3] += x; pq[i & 3] = fmaf(x, x, pq[i & 3]);
+            v0[i] = __float_as_uint(x);
+        }
+        mbar_wait(&bars[2], m2_phase);
+        m2_phase ^= 1;
+        tc_fence_after();
+        YA_STAMP();
+        if (producer && elect_one()) {                                // next stage's weights under the rest of this epilogue
             if (l + 1 < layers) load_stage(w_tile, off.w_trunk + (int64_t)(l + 1) * kWBytes, kWBytes, prm_buf(stage + 1),
                                            off.p_trunk + (int64_t)(l + 1) * 3 * kDim, 3 * kDim);
             else load_stage(w_tile, off.w_v, 128 * 512, prm_buf(stage + 1), off.p_v, 772);
         }
-        if (!worker) continue;
-        // This thread's 64 activations stay in registers across the statistics exchange (no TMEM round trip).
-        // prm = bias / 2 | gamma | beta (the host halves the bias: SiLU(x) = t + t * tanh(t), t = x / 2).
-        uint32_t v0[32], v1[32];
-        tmem_ld32(t_acc64, v0);
-        tmem_ld32(t_acc64 + 32, v1);
+        __syncwarp();
+        tmem_ld32(t_lane + colv[1], v1);
         tmem_ld_wait();
-        float ps[4] = {0, 0, 0, 0}, pq[4] = {0, 0, 0, 0};
-        {
-            const float* hb = prm + part * 64;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                float x = silu_from_half(fmaf(__uint_as_float(v0[i]), 0.5f, hb[i]));
-                ps[i & 3] += x; pq[i & 3] = fmaf(x, x, pq[i & 3]);
-                v0[i] = __float_as_uint(x);
-            }
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                float x = silu_from_half(fmaf(__uint_as_float(v1[i]), 0.5f, hb[32 + i]));
-                ps[i & 3] += x; pq[i & 3] = fmaf(x, x, pq[i & 3]);
-                v1[i] = __float_as_uint(x);
-            }
+        for (int i = 0; i < 32; ++i) {
+            float x = silu_from_half(fmaf(__uint_as_float(v1[i]), 0.5f, prm[colv[1] + i]));
+            ps[i & 3] += x; pq[i & 3] = fmaf(x, x, pq[i & 3]);
+            v1[i] = __float_as_uint(x);
         }
         float mean, rstd;
         row_stats((ps[0] + ps[1]) + (ps[2] + ps[3]), (pq[0] + pq[1]) + (pq[2] + pq[3]), mean, rstd);
         const float nm = -mean * rstd;
-        const float* gamma = prm + kDim + part * 64;
-        const float* beta = prm + 2 * kDim + part * 64;
+        const float* gamma = prm + kDim;
+        const float* beta = prm + 2 * kDim;
         if (second) {                                                 // h += LN(SiLU(fc2(..))); the sum is the next skip
             uint32_t sk[32];
-            tmem_ld32(t_skip, sk);
+            tmem_ld32(t_skip + colv[0], sk);
             tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < 32; ++i)
-                v0[i] = __float_as_uint(fmaf(fmaf(__uint_as_float(v0[i]), rstd, nm), gamma[i], beta[i]) + __uint_as_float(sk[i]));
-            tmem_st32(t_skip, v0);
-            pack_store_a(a_tile, row, part * 8, v0);
-            tmem_ld32(t_skip + 32, sk);
+                v0[i] = __float_as_uint(fmaf(fmaf(__uint_as_float(v0[i]), rstd, nm), gamma[colv[0] + i], beta[colv[0] + i]) + __uint_as_float(sk[i]));
+            tmem_st32(t_skip + colv[0], v0);
+            pack_store_a(a_tile, row, colv[0] / 8, v0);
+            tmem_ld32(t_skip + colv[1], sk);
             tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < 32; ++i)
-                v1[i] = __float_as_uint(fmaf(fmaf(__uint_as_float(v1[i]), rstd, nm), gamma[32 + i], beta[32 + i]) + __uint_as_float(sk[i]));
-            tmem_st32(t_skip + 32, v1);
-            pack_store_a(a_tile, row, part * 8 + 4, v1);
+                v1[i] = __float_as_uint(fmaf(fmaf(__uint_as_float(v1[i]), rstd, nm), gamma[colv[1] + i], beta[colv[1] + i]) + __uint_as_float(sk[i]));
+            tmem_st32(t_skip + colv[1], v1);
+            pack_store_a(a_tile, row, colv[1] / 8, v1);
             tmem_st_wait();
         } else {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v0[i] = __float_as_uint(fmaf(fmaf(__uint_as_float(v0[i]), rstd, nm), gamma[i], beta[i]));
-            pack_store_a(a_tile, row, part * 8, v0);
+            for (int i = 0; i < 32; ++i) v0[i] = __float_as_uint(fmaf(fmaf(__uint_as_float(v0[i]), rstd, nm), gamma[colv[0] + i], beta[colv[0] + i]));
+            pack_store_a(a_tile, row, colv[0] / 8, v0);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v1[i] = __float_as_uint(fmaf(fmaf(__uint_as_float(v1[i]), rstd, nm), gamma[32 + i], beta[32 + i]));
-            pack_store_a(a_tile, row, part * 8 + 4, v1);
+            for (int i = 0; i < 32; ++i) v1[i] = __float_as_uint(fmaf(fmaf(__uint_as_float(v1[i]), rstd, nm), gamma[colv[1] + i], beta[colv[1] + i]));
+            pack_store_a(a_tile, row, colv[1] / 8, v1);
         }
     }
 
@@ -300,7 +333,7 @@ ya_k_forward(const float* __restrict__ features, __nv_bfloat16* __restrict__ log
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
             uint32_t r[32];
-            tmem_ld32(t_skip + c * 32, r);
+            tmem_ld32(t_skip + colv[c], r);
             tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < 32; ++i) { float v = __uint_as_float(r[i]); ps[i & 3] += v; pq[i & 3] = fmaf(v, v, pq[i & 3]); }
@@ -310,10 +343,10 @@ ya_k_forward(const float* __restrict__ features, __nv_bfloat16* __restrict__ log
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
             uint32_t r[32];
-            tmem_ld32(t_skip + c * 32, r);
+            tmem_ld32(t_skip + colv[c], r);
             tmem_ld_wait();
-            const float* gamma = gamma_all + part * 64 + c * 32;
-            const float* beta = beta_all + part * 64 + c * 32;
+            const float* gamma = gamma_all + colv[c];
+            const float* beta = beta_all + colv[c];
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
                 const float ga = rstd * gamma[i];
@@ -327,9 +360,9 @@ ya_k_forward(const float* __restrict__ features, __nv_bfloat16* __restrict__ log
                     __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
                     pk[i] = *reinterpret_cast<uint32_t*>(&h);
                 }
-                tmem_st16(t_lane + (uint32_t)(part * 32 + c * 16), pk);
+                tmem_st16(t_lane + (uint32_t)(colv[c] / 2), pk);       // K elements colv[c].. = packed columns colv[c] / 2..
             } else {
-                pack_store_a(a_tile, row, part * 8 + c * 4, r);
+                pack_store_a(a_tile, row, colv[c] / 8, r);
             }
         }
         if (to_tmem) tmem_st_wait();
