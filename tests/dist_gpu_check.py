@@ -43,8 +43,8 @@ def main():
         rex = ref.execute_episodes()
         for k in ("features", "actions", "counts", "value", "result_p1"):
             assert torch.equal(full[k], rex[k]), "sharded run differs from the single-process run in %s" % k
-    # B. network evaluator: same plumbing; library GEMMs may pick different kernels for different batch sizes, so
-    # only structural properties are compared across shardings
+    # B. network evaluator: the whole forward is one hand-written kernel whose rows do not depend on the batch they
+    # sit in (csrc/ya_forward.cu), so the sharded AlphaZero self-play is bitwise the single-process one too
     sp = BatchedSelfPlay(last - first, sims, evaluator=FusedYachtEvaluator(net, last - first), seed=seed, game_base=first,
                          device=dev)
     full_nn = allgather_examples(sp.execute_episodes())
@@ -52,8 +52,12 @@ def main():
     visits = full_nn["counts"].sum(-1)
     assert int(visits[0].min()) == sims - 1 and int(visits[0].max()) == sims - 1      # fresh roots: numMCTSSims - 1 visits
     if rank == 0:
-        print("dist ok: %d games over %d GPUs == 1 process (uniform evaluator, bitwise); NCCL all-gather %s, weight "
-              "broadcast verified" % (total, world, tuple(full["counts"].shape)))
+        ref = BatchedSelfPlay(total, sims, evaluator=FusedYachtEvaluator(net, total), seed=seed, game_base=0, device=dev)
+        rex = ref.execute_episodes()
+        for k in ("features", "actions", "counts", "value", "result_p1"):
+            assert torch.equal(full_nn[k], rex[k]), "sharded network run differs from the single-process run in %s" % k
+        print("dist ok: %d games over %d GPUs == 1 process, bitwise, for the uniform AND the network evaluator; NCCL "
+              "all-gather %s, weight broadcast verified" % (total, world, tuple(full["counts"].shape)))
     dist.barrier()
     dist.destroy_process_group()
 
