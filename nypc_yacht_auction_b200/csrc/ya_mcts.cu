@@ -22,8 +22,7 @@ namespace {
 constexpr int kNodeWords = 16;        // 64-byte node record
 constexpr int kCursorWords = 32;      // 128-byte per-game search cursor
 constexpr int kMaxDepth = 16;
-constexpr int kChunkEdges = 32;
-constexpr int kChunkWords = 114;      // [0] next, [1] pad, [2..17] idx u16 x32, [18..49] nsa u32 x32, [50..113] q f64 x32
+constexpr int kMinEdgeCap = 32;
 constexpr int kWarpsPerBlock = 4;
 #ifndef YA_MCTS_MIN_BLOCKS
 #define YA_MCTS_MIN_BLOCKS 8          // <= 64 registers: 32 resident warps per SM for the latency-bound tree walks
@@ -68,6 +67,25 @@ __device__ __forceinline__ View make_view(const ya_mcts_tree& t, int64_t g) {
 // up to 3,024 unvisited children is: best group from <= 95 words, then the 32 priors of that one group.
 __device__ __forceinline__ int row_words(int L) { return ((L + 3) & ~3) + ((L + 31) >> 5); }
 __device__ __forceinline__ int group_max_at(int L) { return (L + 3) & ~3; }
+
+// A node's visited edges: ONE contiguous array in the arena, capacity C = 32, 64, 128, ... (it doubles when full; the
+// old copy is abandoned in the bump arena): C x u16 legal index | C x u32 Nsa (bit 31: Q is a Python float, else a
+// numpy float32) | C x f64 Q.  Every lane can address any edge directly, so a node with 100 edges costs one
+// round of independent loads, not a walk over a chunk list.
+__device__ __forceinline__ int edge_cap(int n) { return n <= kMinEdgeCap ? kMinEdgeCap : 1 << (32 - __clz(n - 1)); }
+__device__ __forceinline__ int edge_words(int cap) { return cap / 2 + cap + 2 * cap; }
+struct Edges {
+    uint16_t* idx;
+    uint32_t* nsa;
+    double* q;
+};
+__device__ __forceinline__ Edges edges_at(uint32_t* base, int cap) {
+    Edges e;
+    e.idx = reinterpret_cast<uint16_t*>(base);
+    e.nsa = base + cap / 2;
+    e.q = reinterpret_cast<double*>(base + cap / 2 + cap);
+    return e;
+}
 
 // writes priors [k0, k0 + 32) of a fresh row (one per lane; lanes with k >= L idle) and the group's maximum
 __device__ __forceinline__ void store_prior_group(float* __restrict__ row, int L, int k0, float p, int lane) {
@@ -121,24 +139,35 @@ __device__ __forceinline__ int ucb_select(const View& v, const uint32_t* node, i
     const float sq_old = (float)sqrt((double)visits);
     float best = -CUDART_INF_F;
     int besti = 0x7FFFFFFF;
-    // visited edges: u = Q + cpuct * P * sqrt(Ns) / (1 + Nsa)
-    uint32_t off = node[N_EDGES];
-    int remaining = (int)node[N_NEDGE];
-    while (remaining > 0) {
-        int cnt = min(remaining, kChunkEdges);
-        const uint32_t* ch = v.arena + off;
-        if (lane < cnt) {
-            int ai = reinterpret_cast<const uint16_t*>(ch + 2)[lane];
-            uint32_t nsa = ch[18 + lane] & 0x7FFFFFFFu;
-            double q = reinterpret_cast<const double*>(ch + 50)[lane];
-            float p = __uint_as_float(row[ai] & 0x7FFFFFFFu);
-            float t = __fmul_rn(__fmul_rn(cpuct, p), sq_old);
-            t = __fdiv_rn(t, (float)(1u + nsa));
-            float u = __fadd_rn((float)q, t);
-            if (u > best || (u == best && ai < besti)) { best = u; besti = ai; }
+    // visited edges: u = Q + cpuct * P * sqrt(Ns) / (1 + Nsa); two edges per lane in flight
+    const int n_edges = (int)node[N_NEDGE];
+    if (n_edges > 0) {
+        const Edges ed = edges_at(v.arena + node[N_EDGES], edge_cap(n_edges));
+        for (int e0 = 0; e0 < n_edges; e0 += 64) {
+            int ai[2];
+            uint32_t nsa[2], pb[2];
+            double q[2];
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+                const int e = e0 + 32 * t + lane;
+                const bool ok = e < n_edges;
+                ai[t] = ok ? (int)ed.idx[e] : 0;
+                nsa[t] = ok ? ed.nsa[e] & 0x7FFFFFFFu : 0u;
+                q[t] = ok ? ed.q[e] : 0.0;
+            }
+#pragma unroll
+            for (int t = 0; t < 2; ++t) pb[t] = row[ai[t]];
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+                if (e0 + 32 * t + lane < n_edges) {
+                    float p = __uint_as_float(pb[t] & 0x7FFFFFFFu);
+                    float x = __fmul_rn(__fmul_rn(cpuct, p), sq_old);
+                    x = __fdiv_rn(x, (float)(1u + nsa[t]));
+                    float u = __fadd_rn((float)q[t], x);
+                    if (u > best || (u == best && ai[t] < besti)) { best = u; besti = ai[t]; }
+                }
+            }
         }
-        off = ch[0];
-        remaining -= cnt;
     }
     // unvisited edges: u = cpuct * P * sqrt(Ns + EPS), float32.  u is monotone (non-strictly) in P, so the
     // lowest-index maximiser lives in the lowest group whose largest unvisited prior reaches the maximal u.
@@ -185,29 +214,45 @@ __device__ __forceinline__ int ucb_select(const View& v, const uint32_t* node, i
 __device__ __forceinline__ bool backup_edge(const View& v, uint32_t* node, int ai, const Val& val, uint32_t& arena_top, int lane) {
     int failed = 0, fresh = 0;
     // locate the edge
-    uint32_t off = node[N_EDGES];
-    int n_edges = (int)node[N_NEDGE];
-    int remaining = n_edges;
-    uint32_t last = 0, found_off = 0;
-    int found_slot = -1;
-    while (remaining > 0) {
-        int cnt = min(remaining, kChunkEdges);
-        const uint32_t* ch = v.arena + off;
-        bool hit = lane < cnt && reinterpret_cast<const uint16_t*>(ch + 2)[lane] == ai;
-        uint32_t m = __ballot_sync(0xFFFFFFFFu, hit);
-        if (m) { found_off = off; found_slot = __ffs(m) - 1; break; }
-        last = off;
-        off = ch[0];
-        remaining -= cnt;
+    const int n_edges = (int)node[N_NEDGE];
+    const int cap = edge_cap(n_edges);
+    uint32_t* base = v.arena + node[N_EDGES];
+    int found = -1;
+    if (n_edges > 0) {
+        const Edges ed = edges_at(base, cap);
+        for (int e0 = 0; e0 < n_edges && found < 0; e0 += 64) {
+            const int ea = e0 + lane, eb = e0 + 32 + lane;
+            const int ia = ea < n_edges ? (int)ed.idx[ea] : -1, ib = eb < n_edges ? (int)ed.idx[eb] : -1;
+            const uint32_t ma = __ballot_sync(0xFFFFFFFFu, ia == ai), mb = __ballot_sync(0xFFFFFFFFu, ib == ai);
+            if (ma) found = e0 + __ffs(ma) - 1;
+            else if (mb) found = e0 + 32 + __ffs(mb) - 1;
+        }
+    }
+    // a first visit appends; a full array moves to one of twice the capacity first (all lanes copy)
+    if (found < 0 && (n_edges == 0 || n_edges == cap)) {
+        const int new_cap = n_edges == 0 ? kMinEdgeCap : 2 * cap;
+        const uint32_t top = (arena_top + 1u) & ~1u;                 // 8-byte aligned: the Q values are doubles
+        if (top + (uint32_t)edge_words(new_cap) > v.arena_words) {
+            failed = 1;
+        } else {
+            uint32_t* nb = v.arena + top;
+            if (n_edges > 0) {
+                const Edges from = edges_at(base, cap), to = edges_at(nb, new_cap);
+                for (int e = lane; e < n_edges; e += 32) { to.idx[e] = from.idx[e]; to.nsa[e] = from.nsa[e]; to.q[e] = from.q[e]; }
+            }
+            __syncwarp();
+            if (lane == 0) node[N_EDGES] = top;
+            arena_top = top + (uint32_t)edge_words(new_cap);
+            base = nb;
+        }
     }
     if (lane == 0) {
-        if (found_slot >= 0) {
-            uint32_t* ch = v.arena + found_off;
-            uint32_t raw = ch[18 + found_slot];
+        if (found >= 0) {
+            const Edges ed = edges_at(base, cap);
+            uint32_t raw = ed.nsa[found];
             uint32_t nsa = raw & 0x7FFFFFFFu;
             bool q_f32 = (raw >> 31) == 0;
-            double* qp = reinterpret_cast<double*>(ch + 50) + found_slot;
-            double q = *qp;
+            double q = ed.q[found];
             if (!q_f32 && !val.is_f32) {
                 // Python floats all the way: (Nsa * Q + v) / (Nsa + 1) in double
                 q = __ddiv_rn(__dadd_rn(__dmul_rn((double)nsa, q), val.d), (double)(nsa + 1u));
@@ -218,40 +263,19 @@ __device__ __forceinline__ bool backup_edge(const View& v, uint32_t* node, int a
                 q = (double)__fdiv_rn(sum, (float)(nsa + 1u));
                 q_f32 = true;
             }
-            *qp = q;
-            ch[18 + found_slot] = (nsa + 1u) | (q_f32 ? 0u : 0x80000000u);
-        } else {
-            int slot = n_edges % kChunkEdges;
-            uint32_t choff;
-            bool ok = true;
-            if (slot == 0) {                                         // need a new chunk
-                uint32_t top = (arena_top + 1u) & ~1u;
-                if (top + kChunkWords > v.arena_words) ok = false;
-                else {
-                    choff = top;
-                    arena_top = top + kChunkWords;
-                    v.arena[choff] = 0;
-                    if (n_edges == 0) node[N_EDGES] = choff; else v.arena[last] = choff;
-                }
-            } else {
-                choff = last;                                        // the tail chunk still has room
-            }
-            if (ok) {
-                uint32_t* ch = v.arena + choff;
-                reinterpret_cast<uint16_t*>(ch + 2)[slot] = (uint16_t)ai;
-                ch[18 + slot] = 1u | (val.is_f32 ? 0u : 0x80000000u);       // Qsa = v, Nsa = 1
-                reinterpret_cast<double*>(ch + 50)[slot] = val.d;
-                node[N_NEDGE] = (uint32_t)(n_edges + 1);
-                v.arena[node[N_PRIOR] + ai] |= 0x80000000u;                 // mark the prior entry as visited
-                fresh = 1;
-            } else {
-                failed = 1;
-            }
+            ed.q[found] = q;
+            ed.nsa[found] = (nsa + 1u) | (q_f32 ? 0u : 0x80000000u);
+        } else if (!failed) {
+            const Edges ed = edges_at(base, edge_cap(n_edges + 1));
+            ed.idx[n_edges] = (uint16_t)ai;
+            ed.nsa[n_edges] = 1u | (val.is_f32 ? 0u : 0x80000000u);        // Qsa = v, Nsa = 1
+            ed.q[n_edges] = val.d;
+            node[N_NEDGE] = (uint32_t)(n_edges + 1);
+            v.arena[node[N_PRIOR] + ai] |= 0x80000000u;                     // mark the prior entry as visited
+            fresh = 1;
         }
         node[N_VISITS] += 1;                                         // Ns[s] += 1
     }
-    arena_top = __shfl_sync(0xFFFFFFFFu, arena_top, 0);
-    failed = __shfl_sync(0xFFFFFFFFu, failed, 0);
     fresh = __shfl_sync(0xFFFFFFFFu, fresh, 0);
     __syncwarp();
     if (fresh) {                                                     // the child's group lost an unvisited prior
@@ -636,18 +660,54 @@ ya_k_mcts_expand_logits(ya_mcts_tree tree, const __nv_bfloat16* __restrict__ log
         }
         asm volatile("cp.async.wait_all;" ::: "memory");
         __syncwarp();
+        // exp(l - max) = 2^(l * log2(e) - max * log2(e)): one FMA + one EX2 per logit; the normalisation is folded into
+        // the exponent as well (P = 2^(.. - log2(total))).  Two logits per lane and iteration (one 32-bit word).
+        constexpr float kLog2e = 1.4426950408889634f;
+        const float off_sum = -mx * kLog2e;
+        auto ex2 = [](float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; };
         const uint16_t* rc = reinterpret_cast<const uint16_t*>(raw);
-        auto ex = [rc, mx](int k) { return __expf(__uint_as_float((uint32_t)rc[k] << 16) - mx); };
+        const bool pairs = !(L & 1);
+        const int nw = L >> 1;
         float total = 0.0f;
-        for (int k = lane; k < L; k += 32) total += ex(k);
+        if (pairs) {
+            float t1 = 0.0f;
+            for (int j = lane; j < nw; j += 32) {
+                const uint32_t w = raw[j];
+                total += ex2(fmaf(__uint_as_float(w << 16), kLog2e, off_sum));
+                t1 += ex2(fmaf(__uint_as_float(w & 0xFFFF0000u), kLog2e, off_sum));
+            }
+            total += t1;
+        } else {
+            for (int k = lane; k < L; k += 32) total += ex2(fmaf(__uint_as_float((uint32_t)rc[k] << 16), kLog2e, off_sum));
+        }
 #pragma unroll
         for (int o = 16; o; o >>= 1) total += __shfl_xor_sync(0xFFFFFFFFu, total, o);
         float* row = reinterpret_cast<float*>(v.arena + node[N_PRIOR]);
         if (total > 0.0f) {
-            const float scale = __fdiv_rn(1.0f, total);
-            for (int k0 = 0; k0 < L; k0 += 32) {
-                const int k = k0 + lane;
-                store_prior_group(row, L, k0, k < L ? __fmul_rn(ex(k), scale) : 0.0f, lane);
+            const float off_p = off_sum - __log2f(total);
+            if (pairs) {
+                uint32_t* gm = reinterpret_cast<uint32_t*>(row) + group_max_at(L);
+                const int ngroups = (L + 31) >> 5;
+                for (int j0 = 0; j0 < nw; j0 += 32) {                  // 64 priors = two groups per iteration
+                    const int j = j0 + lane;
+                    uint32_t e = 0;
+                    if (j < nw) {
+                        const uint32_t w = raw[j];
+                        const float p0 = ex2(fmaf(__uint_as_float(w << 16), kLog2e, off_p));
+                        const float p1 = ex2(fmaf(__uint_as_float(w & 0xFFFF0000u), kLog2e, off_p));
+                        reinterpret_cast<float2*>(row)[j] = make_float2(p0, p1);
+                        e = max(__float_as_uint(p0), __float_as_uint(p1)) + 1u;
+                    }
+                    const uint32_t lo = __reduce_max_sync(0xFFFFFFFFu, lane < 16 ? e : 0u);
+                    const uint32_t hi = __reduce_max_sync(0xFFFFFFFFu, lane < 16 ? 0u : e);
+                    const int gi = (j0 >> 4) + (lane >> 4);
+                    if ((lane & 15) == 0 && gi < ngroups) gm[gi] = lane ? hi : lo;
+                }
+            } else {
+                for (int k0 = 0; k0 < L; k0 += 32) {
+                    const int k = k0 + lane;
+                    store_prior_group(row, L, k0, k < L ? ex2(fmaf(__uint_as_float((uint32_t)rc[k] << 16), kLog2e, off_p)) : 0.0f, lane);
+                }
             }
         } else {                                                       // every legal move underflowed: MCTS.py:97-101
             const float u = __fdiv_rn(1.0f, (float)L);
@@ -737,20 +797,15 @@ ya_k_mcts_root_counts(ya_mcts_tree tree, const uint4* __restrict__ states, int64
     const uint32_t* node = v.nodes + (int64_t)idx * kNodeWords;
     if (lane == 0 && visits) visits[g] = (int32_t)node[N_VISITS];
     uint32_t desc = node[N_DESC];
-    uint32_t off = node[N_EDGES];
-    int remaining = (int)node[N_NEDGE];
-    while (remaining > 0) {
-        int cnt = min(remaining, kChunkEdges);
-        const uint32_t* ch = v.arena + off;
-        if (lane < cnt) {
-            int a = ya_nth_legal(desc, reinterpret_cast<const uint16_t*>(ch + 2)[lane]);
-            uint32_t raw = ch[18 + lane];
-            row[a] = (int32_t)(raw & 0x7FFFFFFFu);
-            if (qvals) qvals[g * YA_N_ACTION + a] = reinterpret_cast<const double*>(ch + 50)[lane];
-            if (qkind) qkind[g * YA_N_ACTION + a] = (raw >> 31) ? 2 : 1;       // 1 = float32, 2 = Python float
-        }
-        off = ch[0];
-        remaining -= cnt;
+    const int n_edges = (int)node[N_NEDGE];
+    if (n_edges == 0) return;
+    const Edges ed = edges_at(v.arena + node[N_EDGES], edge_cap(n_edges));
+    for (int e = lane; e < n_edges; e += 32) {
+        int a = ya_nth_legal(desc, ed.idx[e]);
+        uint32_t raw = ed.nsa[e];
+        row[a] = (int32_t)(raw & 0x7FFFFFFFu);
+        if (qvals) qvals[g * YA_N_ACTION + a] = ed.q[e];
+        if (qkind) qkind[g * YA_N_ACTION + a] = (raw >> 31) ? 2 : 1;           // 1 = float32, 2 = Python float
     }
 }
 
@@ -778,19 +833,13 @@ ya_k_mcts_root_sparse(ya_mcts_tree tree, const uint4* __restrict__ states, int64
     const int n_edges = (int)node[N_NEDGE];
     if (lane == 0 && overflow) overflow[g] = n_edges > k ? n_edges : 0;
     // legal indices ascend with actions, so the rank of an edge = number of edges with a smaller legal index
+    if (n_edges == 0) return;
+    const Edges ed = edges_at(v.arena + node[N_EDGES], edge_cap(n_edges));
     for (int e = lane; e < n_edges; e += 32) {
-        uint32_t off = node[N_EDGES];
-        for (int c = 0; c < e / kChunkEdges; ++c) off = v.arena[off];
-        const uint32_t* ch = v.arena + off;
-        const int my = reinterpret_cast<const uint16_t*>(ch + 2)[e % kChunkEdges];
-        const uint32_t nsa = ch[18 + e % kChunkEdges] & 0x7FFFFFFFu;
+        const int my = ed.idx[e];
+        const uint32_t nsa = ed.nsa[e] & 0x7FFFFFFFu;
         int rank = 0;
-        uint32_t o = node[N_EDGES];
-        for (int base = 0; base < n_edges; base += kChunkEdges, o = v.arena[o]) {
-            const uint16_t* ids = reinterpret_cast<const uint16_t*>(v.arena + o + 2);
-            const int cnt = min(kChunkEdges, n_edges - base);
-            for (int j = 0; j < cnt; ++j) rank += ids[j] < my;
-        }
+        for (int j = 0; j < n_edges; ++j) rank += ed.idx[j] < my;
         if (rank < k) { arow[rank] = (int16_t)ya_nth_legal(node[N_DESC], my); crow[rank] = (int32_t)nsa; }
     }
 }

@@ -30,7 +30,8 @@ elif what == "uniform":
 else:
     torch.manual_seed(0)
     net = YachtPolicyValueNet().to(dev)
-    sp = BatchedSelfPlay(4096, 100, evaluator=FusedYachtEvaluator(net, 4096), seed=1, device=dev, record_examples=False)
+    n = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
+    sp = BatchedSelfPlay(n, 100, evaluator=FusedYachtEvaluator(net, n), seed=1, device=dev, record_examples=False)
     for t in range(5):
         sp.play_ply(t)
 torch.cuda.synchronize()
