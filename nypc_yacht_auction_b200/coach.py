@@ -56,11 +56,12 @@ class BatchedSelfPlay:
     PLIES = 48
 
     def __init__(self, n, num_sims, cpuct=1.5, evaluator=None, temp_threshold=15, seed=0, game_base=0,
-                 device="cuda", arena_mb_per_game=None, record_examples=True, max_edges=None):
+                 device="cuda", arena_mb_per_game=None, record_examples=True, max_edges=None, record_states=False):
         self.env = BatchedYacht(n, seed=seed, game_base=game_base, device=device)
         self.mcts = BatchedMCTS(self.env, num_sims, cpuct, evaluator, temp_threshold, arena_mb_per_game)
         self.n = n
         self.record = record_examples
+        self.record_states = bool(record_states) and self.record      # packed canonical boards: examples.to_reference_examples
         self.k = int(max_edges or min(ACTION_SIZE, 2 * num_sims))
         d = self.env.device
         if self.record:
@@ -69,11 +70,16 @@ class BatchedSelfPlay:
             self.ex_counts = torch.zeros((self.PLIES, n, self.k), dtype=torch.int32, device=d)
             self.ex_players = torch.zeros((self.PLIES, n), dtype=torch.int8, device=d)
             self.ex_overflow = torch.zeros(n, dtype=torch.int32, device=d)
+            if self.record_states:
+                self.ex_states = torch.zeros((self.PLIES, 2, n, 4), dtype=torch.int32, device=d)
 
     def play_ply(self, t):
         env, m = self.env, self.mcts
         if self.record:
-            env.features(out=self.ex_features[t])                    # state_to_vec of the canonical root
+            if self.record_states:
+                env.features(canonical_states=env.canonical(out=self.ex_states[t]), out=self.ex_features[t])
+            else:
+                env.features(out=self.ex_features[t])                # state_to_vec of the canonical root
             self.ex_players[t].copy_(env.players)
         m.search()
         m.root_counts()
@@ -100,6 +106,8 @@ class BatchedSelfPlay:
             value = result_p1.unsqueeze(0) * self.ex_players.float()
             out = {"features": self.ex_features, "actions": self.ex_actions, "counts": self.ex_counts, "value": value,
                    "result_p1": result_p1}
+            if self.record_states:
+                out["states"] = self.ex_states
         return out
 
     def next_episode(self):

@@ -7,6 +7,7 @@ import pickle
 
 import numpy as np
 import pytest
+import torch
 
 from oracle import mcts_oracle
 from conftest import to_oracle_board
@@ -183,3 +184,26 @@ def test_seeded_episode_matches_unpatched_reference():
             assert {str(a): float(p).hex() for a, p in enumerate(pi) if p} == ref["pi"]
         assert int(np.random.randint(0, 2 ** 31)) == case["rng_after"]
         assert random.random().hex() == case["py_rng_after"]
+
+
+def test_examples_round_trip_through_reference_format(tmp_path):
+    """device examples -> (board, pi, v) tuples (what Coach.executeEpisode returns and
+    Coach.saveTrainExamples pickles, Coach.py:66-72,144-152) -> pickle -> tensors again."""
+    from nypc_yacht_auction_b200 import examples as exm
+    from nypc_yacht_auction_b200.coach import BatchedSelfPlay
+    sp = BatchedSelfPlay(5, 6, evaluator=None, seed=9, record_states=True)
+    ex = sp.execute_episodes()
+    tuples = exm.to_reference_examples(ex)
+    assert len(tuples) == 5 * 48
+    board, pi, v = tuples[48 + 3]                                     # game 1, ply 3
+    assert abs(sum(pi) - 1.0) < 1e-12 and len(pi) == 3226 and v in (1.0, -1.0, 1e-4, -1e-4)
+    assert 1 <= board.round_no <= 13 and board.phase in (0, 1)
+    path = tmp_path / "checkpoint_0.pth.tar.examples"
+    exm.save_train_examples(str(path), [tuples])
+    history = exm.load_train_examples(str(path))
+    back = exm.from_reference_examples(history[0])
+    feats = ex["features"].permute(1, 0, 2).reshape(-1, 59)           # game-major, like the tuple list
+    assert torch.equal(back["features"], feats)
+    dense = BatchedSelfPlay.dense_policy(ex["actions"], ex["counts"]).permute(1, 0, 2).reshape(-1, 3226)
+    assert torch.allclose(back["pi"].double(), dense, atol=1e-7)
+    assert torch.equal(back["value"], ex["value"].permute(1, 0).reshape(-1))
