@@ -60,8 +60,9 @@ def run(args, torch, dev, rank=0, world=1, dist=None):
     r = _run_selfplay(torch, dev, 16384, 100, ev, plies=4, warm_plies=4, seed=args.seed + 2, game_base=rank * 16384,
                       use_graph=True, dist=dist, world=world)
     out["mcts_nn"] = {
-        "workload": "configs[3]: AlphaZero self-play, random-init YachtNNet (hidden 256, 6 blocks; bf16 cuBLASLt GEMMs via torch, SiLU/LayerNorm/residual fused in csrc/ya_nn.cu), "
-                    "numMCTSSims=100, 16384 games/GPU, one batched forward per simulation wave, softmax+mask fused into the expand kernel, plies 4..7",
+        "workload": "configs[3]: AlphaZero self-play, random-init YachtNNet (hidden 256, 6 blocks; the whole forward is one tcgen05 kernel, csrc/ya_forward.cu, bf16 operands / float32 accumulation), "
+                    "numMCTSSims=100, 16384 games/GPU, one batched forward per simulation wave (3 launches per wave: select, forward, expand), "
+                    "softmax+mask fused into the expand kernel, plies 4..7",
         "sims_per_sec": r["sims_per_sec"], "game_steps_per_sec": r["steps_per_sec"], "ms": r["ms"], "gpu_launches": r["launches"],
         "pool_gb": r["pool_gb"], "max_nodes_in_use": r["max_nodes_in_use"],
         "nn_flops_per_leaf": 2 * YachtPolicyValueNet.num_macs()}
