@@ -256,6 +256,11 @@ def run_ours(args):
             cpu["mcts_uniform_sims_per_s"] = m["sims_per_s"]
             cpu["mcts_sample"] = "oracle port of MCTS.py self-play, uniform evaluator, numMCTSSims=25, %d sims in %.1f s on %d processes" % (
                 m["sims"], m["seconds"], m["cores"])
+            m = arena_port.timed_mcts_nn_sample(seed=args.seed, sims=100, budget_s=min(6.0, args.cpu_seconds))
+            cpu["mcts_nn_sims_per_s"] = m["sims_per_s"]
+            cpu["mcts_nn_sample"] = ("oracle port of MCTS.py + a float32 CPU forward of the same network per leaf (batch 1, as "
+                                     "NNetWrapper.predict), numMCTSSims=100, %d sims in %.1f s on %d processes" % (
+                                         m["sims"], m["seconds"], m["cores"]))
         try:                                  # context only: the same workload in plain C (OpenMP), not the reference's cost
             from oracle import c_oracle
             t0 = time.perf_counter()

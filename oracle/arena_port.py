@@ -94,3 +94,44 @@ def timed_mcts_sample(seed=0, sims=25, budget_s=8.0, procs=None):
             res = pool.map(_mcts_worker, jobs)
     return {"sims_per_s": sum(r[0] / r[2] for r in res), "steps_per_s": sum(r[1] / r[2] for r in res), "cores": procs,
             "sims": sum(r[0] for r in res), "seconds": max(r[2] for r in res)}
+
+
+# ---------------------------------------------------------------------------- MCTS + network baseline
+def _mcts_nn_worker(args):
+    """MCTS.py self-play with NNetWrapper.predict on the CPU (yacht/NNet.py:177-195: state_to_vec, one float32
+    forward of YachtNNet for ONE board, softmax) -- the reference's configs[3] cost profile, batch 1."""
+    import torch
+    from . import mcts_oracle
+    from nypc_yacht_auction_b200.nnet import YachtPolicyValueNet       # same architecture as yacht/pytorch/YachtNNet.py
+    seed, first, sims, budget_s = args
+    torch.set_num_threads(1)
+    torch.manual_seed(0)
+    net = YachtPolicyValueNet().eval()
+
+    def predict(board):
+        x = torch.from_numpy(yr.features(board)).unsqueeze(0)
+        with torch.no_grad():
+            logits, v = net(x)
+        return torch.softmax(logits, dim=1)[0].numpy(), np.float32(v.reshape(-1)[0].item())
+
+    t0 = time.perf_counter()
+    done = 0
+    g = first
+    while time.perf_counter() - t0 < budget_s:
+        trace, *_ = mcts_oracle.self_play_game(predict, sims, 1.5, seed, g, max_plies=2)
+        done += len(trace) * sims
+        g += 1
+    return done, time.perf_counter() - t0
+
+
+def timed_mcts_nn_sample(seed=0, sims=100, budget_s=6.0, procs=None):
+    """Oracle MCTS + float32 CPU forward per leaf (batch 1, one thread per process), first 2 plies of each game."""
+    procs = procs or os.cpu_count() or 1
+    jobs = [(seed, 1000 * i, sims, budget_s) for i in range(procs)]
+    if procs == 1:
+        res = [_mcts_nn_worker(jobs[0])]
+    else:
+        with mp.get_context("fork").Pool(procs) as pool:
+            res = pool.map(_mcts_nn_worker, jobs)
+    return {"sims_per_s": sum(r[0] / r[1] for r in res), "cores": procs, "sims": sum(r[0] for r in res),
+            "seconds": max(r[1] for r in res)}
