@@ -641,7 +641,13 @@ ya_k_mcts_expand_logits(ya_mcts_tree tree, const __nv_bfloat16* __restrict__ log
             int k0 = 0;
             for (uint32_t open = (desc >> 1) & 0xFFFu; open; open &= open - 1, k0 += YA_N_SUBSET / 2) {
                 const int a0 = (YA_N_BID + (__ffs(open) - 1) * YA_N_SUBSET) / 2;
-                for (int t = lane; t < YA_N_SUBSET / 2; t += 32) copy_word(k0 + t, a0 + t);
+                const uint32_t dst = raw_s + 4u * (uint32_t)(k0 + lane);
+                const uint32_t* src = lg + a0 + lane;                  // 126 words: lanes 0..29 take a fourth one
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n\t"
+                             "cp.async.ca.shared.global [%0 + 128], [%1 + 128], 4;\n\t"
+                             "cp.async.ca.shared.global [%0 + 256], [%1 + 256], 4;" ::"r"(dst), "l"(src) : "memory");
+                if (lane < YA_N_SUBSET / 2 - 96)
+                    asm volatile("cp.async.ca.shared.global [%0 + 384], [%1 + 384], 4;" ::"r"(dst), "l"(src) : "memory");
             }
         } else {                                                       // five dice: subset 0 of every open category
             if (lane < L) reinterpret_cast<uint16_t*>(raw)[lane] = reinterpret_cast<const uint16_t*>(lg)[ya_nth_legal(desc, lane)];
@@ -666,10 +672,21 @@ ya_k_mcts_expand_logits(ya_mcts_tree tree, const __nv_bfloat16* __restrict__ log
         const float off_sum = -mx * kLog2e;
         auto ex2 = [](float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; };
         const uint16_t* rc = reinterpret_cast<const uint16_t*>(raw);
-        const bool pairs = !(L & 1);
+        const bool pairs = !(L & 1), quads = !(L & 3);                 // ten-dice rows: L = 252 * open categories
         const int nw = L >> 1;
         float total = 0.0f;
-        if (pairs) {
+        if (quads) {
+            float t1 = 0.0f, t2 = 0.0f, t3 = 0.0f;
+            const uint2* raw2 = reinterpret_cast<const uint2*>(raw);
+            for (int j = lane; j < (L >> 2); j += 32) {
+                const uint2 w = raw2[j];
+                total += ex2(fmaf(__uint_as_float(w.x << 16), kLog2e, off_sum));
+                t1 += ex2(fmaf(__uint_as_float(w.x & 0xFFFF0000u), kLog2e, off_sum));
+                t2 += ex2(fmaf(__uint_as_float(w.y << 16), kLog2e, off_sum));
+                t3 += ex2(fmaf(__uint_as_float(w.y & 0xFFFF0000u), kLog2e, off_sum));
+            }
+            total = (total + t1) + (t2 + t3);
+        } else if (pairs) {
             float t1 = 0.0f;
             for (int j = lane; j < nw; j += 32) {
                 const uint32_t w = raw[j];
@@ -685,7 +702,31 @@ ya_k_mcts_expand_logits(ya_mcts_tree tree, const __nv_bfloat16* __restrict__ log
         float* row = reinterpret_cast<float*>(v.arena + node[N_PRIOR]);
         if (total > 0.0f) {
             const float off_p = off_sum - __log2f(total);
-            if (pairs) {
+            if (quads) {
+                // 128 priors = four groups per iteration: a lane owns four consecutive priors (one 16-byte store),
+                // eight lanes own a group and reduce its maximum with three shuffles
+                uint32_t* gm = reinterpret_cast<uint32_t*>(row) + group_max_at(L);
+                const uint2* raw2 = reinterpret_cast<const uint2*>(raw);
+                const int nq = L >> 2;
+                for (int j0 = 0; j0 < nq; j0 += 32) {
+                    const int j = j0 + lane;
+                    uint32_t e = 0;
+                    if (j < nq) {
+                        const uint2 w = raw2[j];
+                        float4 p;
+                        p.x = ex2(fmaf(__uint_as_float(w.x << 16), kLog2e, off_p));
+                        p.y = ex2(fmaf(__uint_as_float(w.x & 0xFFFF0000u), kLog2e, off_p));
+                        p.z = ex2(fmaf(__uint_as_float(w.y << 16), kLog2e, off_p));
+                        p.w = ex2(fmaf(__uint_as_float(w.y & 0xFFFF0000u), kLog2e, off_p));
+                        reinterpret_cast<float4*>(row)[j] = p;
+                        e = __float_as_uint(fmaxf(fmaxf(p.x, p.y), fmaxf(p.z, p.w))) + 1u;
+                    }
+                    e = max(e, __shfl_xor_sync(0xFFFFFFFFu, e, 1));
+                    e = max(e, __shfl_xor_sync(0xFFFFFFFFu, e, 2));
+                    e = max(e, __shfl_xor_sync(0xFFFFFFFFu, e, 4));
+                    if ((lane & 7) == 0 && j < nq) gm[j >> 3] = e;     // group of priors 4j .. 4j + 31
+                }
+            } else if (pairs) {
                 uint32_t* gm = reinterpret_cast<uint32_t*>(row) + group_max_at(L);
                 const int ngroups = (L + 31) >> 5;
                 for (int j0 = 0; j0 < nw; j0 += 32) {                  // 64 priors = two groups per iteration
