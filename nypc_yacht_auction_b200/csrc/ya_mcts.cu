@@ -652,6 +652,28 @@ ya_k_mcts_expand_logits(ya_mcts_tree tree, const __nv_bfloat16* __restrict__ log
         } else {                                                       // five dice: subset 0 of every open category
             if (lane < L) reinterpret_cast<uint16_t*>(raw)[lane] = reinterpret_cast<const uint16_t*>(lg)[ya_nth_legal(desc, lane)];
         }
+        // While the logits are in flight: pull the lines the backup will walk (one lane per level of the path --
+        // the node, the head of its edge index array, the prior group and group maximum of the chosen child).
+        {
+            const int depth = (int)v.cur[C_DEPTH];
+            if (lane < depth) {
+                const uint32_t pe = v.cur[C_PATH + lane];
+                const uint32_t* nd = v.nodes + (int64_t)(pe & 0xFFFFu) * kNodeWords;
+                const int ne = (int)nd[N_NEDGE], ai = (int)(pe >> 16);
+                const uint32_t* prow = v.arena + nd[N_PRIOR];
+                const int Lp = ya_legal_count(nd[N_DESC]);
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(prow + (ai & ~31)));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(prow + group_max_at(Lp) + (ai >> 5)));
+                if (ne > 0) {
+                    const uint32_t* eb = v.arena + nd[N_EDGES];
+                    const int cap = edge_cap(ne);
+                    for (int b = 0; b < ne * 2; b += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(eb) + b));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(eb + cap / 2));            // Nsa / Q of a one-chunk node
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(eb + cap / 2 + cap));
+                }
+            }
+            __syncwarp();
+        }
         float mx;
         if (row_max) {
             mx = row_max[g];
