@@ -167,7 +167,7 @@ class BatchedArena:
         return a_wins, b_wins, draws
 
 
-def self_play_in_waves(total_games, wave_games, num_sims, evaluator, first_game=0, on_wave=None, **kwargs):
+def self_play_in_waves(total_games, wave_games, num_sims, evaluator, first_game=0, on_wave=None, use_graph=True, **kwargs):
     """BASELINE.json configs[4]: more concurrent games than one tree pool fits in HBM (1,048,576 games over
     8 GPUs = 131,072 per GPU at ~4 MB of tree per game) are played as consecutive waves of `wave_games`
     games on ONE pool; wave w owns global games [first_game + w*wave_games, ...), so the result is the same
@@ -176,6 +176,8 @@ def self_play_in_waves(total_games, wave_games, num_sims, evaluator, first_game=
     (p1_wins, p2_wins, draws)."""
     assert total_games % wave_games == 0, "total_games must be a multiple of wave_games"
     sp = BatchedSelfPlay(wave_games, num_sims, evaluator=evaluator, game_base=first_game, **kwargs)
+    if use_graph and not getattr(sp.mcts.evaluator, "uniform", False):
+        sp.mcts.capture_graph()                                  # one simulation wave, replayed numMCTSSims times per move
     p1 = p2 = dr = 0
     for w in range(total_games // wave_games):
         if w:

@@ -39,7 +39,9 @@ def _run_selfplay(torch, dev, n, sims, evaluator, plies, warm_plies, seed, game_
     return {"ms": ms, "wall_s": wall, "sims": world * n * sims * plies, "game_steps": world * n * plies,
             "sims_per_sec": world * n * sims * plies / (ms * 1e-3), "steps_per_sec": world * n * plies / (ms * 1e-3),
             "pool_gb": sp.mcts.pool.bytes() / 1e9, "max_nodes_in_use": int(nodes.max().item()),
-            "launches": plies * (sims * 2 + 4)}
+            # per move: features, root counts, sparse root policy, pick, transition + the search itself (uniform prior:
+            # ONE launch for all simulations; network: select, forward, expand per simulation)
+            "launches": plies * (5 + (1 if getattr(evaluator, "uniform", False) else 3 * sims))}
 
 
 def run(args, torch, dev, rank=0, world=1, dist=None):
