@@ -1,16 +1,22 @@
 // Yacht-Auction B200 engine -- the WHOLE leaf-evaluator forward (YachtNNet.forward,
 // yacht/pytorch/YachtNNet.py:62-70) as one persistent tcgen05 kernel: state_to_vec features in, bf16 policy
-// logits (padded to 3232 columns) and tanh values out.  A CTA owns 128 leaves from the first Linear to the
-// last: activations stay in shared memory (bf16, 128-byte-swizzled K-major A operand), the skip connection
-// and the accumulators live in TMEM, every weight matrix arrives as a pre-swizzled image through
-// cp.async.bulk while the previous stage's epilogue runs, and all bias / SiLU / LayerNorm / residual / tanh
-// work happens in the tcgen05.ld epilogues.  Stages:
+// logits (padded to 3232 columns), tanh values and each row's largest logit out.  A CTA owns 128 leaves from
+// the first Linear to the last: the skip connection (float32) and the accumulators live in TMEM, every weight
+// matrix arrives as a pre-swizzled image through cp.async.bulk while an earlier stage computes, and all bias /
+// SiLU / LayerNorm / residual / tanh work happens in the tcgen05.ld epilogues.  Stages:
 //   input   Linear(59->256) + LN + SiLU                         (1 K-block of 64, N = 256)
-//   trunk   nblocks x [LN(SiLU(fc1)), skip + LN(SiLU(fc2))]     (4 K-blocks, N = 256)
+//   trunk   nblocks x [LN(SiLU(fc1)), skip + LN(SiLU(fc2))]     (4 K-blocks; two N = 128 halves per layer, each with
+//           its own completion barrier: the first epilogue pass over one half runs under the other half's MMAs;
+//           activations go back to shared memory as the next bf16, 128-byte-swizzled K-major A operand)
 //   value   SiLU(LN_v(h)) -> Linear(256->128) + SiLU -> dot(w2) + b2 -> tanh      (N = 128)
-//   policy  SiLU(LN_pi(h)) -> 26 tiles of Linear(256->128 columns) + bias -> bf16 logits
-// Every row is computed independently of the batch it sits in (fixed tile shapes, fixed accumulation order),
-// so the evaluator is batch-invariant: sharding leaves over GPUs or waves cannot change a single bit.
+//   policy  SiLU(LN_pi(h)) written ONCE to tensor memory (A operand from TMEM) -> 26 tiles of 128 columns:
+//           the freed A tile + the weight region = three 64 KB weight slots, three TMEM accumulators, full /
+//           drained mbarriers; warp 15 only produces (copies, MMAs), the other 15 warps run the epilogue
+//           (bias, running row maximum, bf16 packing, 256-bit stores)
+// Single-thread instructions (MMA, commit, bulk copy) are issued under elect.sync so they compile to
+// straight-line SASS.  Every row is computed independently of the batch it sits in (fixed tile shapes, fixed
+// accumulation order), so the evaluator is batch-invariant: sharding leaves over GPUs or waves cannot change a bit.
+// -DYA_FWD_TIMELINE builds the profiling variant used by profiles/tools/forward_timeline.py.
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <cstdint>
@@ -42,11 +48,8 @@ struct Blob {                                        // byte / float offsets of 
 __device__ unsigned long long g_timeline[1024];
 #define YA_STAMP() do { if (blockIdx.x == 0 && tid == 0 && tl_n < 1024) { unsigned long long t_; \
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); g_timeline[tl_n++] = t_; } } while (0)
-#define YA_STAMP2() do { if (blockIdx.x == 0 && tl_n < 512) { unsigned long long t_; \
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); g_timeline[512 + tl_n++] = t_; } } while (0)
 #else
 #define YA_STAMP() do { } while (0)
-#define YA_STAMP2() do { } while (0)
 #endif
 
 __device__ __forceinline__ uint32_t a_tile_offset(int r, int c8) {
@@ -112,7 +115,9 @@ ya_k_forward(const float* __restrict__ features, __nv_bfloat16* __restrict__ log
     const int colv[2] = {part * 32, 128 + part * 32};
     const uint32_t t_skip = t_lane + 256;                             // float32 skip connection: TMEM columns 256..511
     uint32_t w_phase = 0, m_phase = 0, m2_phase = 0;
-    int tl_n = 0; (void)tl_n;
+#ifdef YA_FWD_TIMELINE
+    int tl_n = 0;
+#endif
     int stage = 0;                                                    // parameter double buffer index = stage & 1
 
     // one weight image + one parameter block per stage, on one transaction barrier
@@ -436,14 +441,6 @@ ya_k_forward(const float* __restrict__ features, __nv_bfloat16* __restrict__ log
                 for (int k = 0; k < 4; ++k)
                     umma_ts(tmem + kPolicyTile + (j % 3) * kPolicyTile, tmem + kb * 32 + k * 8,
                             umma_desc_advance(db, kb * (kPolicyTile * 128) + k * 32), (uint32_t)((kb | k) != 0), idesc);
-#ifdef YA_FWD_EXP_DOUBLE_MMA
-#pragma unroll
-            for (int kb = 0; kb < 4; ++kb)
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    umma_ts(tmem + kPolicyTile + (j % 3) * kPolicyTile, tmem + kb * 32 + k * 8,
-                            umma_desc_advance(db, kb * (kPolicyTile * 128) + k * 32), 1u, idesc);
-#endif
             umma_commit(&bars[6 + j % 3]);
         };
         proxy_fence();
@@ -458,24 +455,16 @@ ya_k_forward(const float* __restrict__ features, __nv_bfloat16* __restrict__ log
             // streams into its slot.
             for (int j = 0; j < kPolicyTiles; ++j) {
                 const uint32_t par = (uint32_t)((j / 3) & 1);
-#ifndef YA_FWD_EXP_NOLOAD
                 mbar_wait(&bars[3 + policy_slot(j)], par);
-#else
-                if (j < 3) mbar_wait(&bars[3 + policy_slot(j)], par);
-#endif
-#ifndef YA_FWD_EXP_NODRAINWAIT
                 if (j >= 3) mbar_wait(&bars[9 + j % 3], par ^ 1u);
-#endif
                 tc_fence_after();
                 if (elect_one()) issue_tile(j);
                 __syncwarp();
-#ifndef YA_FWD_EXP_NOLOAD
                 if (j >= 1 && j + 2 < kPolicyTiles) {
                     mbar_wait(&bars[6 + (j - 1) % 3], (uint32_t)(((j - 1) / 3) & 1));
                     if (elect_one()) load_tile(j + 2);
                     __syncwarp();
                 }
-#endif
             }
         } else {
             // 15 epilogue warps: the issuer warp's share (rows 96..127, column part 3) goes to warp 11 on top of its own
@@ -517,15 +506,11 @@ ya_k_forward(const float* __restrict__ features, __nv_bfloat16* __restrict__ log
                                 p[i] = *reinterpret_cast<uint32_t*>(&h);
                             }
                             __nv_bfloat16* dst = logits + grow * kPolicyCols + col0;    // 64 bytes, 32-byte aligned
-#ifndef YA_FWD_EXP_NOSTORE
 #pragma unroll
                             for (int h2 = 0; h2 < 2; ++h2)            // 256-bit stores: half the LSU work of 4 x 16 bytes
                                 asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + 16 * h2),
                                              "r"(p[8 * h2]), "r"(p[8 * h2 + 1]), "r"(p[8 * h2 + 2]), "r"(p[8 * h2 + 3]),
                                              "r"(p[8 * h2 + 4]), "r"(p[8 * h2 + 5]), "r"(p[8 * h2 + 6]), "r"(p[8 * h2 + 7]) : "memory");
-#else
-                            if (p[0] == 0x12345678u && p[5] == 0x9abcdef0u) *reinterpret_cast<uint4*>(dst) = make_uint4(p[1] ^ p[9], p[2] ^ p[10], p[3] ^ p[11], p[4] ^ p[15]);
-#endif
                         }
                     }
                 }

@@ -39,12 +39,6 @@ for k in range(nst):
     nxt = t[3 * k + 3]
     print("%-10s %9.2f %9.2f %9.2f %9.2f" % (names[k], (a - t0) / 1e3, (b - a) / 1e3, (c - b) / 1e3, (nxt - c) / 1e3))
 base = 3 * nst
-pt = t[512:512 + 130]
-if pt[0]:
-    print("producer, per policy tile (us since tile 0 top): top  +wait weights  +wait drained  +issue MMAs  +wait prev retired & load next")
-    for j in range(26):
-        q = pt[5 * j:5 * j + 5]
-        print("  tile %2d  %6.2f  %5.2f %5.2f %5.2f %5.2f" % (j, (q[0] - pt[0]) / 1e3, (q[1] - q[0]) / 1e3, (q[2] - q[1]) / 1e3, (q[3] - q[2]) / 1e3, (q[4] - q[3]) / 1e3))
 pol = t[base:base + 27]
 print("policy: first accumulator ready at %.2f us; per tile (us):" % ((pol[0] - t0) / 1e3), " ".join("%.2f" % ((pol[i + 1] - pol[i]) / 1e3) for i in range(26)))
 print("total %.2f us" % ((pol[26] - t0) / 1e3))
