@@ -164,7 +164,10 @@ int ya_mcts_expand_logits(const ya_mcts_tree* tree, const void* logits_bf16, int
 
 /* getActionProb's whole simulation loop (MCTS.py:37-38) in ONE launch for the uniform evaluator
  * (pi = uniform_p, v = uniform_v; BASELINE.json configs[2]): num_sims x (descent, expansion, backup) per
- * game without leaving the SM.  Same results as num_sims x (ya_mcts_select, ya_mcts_expand(uniform)). */
+ * game without leaving the SM.  Same results as num_sims x (ya_mcts_select, ya_mcts_expand(uniform)).
+ * With one prior value for every legal move of a node, the nodes this call creates keep that value and a visited
+ * bitmask instead of a float32 prior row (0.4 KB instead of up to 12 KB): drive a tree either with this call or
+ * with ya_mcts_select / ya_mcts_expand*, not both (ya_mcts_reset in between); the root_* readers accept both. */
 int ya_mcts_search_uniform(const ya_mcts_tree* tree, const uint32_t* states, int64_t stride, const int8_t* players,
                            const int32_t* ply, const uint32_t* episode, uint64_t seed, uint64_t game_base, int num_sims,
                            float cpuct, float uniform_p, float uniform_v, const uint8_t* active, int32_t* err_flag,

@@ -29,7 +29,9 @@ constexpr int kWarpsPerBlock = 4;
 #endif
 
 // node words
-enum { N_KEY = 0, N_DESC = 8, N_VISITS = 9, N_PRIOR = 10, N_EDGES = 11, N_NEDGE = 12 };
+enum { N_KEY = 0, N_DESC = 8, N_VISITS = 9, N_PRIOR = 10, N_EDGES = 11, N_NEDGE = 12, N_KIND = 13, N_PCONST = 14 };
+// N_KIND 0: N_PRIOR -> float32 prior row + group maxima.  N_KIND 1 (uniform evaluator): every legal move has the SAME prior
+// (bits in N_PCONST), so N_PRIOR -> just a visited bitmask of ceil(L / 32) words: 0.4 KB instead of 12 KB per node.
 // cursor words
 enum { C_LEAF = 0, C_DEPTH = 8, C_KIND = 9, C_NODE = 10, C_PENDING = 11, C_PATH = 12 };
 enum { KIND_DONE = 0, KIND_NEED_EVAL = 1, KIND_ERROR = 2, KIND_NEED_DRAW = 3 };
@@ -132,6 +134,9 @@ __device__ __forceinline__ double es_as_double(float es) {       // getGameEnded
 }
 
 // ---------------------------------------------------------------- UCB argmax (MCTS.py:117-133)
+// CONST_ROWS: the walk may meet constant-prior nodes (only ya_k_mcts_search_uniform creates them, and a tree pool is
+// driven either by that kernel or by select / expand -- mcts.BatchedMCTS fixes the choice at construction).
+template <bool CONST_ROWS>
 __device__ __forceinline__ int ucb_select(const View& v, const uint32_t* node, int L, float cpuct, int lane) {
     const uint32_t visits = node[N_VISITS];
     const uint32_t* row = v.arena + node[N_PRIOR];
@@ -139,8 +144,40 @@ __device__ __forceinline__ int ucb_select(const View& v, const uint32_t* node, i
     const float sq_old = (float)sqrt((double)visits);
     float best = -CUDART_INF_F;
     int besti = 0x7FFFFFFF;
-    // visited edges: u = Q + cpuct * P * sqrt(Ns) / (1 + Nsa); two edges per lane in flight
     const int n_edges = (int)node[N_NEDGE];
+    if (CONST_ROWS && node[N_KIND]) {
+        // constant prior p: every unvisited child has the same u, so the lowest unvisited index wins among them
+        const float cp = __fmul_rn(cpuct, __uint_as_float(node[N_PCONST]));
+        if (n_edges > 0) {
+            const Edges ed = edges_at(v.arena + node[N_EDGES], edge_cap(n_edges));
+            for (int e = lane; e < n_edges; e += 32) {
+                const int ai = (int)ed.idx[e];
+                float x = __fdiv_rn(__fmul_rn(cp, sq_old), (float)(1u + (ed.nsa[e] & 0x7FFFFFFFu)));
+                float u = __fadd_rn((float)ed.q[e], x);
+                if (u > best || (u == best && ai < besti)) { best = u; besti = ai; }
+            }
+        }
+        int first = 0x7FFFFFFF;
+        for (int b = lane; b < ((L + 31) >> 5) && first == 0x7FFFFFFF; b += 32) {
+            const int nbits = min(32, L - 32 * b);
+            const uint32_t open = ~row[b] & (nbits == 32 ? 0xFFFFFFFFu : ((1u << nbits) - 1u));
+            if (open) first = 32 * b + __ffs(open) - 1;
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) first = min(first, __shfl_xor_sync(0xFFFFFFFFu, first, o));
+        if (first != 0x7FFFFFFF) {
+            const float u = __fmul_rn(cp, sq_new);
+            if (u > best || (u == best && first < besti)) { best = u; besti = first; }
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            float ou = __shfl_xor_sync(0xFFFFFFFFu, best, o);
+            int oi = __shfl_xor_sync(0xFFFFFFFFu, besti, o);
+            if (ou > best || (ou == best && oi < besti)) { best = ou; besti = oi; }
+        }
+        return besti;
+    }
+    // visited edges: u = Q + cpuct * P * sqrt(Ns) / (1 + Nsa); two edges per lane in flight
     if (n_edges > 0) {
         const Edges ed = edges_at(v.arena + node[N_EDGES], edge_cap(n_edges));
         for (int e0 = 0; e0 < n_edges; e0 += 64) {
@@ -271,8 +308,12 @@ __device__ __forceinline__ bool backup_edge(const View& v, uint32_t* node, int a
             ed.nsa[n_edges] = 1u | (val.is_f32 ? 0u : 0x80000000u);        // Qsa = v, Nsa = 1
             ed.q[n_edges] = val.d;
             node[N_NEDGE] = (uint32_t)(n_edges + 1);
-            v.arena[node[N_PRIOR] + ai] |= 0x80000000u;                     // mark the prior entry as visited
-            fresh = 1;
+            if (node[N_KIND]) {
+                v.arena[node[N_PRIOR] + (ai >> 5)] |= 1u << (ai & 31);      // constant-prior node: visited bitmask
+            } else {
+                v.arena[node[N_PRIOR] + ai] |= 0x80000000u;                 // mark the prior entry as visited
+                fresh = 1;
+            }
         }
         node[N_VISITS] += 1;                                         // Ns[s] += 1
     }
@@ -336,7 +377,7 @@ struct DrawSource {
 // state), KIND_DONE (terminal / dead end: w.ret is the value returned by the deepest call), KIND_NEED_DRAW
 // (injected mode only: the chosen transition needs dice the host has not supplied yet; w.leaf / w.depth /
 // w.pending describe where to resume) or KIND_ERROR.
-template <bool FEATURES, bool INJECT>
+template <bool FEATURES, bool INJECT, bool CONST_ROWS = false>
 __device__ __forceinline__ void descend(const View& v, YaState cur, Walk& w, uint64_t seed, uint32_t gid, uint32_t ep,
                                         uint32_t pl, uint32_t sim, float cpuct, float* __restrict__ feat_row, int lane,
                                         DrawSource src = DrawSource{nullptr, 0}) {
@@ -363,17 +404,19 @@ __device__ __forceinline__ void descend(const View& v, YaState cur, Walk& w, uin
                 int L = ya_legal_count(desc);
                 uint32_t row_at = (w.arena_top + 3u) & ~3u;         // 16-byte aligned prior rows
                 if ((int)w.node_count >= v.max_nodes) { w.err = E_NODES_FULL; w.kind = KIND_ERROR; break; }
-                if (row_at + (uint32_t)row_words(L) > v.arena_words) { w.err = E_ARENA_FULL; w.kind = KIND_ERROR; break; }
+                const uint32_t words = CONST_ROWS ? (uint32_t)((L + 31) >> 5) : (uint32_t)row_words(L);
+                if (row_at + words > v.arena_words) { w.err = E_ARENA_FULL; w.kind = KIND_ERROR; break; }
                 idx = (int)w.node_count;
                 if (lane == 0) {
                     uint32_t* nd = v.nodes + (int64_t)idx * kNodeWords;
 #pragma unroll
                     for (int i = 0; i < 8; ++i) nd[N_KEY + i] = cur.w[i];
                     nd[N_DESC] = desc; nd[N_VISITS] = 0; nd[N_PRIOR] = row_at; nd[N_EDGES] = 0; nd[N_NEDGE] = 0;
+                    nd[N_KIND] = CONST_ROWS ? 1u : 0u; nd[N_PCONST] = 0;
                     v.ht[free_slot] = (uint16_t)(idx + 1);
                 }
                 w.node_count += 1;
-                w.arena_top = row_at + (uint32_t)row_words(L);
+                w.arena_top = row_at + words;
                 if (FEATURES)
                     for (int f = lane; f < YA_N_FEATURE; f += 32) feat_row[f] = ya_feature(cur, f);
                 w.leaf_node = idx;
@@ -386,7 +429,7 @@ __device__ __forceinline__ void descend(const View& v, YaState cur, Walk& w, uin
             int L = ya_legal_count(desc);
             if (L == 0) { w.ret.d = 0.0; w.ret.is_f32 = false; break; }    // MCTS.py:138-147: `return 0`, not negated
             if (w.depth >= kMaxDepth) { w.err = E_DEPTH; w.kind = KIND_ERROR; break; }
-            int ai = ucb_select(v, node, L, cpuct, lane);
+            int ai = ucb_select<CONST_ROWS>(v, node, L, cpuct, lane);
             a = ya_nth_legal(desc, ai);
             if (lane == 0) v.cur[C_PATH + w.depth] = (uint32_t)idx | ((uint32_t)ai << 16);
         }
@@ -814,14 +857,22 @@ ya_k_mcts_search_uniform(ya_mcts_tree tree, const uint4* __restrict__ states, in
     prune_on_new_round(v, root, w, lane);
     int err = 0;
     for (int sim = 0; sim < num_sims; ++sim) {
-        descend<false, false>(v, root, w, seed, gid, ep, pl, (uint32_t)sim, cpuct, nullptr, lane);
+        descend<false, false, true>(v, root, w, seed, gid, ep, pl, (uint32_t)sim, cpuct, nullptr, lane);
         if (w.kind == KIND_ERROR) { err = w.err; break; }
         Val ret = w.ret;
         if (w.kind == KIND_NEED_EVAL) {
             uint32_t* node = v.nodes + (int64_t)w.leaf_node * kNodeWords;
             const uint32_t desc = node[N_DESC];
             const int L = ya_legal_count(desc);
-            if (L > 0) write_prior_row<1>(reinterpret_cast<float*>(v.arena + node[N_PRIOR]), desc, L, nullptr, uniform_p, lane);
+            if (L > 0) {
+                // Ps = uniform_p * valids, renormalised (MCTS.py:88-101): one value for every legal move; only the
+                // numpy-ordered sum decides its bits.  The node keeps that value and a visited bitmask.
+                float total = masked_pairwise_sum([uniform_p](int) { return uniform_p; }, desc, lane);
+                const float p = total > 0.0f ? __fdiv_rn(uniform_p, total) : __fdiv_rn(1.0f, (float)L);
+                uint32_t* mask = v.arena + node[N_PRIOR];
+                for (int b = lane; b < ((L + 31) >> 5); b += 32) mask[b] = 0u;
+                if (lane == 0) node[N_PCONST] = __float_as_uint(p);
+            }
             __syncwarp();
             ret.d = -(double)uniform_v;
             ret.is_f32 = true;

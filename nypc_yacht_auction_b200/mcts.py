@@ -324,7 +324,10 @@ class BatchedMCTS:
         self.picked = torch.zeros(n, dtype=torch.int32, device=d)
         self.sims_run = 0
         self.graph = None
-        self.fuse_uniform = True        # uniform evaluator: run all simulations of a move in one kernel
+        # uniform evaluator: all simulations of a move in one kernel.  That kernel's nodes carry one prior value and a
+        # visited bitmask instead of a prior row, so the choice holds for the life of the trees (set it before the
+        # first search, or call pool.reset() when changing it).
+        self.fuse_uniform = True
         uniform = getattr(self.evaluator, "uniform", False)
         if groups is None:
             groups = 1       # >1 overlaps slices on separate streams; measured gain on B200 is ~2 %, off by default
