@@ -422,3 +422,25 @@ def test_whole_forward_kernel():
     for lo, hi in ((0, 1), (5, 6), (100, 229), (640, 777)):
         l2, v2 = one(x[lo:hi].contiguous())
         assert torch.equal(l2[:, :3226], lf[lo:hi, :3226]) and torch.equal(v2, vf[lo:hi])
+
+
+def test_evaluator_abi_rejects_bad_arguments():
+    """The C entry points of the leaf evaluator report misuse as CUDA error codes instead of launching."""
+    from nypc_yacht_auction_b200 import _lib
+    from nypc_yacht_auction_b200.mcts import FusedYachtEvaluator
+    from nypc_yacht_auction_b200.nnet import YachtPolicyValueNet
+    lib = _lib.load()
+    ev = FusedYachtEvaluator(YachtPolicyValueNet().cuda().eval(), 256)
+    x = torch.zeros((256, 59), device="cuda")
+    s = _lib.current_stream()
+    args = lambda logits_ptr, n: (_lib.ptr(x), logits_ptr, _lib.ptr(ev.values), _lib.ptr(ev.row_max), _lib.ptr(ev.fw_w),
+                                  _lib.ptr(ev.fw_p), ev.fw_off, ev.nblocks, n, ev.eps, s)
+    assert lib.ya_nn_forward(*args(_lib.ptr(ev.logits), 0)) == 0                     # nothing to do
+    assert lib.ya_nn_forward(*args(ev.logits.data_ptr() + 2, 256)) != 0              # logits not 32-byte aligned
+    env = _engine(4, 1, 1)
+    from nypc_yacht_auction_b200.mcts import BatchedMCTS
+    m = BatchedMCTS(env, 2, 1.5, evaluator=ev.with_private_buffers(4))
+    v = torch.zeros(4, device="cuda")
+    bad_ld = lib.ya_mcts_expand_logits(m.pool.ref, _lib.ptr(ev.logits), 3226, None, _lib.ptr(v), None, _lib.ptr(m.err_flag), s)
+    assert bad_ld != 0                                                               # row stride must be >= 3232 and % 8 == 0
+    torch.cuda.synchronize()
