@@ -130,7 +130,9 @@ int ya_mcts_reset(const ya_mcts_tree* tree, const uint8_t* which, void* stream);
  * state_to_vec row in features[g][59] and (optionally) their packed state in leaf_states; all other
  * paths (terminal, dead end) are backed up inside this call.  err_flag bits: 0x100 node pool full,
  * 0x200 arena full, 0x400 path deeper than 16, 0x800 | (1 << status) rule error.  If sim_ptr (device)
- * is not NULL the simulation index is read from it, so one captured CUDA graph can be replayed. */
+ * is not NULL the simulation index is read from it, so one captured CUDA graph can be replayed.
+ * cpuct must be >= 0 (main.py:25 uses 1.5): the unvisited arg-max goes through per-group maxima of the priors,
+ * which needs cpuct * P * sqrt(Ns + EPS) to be monotone in P; a negative value is rejected (invalid value). */
 int ya_mcts_select(const ya_mcts_tree* tree, const uint32_t* states, int64_t stride, const int8_t* players,
                    const int32_t* ply, const uint32_t* episode, uint64_t seed, uint64_t game_base, uint32_t sim,
                    const uint32_t* sim_ptr, float cpuct, const uint8_t* active, float* features, uint8_t* need_eval,

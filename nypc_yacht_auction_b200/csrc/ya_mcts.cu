@@ -1040,7 +1040,7 @@ int ya_mcts_select(const ya_mcts_tree* tree, const uint32_t* states, int64_t str
                    const int32_t* ply, const uint32_t* episode, uint64_t seed, uint64_t game_base, uint32_t sim,
                    const uint32_t* sim_ptr, float cpuct, const uint8_t* active, float* features, uint8_t* need_eval,
                    uint32_t* leaf_states, int32_t* err_flag, void* stream) {
-    if (!tree_ok(tree)) return (int)cudaErrorInvalidValue;
+    if (!tree_ok(tree) || !(cpuct >= 0.0f)) return (int)cudaErrorInvalidValue;   // group maxima rely on u monotone in P
     if (leaf_states)
         ya_k_mcts_select<true, false><<<warp_blocks(tree->n), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
             *tree, reinterpret_cast<const uint4*>(states), stride, players, ply, episode, seed, game_base, sim, sim_ptr,
@@ -1055,7 +1055,7 @@ int ya_mcts_select(const ya_mcts_tree* tree, const uint32_t* states, int64_t str
 int ya_mcts_select_injected(const ya_mcts_tree* tree, const uint32_t* states, int64_t stride, const int8_t* players,
                             uint32_t sim, float cpuct, const uint8_t* injected, int resume, float* features,
                             uint8_t* need_eval, uint32_t* leaf_states, int32_t* err_flag, void* stream) {
-    if (!tree_ok(tree) || !injected || !leaf_states) return (int)cudaErrorInvalidValue;
+    if (!tree_ok(tree) || !injected || !leaf_states || !(cpuct >= 0.0f)) return (int)cudaErrorInvalidValue;
     ya_k_mcts_select<true, true><<<warp_blocks(tree->n), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
         *tree, reinterpret_cast<const uint4*>(states), stride, players, nullptr, nullptr, 0, 0, sim, nullptr,
         cpuct, nullptr, features, need_eval, leaf_states, err_flag, injected, resume);
@@ -1088,7 +1088,7 @@ int ya_mcts_search_uniform(const ya_mcts_tree* tree, const uint32_t* states, int
                            const int32_t* ply, const uint32_t* episode, uint64_t seed, uint64_t game_base, int num_sims,
                            float cpuct, float uniform_p, float uniform_v, const uint8_t* active, int32_t* err_flag,
                            void* stream) {
-    if (!tree_ok(tree) || num_sims < 0) return (int)cudaErrorInvalidValue;
+    if (!tree_ok(tree) || num_sims < 0 || !(cpuct >= 0.0f)) return (int)cudaErrorInvalidValue;
     ya_k_mcts_search_uniform<<<warp_blocks(tree->n), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
         *tree, reinterpret_cast<const uint4*>(states), stride, players, ply, episode, seed, game_base, num_sims, cpuct,
         uniform_p, uniform_v, active, err_flag);
