@@ -199,8 +199,16 @@ def test_fused_logits_expand_matches_softmax_mask_renorm():
             return self.logits, self.v
 
     n = 9
+    legal_counts = set()
+    for plies in (0, 5, 46, 47):                           # bid row (202), ten-dice score rows, five-dice rows of round 13
+        legal_counts |= _check_expand_rows(n, plies, LogitEval)
+    assert 202 in legal_counts and max(legal_counts) >= 2016 and min(legal_counts) <= 12, legal_counts
+
+
+def _check_expand_rows(n, plies, LogitEval):
+    from nypc_yacht_auction_b200.mcts import BatchedMCTS
     env = _engine(n, 3, 40)
-    for ply in range(5):                                   # reach a score ply for the first movers
+    for ply in range(plies):
         env.play_ply(masks=None, auto_reset=False)
     ev = LogitEval(n)
     mcts = BatchedMCTS(env, 4, 1.5, evaluator=ev)
@@ -210,6 +218,7 @@ def test_fused_logits_expand_matches_softmax_mask_renorm():
     arena = mcts.pool.arena.cpu().numpy().view(np.float32)
     nodes = mcts.pool.nodes.cpu().numpy()
     lg = ev.logits.float().cpu().numpy()[:, :3226]
+    counts = set()
     for g in range(n):
         legal = np.flatnonzero(masks[g])
         off = int(nodes[g, 0, 10])
@@ -218,8 +227,14 @@ def test_fused_logits_expand_matches_softmax_mask_renorm():
         pi = e / e.sum(dtype=np.float32)
         p = pi * masks[g]
         p = p / np.sum(p)
-        assert np.allclose(row, p[legal], rtol=2e-6, atol=1e-12), g
+        assert np.allclose(row, p[legal], rtol=2e-6, atol=1e-12), (plies, g)
         assert abs(float(row.sum()) - 1.0) < 1e-5
+        # group maxima: 1 + bits of the largest prior of each 32 (nothing visited yet)
+        gm = mcts.pool.arena.cpu().numpy().view(np.uint32)[g, off + ((len(legal) + 3) & ~3):][: (len(legal) + 31) // 32]
+        want = [int(row[k:k + 32].max().view(np.uint32)) + 1 for k in range(0, len(legal), 32)]
+        assert gm.tolist() == want, (plies, g)
+        counts.add(len(legal))
+    return counts
 
 
 def test_fused_evaluator_matches_module_forward():
