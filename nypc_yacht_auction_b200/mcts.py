@@ -117,10 +117,13 @@ class TorchEvaluator:
 
 
 class FusedYachtEvaluator:
-    """The yacht NNet forward for a whole wave of leaves: bf16 GEMMs through PyTorch (cuBLASLt) with every
-    SiLU / LayerNorm / residual between them fused into one hand-written pass (csrc/ya_nn.cu), the policy
-    head padded to 3232 aligned columns, and its raw bf16 logits consumed by ya_mcts_expand_logits.
-    Weights come from any module with YachtNNet's state dict (yacht/pytorch/YachtNNet.py:25-52)."""
+    """The yacht NNet forward (yacht/pytorch/YachtNNet.py:62-70) for a whole wave of leaves.  Default: ONE
+    hand-written tcgen05 kernel for the whole network (csrc/ya_forward.cu): features in, bf16 logits padded to
+    3232 columns + tanh value + per-row max logit out, consumed by ya_mcts_expand_logits; rows do not depend on
+    the batch they sit in.  whole_forward=False keeps the earlier composition -- bf16 GEMMs through PyTorch
+    (cuBLASLt) for the input layer and the heads, the trunk as one tcgen05 kernel (csrc/ya_trunk.cu) or, with
+    trunk_kernel=False too, a GEMM + fused SiLU / LayerNorm / residual pass (csrc/ya_nn.cu) per layer -- which
+    the tests use as cross-checks.  Weights come from any module with YachtNNet's state dict (:25-52)."""
     uniform = False
     returns_logits = True
     PADDED = 3232
@@ -155,7 +158,6 @@ class FusedYachtEvaluator:
         self.w_v2, self.b_v2 = bf(sd["v_head.4.weight"]).t().contiguous(), bf(sd["v_head.4.bias"])
         self.lib = _lib.load()
         self.eps = 1e-5
-        self._alloc(int(max_batch), dev)
         # the 2 * nblocks trunk layers for the persistent tcgen05 kernel (csrc/ya_trunk.cu)
         self.trunk_kernel = bool(trunk_kernel) and self.nblocks > 0
         if self.trunk_kernel:
@@ -163,7 +165,7 @@ class FusedYachtEvaluator:
             for i in range(self.nblocks):
                 p = "blocks.%d." % i
                 for fc, ln, kind in (("fc1", "ln1", 1), ("fc2", "ln2", 2)):
-                    images.append(self.swizzled_weight_image(sd[p + fc + ".weight"].to(dev)))
+                    images.append(self.swizzled_image(sd[p + fc + ".weight"].to(dev)))
                     params.append(torch.stack([sd[p + fc + ".bias"], sd[p + ln + ".weight"], sd[p + ln + ".bias"]]).float())
                     kinds.append(kind)
             self.trunk_w = torch.cat(images).contiguous()
@@ -199,8 +201,7 @@ class FusedYachtEvaluator:
             p_pi_ln = p_v + sum(psizes[4:9])
             self.fw_off = (ctypes.c_int64 * 9)(*w_off, p_in, p_trunk, p_v, p_pi_ln, p_pi_ln + 512)
             assert sum(psizes[4:9]) == 772 and psizes[3] == 768 * 2 * self.nblocks
-            self.values = torch.empty(int(max_batch), dtype=torch.float32, device=dev)
-            self.row_max = torch.empty(int(max_batch), dtype=torch.float32, device=dev)
+        self._alloc(int(max_batch), dev)
 
     @staticmethod
     def swizzled_image(w):
@@ -213,30 +214,21 @@ class FusedYachtEvaluator:
         img = torch.gather(w, 2, src_chunk.unsqueeze(-1).expand(rows, k // 64, 8, 8))
         return img.permute(1, 0, 2, 3).contiguous().view(torch.uint8).reshape(-1)
 
-    @staticmethod
-    def swizzled_weight_image(w):
-        """[256 out][256 in] weight -> the 128 KB shared-memory image tcgen05.mma reads: 4 K-blocks of
-        [256 rows][64 bf16], 16-byte chunk c of row r stored at chunk c ^ (r & 7) (128-byte swizzle)."""
-        w = w.to(torch.bfloat16).contiguous().view(256, 4, 8, 8)              # [row, k-block, chunk, 8 elements]
-        rows = torch.arange(256, device=w.device).view(256, 1, 1)
-        src_chunk = (torch.arange(8, device=w.device).view(1, 1, 8) ^ (rows & 7)).expand(256, 4, 8)   # position p holds chunk p ^ (r & 7)
-        img = torch.gather(w, 2, src_chunk.unsqueeze(-1).expand(256, 4, 8, 8))
-        return img.permute(1, 0, 2, 3).contiguous().view(torch.uint8).reshape(-1)                   # [k-block][row][128 B]
-
     def _alloc(self, n, dev):
         h = self.hidden
         mk = lambda *shape: torch.empty(shape, dtype=torch.bfloat16, device=dev)
-        self.z, self.h, self.a, self.p, self.q = mk(n, h), mk(n, h), mk(n, h), mk(n, h), mk(n, h)
         self.logits = mk(n, self.PADDED)
+        if self.whole_forward:
+            self.values = torch.empty(n, dtype=torch.float32, device=dev)
+            self.row_max = torch.empty(n, dtype=torch.float32, device=dev)
+        else:                                                             # activations between the layer-by-layer launches
+            self.z, self.h, self.a, self.p, self.q = mk(n, h), mk(n, h), mk(n, h), mk(n, h), mk(n, h)
 
     def with_private_buffers(self, max_batch):
         """Same weights, own activation buffers (one instance per concurrently running game group)."""
         import copy
         other = copy.copy(self)
         other._alloc(int(max_batch), self.w_in.device)
-        if self.whole_forward:
-            other.values = torch.empty(int(max_batch), dtype=torch.float32, device=self.w_in.device)
-            other.row_max = torch.empty(int(max_batch), dtype=torch.float32, device=self.w_in.device)
         return other
 
     def _ln(self, mode, x, ln, out, residual=None, ln2=None, out2=None):
