@@ -459,3 +459,41 @@ def test_evaluator_abi_rejects_bad_arguments():
     bad_ld = lib.ya_mcts_expand_logits(m.pool.ref, _lib.ptr(ev.logits), 3226, None, _lib.ptr(v), None, _lib.ptr(m.err_flag), s)
     assert bad_ld != 0                                                               # row stride must be >= 3232 and % 8 == 0
     torch.cuda.synchronize()
+
+
+def test_full_size_mcts_properties():
+    """BASELINE.json configs[2] and [3] at their full sizes (4,096 games x 25 sims uniform; 16,384 games x 100 sims
+    with the network), checked through size-independent properties of MCTS.getActionProb (MCTS.py:28-54): the
+    root's visit counts sum to Ns, a fresh root has exactly numMCTSSims - 1 child visits, every visited and every
+    picked action is legal, no pool overflow, and the first games of the big batch equal a small batch's games
+    (shard invariance)."""
+    from nypc_yacht_auction_b200.mcts import BatchedMCTS, FusedYachtEvaluator
+    from nypc_yacht_auction_b200.nnet import YachtPolicyValueNet
+    torch.manual_seed(4)
+    net = YachtPolicyValueNet().cuda().eval()
+    for n, sims, make_ev in ((4096, 25, lambda m: None), (16384, 100, lambda m: FusedYachtEvaluator(net, m))):
+        env = _engine(n, 8, 70000)
+        small = _engine(64, 8, 70000)
+        mcts = BatchedMCTS(env, sims, 1.5, evaluator=make_ev(n))
+        ref = BatchedMCTS(small, sims, 1.5, evaluator=make_ev(64))
+        for ply in range(3):
+            masks = env.valid_moves(states=env.canonical(), players=torch.ones(n, dtype=torch.int8, device="cuda")).bool()
+            mcts.search()
+            ref.search()
+            counts, visits = mcts.root_counts()
+            rcounts, _ = ref.root_counts()
+            assert torch.equal(counts[:64], rcounts)
+            assert bool((counts.sum(1) == visits).all())                           # sum of Nsa over the root's edges = Ns
+            if ply == 0:
+                assert bool((counts.sum(1) == sims - 1).all())                     # fresh root: the first search only expands
+            assert not bool((counts.bool() & ~masks).any())                        # visits only on legal moves
+            picked = mcts.pick_actions()
+            assert bool(masks.gather(1, picked.long().unsqueeze(1)).all())
+            assert torch.equal(picked[:64], ref.pick_actions())
+            env.next_state(picked)
+            small.next_state(ref.picked)
+        mcts.check_errors()
+        ref.check_errors()
+        assert int(mcts.pool.node_counts().max().item()) <= mcts.pool.max_nodes
+        del mcts, ref, env, small
+        torch.cuda.empty_cache()
