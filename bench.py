@@ -381,11 +381,14 @@ def run_extras(args, torch, env, dev, n, peak, rank=0, world=1, dist=None):
     ms = timed(lambda: env.play_ply(masks=None, auto_reset=True), 200)
     out["transition_only"] = {"steps_per_sec": n / (ms * 1e-3), "us_per_launch": ms * 1e3,
                               "note": "fused ply without materialising the mask (68 B/step; L2-resident, latency-bound)"}
-    try:
-        from nypc_yacht_auction_b200 import mcts_bench
-        out.update(mcts_bench.run(args, torch, dev, rank, world, dist))
-    except ImportError:
-        pass
+    from nypc_yacht_auction_b200 import mcts_bench
+    out.update(mcts_bench.run(args, torch, dev, rank, world, dist))
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if "nn_forward" in out and os.path.exists(peaks_path):          # tensor-bound kernel: against the measured bf16 GEMM rate
+        tf = json.load(open(peaks_path)).get("bf16_tflops")
+        if tf:
+            out["nn_forward"].update({"bound": "tensor", "peak_tflops": float(tf), "frac": out["nn_forward"]["tflops"] / float(tf),
+                                      "peak_source": "MEASURED_PEAKS.json bf16_tflops (cuBLAS 8192^3 burst)"})
     return out
 
 

@@ -61,6 +61,21 @@ def run(args, torch, dev, rank=0, world=1, dist=None):
     ev = FusedYachtEvaluator(net, 16384)
     r = _run_selfplay(torch, dev, 16384, 100, ev, plies=4, warm_plies=4, seed=args.seed + 2, game_base=rank * 16384,
                       use_graph=True, dist=dist, world=world)
+    # the leaf evaluator alone: one whole-network forward over 16,384 leaves (CUDA events, 50 launches)
+    x = torch.rand((16384, 59), device=dev)
+    for _ in range(5):
+        ev(x)
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(50):
+        ev(x)
+    f1.record()
+    torch.cuda.synchronize(dev)
+    fwd_us = f0.elapsed_time(f1) * 1000.0 / 50
+    real_flops = 2.0 * YachtPolicyValueNet.num_macs() * 16384
+    out["nn_forward"] = {"kernel": "ya_k_forward (tcgen05, bf16 operands, float32 accumulation)", "leaves": 16384,
+                         "us_per_launch": fwd_us, "tflops": real_flops / fwd_us * 1e-6,
+                         "note": "3.32 MFLOP per leaf (unpadded); 128 CTAs of 128 leaves on 148 SMs"}
     out["mcts_nn"] = {
         "workload": "configs[3]: AlphaZero self-play, random-init YachtNNet (hidden 256, 6 blocks; the whole forward is one tcgen05 kernel, csrc/ya_forward.cu, bf16 operands / float32 accumulation), "
                     "numMCTSSims=100, 16384 games/GPU, one batched forward per simulation wave (3 launches per wave: select, forward, expand), "
