@@ -287,7 +287,13 @@ ya_k_forward(const float* __restrict__ features, __nv_bfloat16* __restrict__ log
         if (producer && elect_one()) {                                // next stage's weights under the rest of this epilogue
             if (l + 1 < layers) load_stage(w_tile, off.w_trunk + (int64_t)(l + 1) * kWBytes, kWBytes, prm_buf(stage + 1),
                                            off.p_trunk + (int64_t)(l + 1) * 3 * kDim, 3 * kDim);
-            else load_stage(w_tile, off.w_v, 128 * 512, prm_buf(stage + 1), off.p_v, 772);
+            else {                                                    // value head weights; both heads' parameters
+                mbar_expect_tx(&bars[0], 65536 + 772 * 4 + 2 * kDim * 4);
+                bulk_g2s(w_tile, wblob + off.w_v, 32768, &bars[0]);
+                bulk_g2s(w_tile + 32768, wblob + off.w_v + 32768, 32768, &bars[0]);
+                bulk_g2s(prm_buf(stage + 1), pblob + off.p_v, 772 * 4, &bars[0]);
+                bulk_g2s(pi_prm, pblob + off.p_pi_ln, 2 * kDim * 4, &bars[0]);
+            }
         }
         __syncwarp();
         tmem_ld32(t_lane + colv[1], v1);
@@ -331,9 +337,10 @@ ya_k_forward(const float* __restrict__ features, __nv_bfloat16* __restrict__ log
     }
 
     // ---------------------------------------------------------------- heads: a = SiLU(LN(h; gamma, beta)) from the skip
-    // to_tmem: the activations go to tensor-memory columns [0, 128) as packed bf16 pairs (A operand read from TMEM)
-    auto head_prep = [&](const float* gamma_all, const float* beta_all, bool to_tmem) {
-        if (!worker) return;
+    // Both heads normalise the same h (YachtNNet.py:38-50): one statistics pass, then the value head's activations go
+    // to the shared-memory A tile and the policy head's to tensor-memory columns [0, 128) as packed bf16 pairs
+    // (A operand read from TMEM).
+    auto head_prep = [&](const float* gv, const float* bv, const float* gp, const float* bp) {
         float ps[4] = {0, 0, 0, 0}, pq[4] = {0, 0, 0, 0};
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
@@ -345,55 +352,51 @@ ya_k_forward(const float* __restrict__ features, __nv_bfloat16* __restrict__ log
         }
         float mean, rstd;
         row_stats((ps[0] + ps[1]) + (ps[2] + ps[3]), (pq[0] + pq[1]) + (pq[2] + pq[3]), mean, rstd);
+        const float nm = -mean * rstd;
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
-            uint32_t r[32];
+            uint32_t r[32], a[32];
             tmem_ld32(t_skip + colv[c], r);
             tmem_ld_wait();
-            const float* gamma = gamma_all + colv[c];
-            const float* beta = beta_all + colv[c];
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
-                const float ga = rstd * gamma[i];
-                float y = fmaf(__uint_as_float(r[i]), ga, fmaf(-mean, ga, beta[i]));
-                r[i] = __float_as_uint(silu_from_half(0.5f * y));
+                const float x = fmaf(__uint_as_float(r[i]), rstd, nm);
+                a[i] = __float_as_uint(silu_from_half(0.5f * fmaf(x, gv[colv[c] + i], bv[colv[c] + i])));
+                r[i] = __float_as_uint(silu_from_half(0.5f * fmaf(x, gp[colv[c] + i], bp[colv[c] + i])));
             }
-            if (to_tmem) {
-                uint32_t pk[16];
+            pack_store_a(a_tile, row, colv[c] / 8, a);
+            uint32_t pk[16];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
-                    pk[i] = *reinterpret_cast<uint32_t*>(&h);
-                }
-                tmem_st16(t_lane + (uint32_t)(colv[c] / 2), pk);       // K elements colv[c].. = packed columns colv[c] / 2..
-            } else {
-                pack_store_a(a_tile, row, colv[c] / 8, r);
+            for (int i = 0; i < 16; ++i) {
+                __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
+                pk[i] = *reinterpret_cast<uint32_t*>(&h);
             }
+            tmem_st16(t_lane + (uint32_t)(colv[c] / 2), pk);           // K elements colv[c].. = packed columns colv[c] / 2..
         }
-        if (to_tmem) tmem_st_wait();
+        tmem_st_wait();
     };
 
     // value head (YachtNNet.py:44-50): LN -> SiLU -> Linear(256,128) -> SiLU -> Linear(128,1) -> tanh
     {
         const float* prm = prm_all + (stage & 1) * kPrmFloats;       // gamma_v | beta_v | b1[128] | w2[128] | b2
         mbar_wait(&bars[0], w_phase);                                 // the LayerNorm parameters travel with the weights
-        head_prep(prm, prm + kDim, false);
-        run_mma(w_tile, 4, 128, 0);                                   // (re-waits the same completed phase, then flips it)
+        head_prep(prm, prm + kDim, pi_prm, pi_prm + kDim);
+        run_mma(w_tile, 4, 128, 128);                                 // accumulator in columns 128..255: 0..127 hold the policy A operand
         if (producer && elect_one()) {
             // The policy head reads its activations from tensor memory, so all 192 KB of operand space (A tile +
             // weight region) become three 64 KB weight slots; tiles 0..2 start streaming now.
             for (int j = 0; j < 3; ++j) {
                 uint64_t* bar = &bars[3 + policy_slot(j)];
-                mbar_expect_tx(bar, 65536 + (j == 0 ? kPiPrmFloats * 4 : 0));
+                mbar_expect_tx(bar, 65536 + (j == 0 ? kPolicyTiles * kPolicyTile * 4 : 0));
                 bulk_g2s(base + policy_slot(j) * 65536, wblob + off.w_pi + (int64_t)j * 65536, 32768, bar);
                 bulk_g2s(base + policy_slot(j) * 65536 + 32768, wblob + off.w_pi + (int64_t)j * 65536 + 32768, 32768, bar);
-                if (j == 0) bulk_g2s(pi_prm, pblob + off.p_pi_ln, kPiPrmFloats * 4, bar);
+                if (j == 0) bulk_g2s(pi_prm + 2 * kDim, pblob + off.p_pi_bias, kPolicyTiles * kPolicyTile * 4, bar);   // every bias
             }
         }
         float dot = 0.0f;
         if (worker) {
             uint32_t r[32];
-            tmem_ld32(t_lane + part * 32, r);
+            tmem_ld32(t_lane + 128 + part * 32, r);
             tmem_ld_wait();
             const float* b1 = prm + 2 * kDim + part * 32;
             const float* w2 = prm + 2 * kDim + 128 + part * 32;
@@ -417,13 +420,12 @@ ya_k_forward(const float* __restrict__ features, __nv_bfloat16* __restrict__ log
         ++stage;
     }
 
-    // policy head (YachtNNet.py:38-42): LN -> SiLU -> Linear(256, 3226) as 26 tiles of 128 columns.  Weight tiles
-    // ping-pong between the two 64 KB halves of the weight region (one transaction barrier per half) and
-    // accumulators between TMEM columns 0 and 128: as soon as tile j's MMAs retire, tile j + 2 starts streaming
-    // into the half they read and tile j + 1's MMAs are issued, all under the epilogue of tile j.
+    // policy head (YachtNNet.py:38-42): Linear(256, 3226) on the activations already sitting in tensor memory, as 26
+    // tiles of 128 columns.  Weight tiles rotate over three 64 KB slots and accumulators over TMEM columns 128 /
+    // 256 / 384: as soon as tile j's MMAs retire, tile j + 3's weights start streaming into the slot they read,
+    // and the MMAs of the following tiles run under the epilogue of tile j.
     {
-        mbar_wait(&bars[3 + policy_slot(0)], 0);                      // tile 0, gamma_pi | beta_pi and every bias landed
-        head_prep(pi_prm, pi_prm + kDim, true);
+        mbar_wait(&bars[3 + policy_slot(0)], 0);                      // tile 0 and every bias landed
         const float* bias_all = pi_prm + 2 * kDim;
         auto load_tile = [&](int j) {                                 // producer thread, j >= 3
             uint64_t* bar = &bars[3 + policy_slot(j)];
