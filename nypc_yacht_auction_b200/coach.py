@@ -127,7 +127,10 @@ class BatchedArena:
     populations: `n` games with evaluator A as player 1 and `n` games with the sides swapped, every player
     moving greedily on its own visit counts (temp = 0: np.argmax(getActionProb(x, temp=0)), ties broken
     uniformly).  Each side keeps its own trees, like the reference's separate pmcts / nmcts objects.
-    All games follow the same ply schedule, so at every ply one population searches a whole batch."""
+    All games follow the same ply schedule, so at every ply one population searches a whole batch.
+    A seat can also be a scripted device player -- pass "greedy" (GreedyYachtPlayer, yacht/YachtPlayers.py:186-214)
+    or "random" (RandomYachtPlayer, :174-183) instead of an evaluator -- which is how a network is measured
+    against the reference's heuristic opponent (Arena(mcts_player, GreedyYachtPlayer(g).play, g))."""
 
     PLIES = 48
 
@@ -138,8 +141,12 @@ class BatchedArena:
                      BatchedYacht(n, seed=seed, game_base=game_base + n, device=device)]
         evs = (evaluator_a, evaluator_b)
         # searchers[e][k]: the searcher of evaluator k on env e; env 0: A is player +1, env 1: B is player +1
-        self.searchers = [[BatchedMCTS(env, num_sims, cpuct, evs[k], temp_threshold=0, arena_mb_per_game=arena_mb_per_game)
+        self.searchers = [[evs[k] if isinstance(evs[k], str) else
+                           BatchedMCTS(env, num_sims, cpuct, evs[k], temp_threshold=0, arena_mb_per_game=arena_mb_per_game)
                            for k in range(2)] for env in self.envs]
+        for ev in evs:
+            if isinstance(ev, str) and ev not in ("greedy", "random"):
+                raise ValueError("scripted seat must be 'greedy' or 'random', got %r" % (ev,))
 
     def play_games(self):
         """Returns (a_wins, b_wins, draws) over the 2n games."""
@@ -148,13 +155,17 @@ class BatchedArena:
                 mover = int(env.players[0].item())                  # identical for every game of the batch
                 k = (0 if mover == 1 else 1) ^ e                    # which evaluator owns this seat
                 m = self.searchers[e][k]
+                if isinstance(m, str):                              # scripted seat
+                    env.next_state(env.greedy_actions() if m == "greedy" else env.random_actions(), check=False)
+                    continue
                 m.search()
                 m.root_counts()
                 env.next_state(m.pick_actions(), check=False)
         a_wins = b_wins = draws = 0
         for e, env in enumerate(self.envs):
             for row in self.searchers[e]:
-                row.check_errors()
+                if not isinstance(row, str):
+                    row.check_errors()
             r = env.game_ended(players=torch.ones_like(env.players))
             assert bool((r != 0).all())
             p1 = int((r > 0.5).sum().item())

@@ -368,6 +368,42 @@ def test_batched_arena_vs_oracle():
     assert (a, b, d) == (exp_a, exp_b, exp_d) and a + b + d == 2 * n
 
 
+def test_batched_arena_against_scripted_greedy_seat():
+    """An MCTS population against the device GreedyYachtPlayer (seat "greedy"), both seatings, against the oracle's
+    tree search and the oracle's restatement of the heuristic on the same Philox streams."""
+    from nypc_yacht_auction_b200.coach import BatchedArena
+    from nypc_yacht_auction_b200.mcts import UniformEvaluator
+    from oracle import greedy_oracle, philox
+    n, sims, seed, base = 4, 8, 17, 300
+
+    def oracle_game(gid, mcts_seat):
+        tree = mcts_oracle.TreeSearch(mcts_oracle.uniform_evaluator, sims, 1.5, seed, gid)
+        board = yr.new_game(philox.Draw(seed, gid, 0, 0, philox.TAG_INIT))
+        cur, ply = 1, 0
+        while yr.outcome(board, cur) == 0:
+            canon = yr.canonical(board, cur)
+            if cur == mcts_seat:
+                counts = tree.root_counts(canon, ply)
+                best = np.flatnonzero(counts == counts.max())
+                word = philox.draw_words(seed, gid, 0, ply, philox.TAG_ACTION)[3]
+                a = int(best[(word * len(best)) >> 32])
+            else:
+                a, legal = greedy_oracle.greedy_action(canon)
+                assert legal                                           # the overflow fallback (Q11) has its own test
+            board, cur = yr.next_state(board, cur, a, philox.Draw(seed, gid, 0, ply, philox.TAG_REAL))
+            ply += 1
+        return yr.outcome(board, 1)
+
+    arena = BatchedArena(n, sims, UniformEvaluator(), "greedy", seed=seed, game_base=base)
+    a, b, d = arena.play_games()
+    exp = [0, 0, 0]
+    for e in range(2):
+        for g in range(n):
+            r = oracle_game(base + e * n + g, 1 if e == 0 else -1)
+            exp[2 if abs(r) < 0.5 else (0 if (r > 0) == (e == 0) else 1)] += 1
+    assert [a, b, d] == exp and a + b + d == 2 * n
+
+
 def test_tcgen05_trunk_kernel_matches_layerwise_path():
     """csrc/ya_trunk.cu (persistent tcgen05 kernel for all residual blocks) against the layer-by-layer path
     (cuBLASLt GEMM + fused epilogue per layer) and the fp32 module: same bf16-level agreement, ragged row
