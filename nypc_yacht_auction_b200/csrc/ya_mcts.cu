@@ -24,6 +24,10 @@ constexpr int kCursorWords = 32;      // 128-byte per-game search cursor
 constexpr int kMaxDepth = 16;
 constexpr int kMinEdgeCap = 32;
 constexpr int kWarpsPerBlock = 4;
+#ifndef YA_SELECT_TEAM
+#define YA_SELECT_TEAM 8
+#endif
+constexpr int kSelectTeam = YA_SELECT_TEAM;   // lanes per game in the descent kernels (8: four games per warp)
 #ifndef YA_MCTS_MIN_BLOCKS
 #define YA_MCTS_MIN_BLOCKS 8          // <= 64 registers: 32 resident warps per SM for the latency-bound tree walks
 #endif
@@ -98,6 +102,33 @@ __device__ __forceinline__ void store_prior_group(float* __restrict__ row, int L
     if (lane == 0) reinterpret_cast<uint32_t*>(row)[group_max_at(L) + (k0 >> 5)] = e;
 }
 
+// W lanes cooperate on one game: W = 32 is a warp per game (the expand kernels, whose work is streaming a prior row);
+// W = 8 puts four games in a warp (the descent: mostly per-game scalar control flow -- rules, hashing, draws -- that
+// every lane of a team executes redundantly, so narrower teams mean fewer instructions per game and four
+// independent chains of dependent loads per warp).  All collectives are restricted to the team's lanes.
+template <int W>
+struct Team {
+    int sub;            // this lane's index inside the team
+    int shift;          // first lane of the team
+    uint32_t mask;      // the team's lanes
+    __device__ __forceinline__ static Team make() {
+        const int lane = threadIdx.x & 31;
+        Team t;
+        t.sub = lane & (W - 1);
+        t.shift = lane & ~(W - 1);
+        t.mask = W == 32 ? 0xFFFFFFFFu : ((W == 32 ? 0u : ((1u << (W & 31)) - 1u)) << t.shift);
+        return t;
+    }
+    __device__ __forceinline__ void sync() const { __syncwarp(mask); }
+    __device__ __forceinline__ uint32_t ballot(bool p) const {
+        const uint32_t b = __ballot_sync(mask, p) >> shift;
+        return W == 32 ? b : (b & ((1u << (W & 31)) - 1u));
+    }
+    template <class T> __device__ __forceinline__ T bcast(T v, int src_sub) const { return __shfl_sync(mask, v, shift + src_sub); }
+    template <class T> __device__ __forceinline__ T xor_(T v, int o) const { return __shfl_xor_sync(mask, v, o); }
+    __device__ __forceinline__ uint32_t reduce_max(uint32_t v) const { return __reduce_max_sync(mask, v); }
+};
+
 // A value travelling up the tree with the numeric type Python would give it.
 struct Val {
     double d;        // value (exact float32 value when is_f32)
@@ -136,8 +167,9 @@ __device__ __forceinline__ double es_as_double(float es) {       // getGameEnded
 // ---------------------------------------------------------------- UCB argmax (MCTS.py:117-133)
 // CONST_ROWS: the walk may meet constant-prior nodes (only ya_k_mcts_search_uniform creates them, and a tree pool is
 // driven either by that kernel or by select / expand -- mcts.BatchedMCTS fixes the choice at construction).
-template <bool CONST_ROWS>
-__device__ __forceinline__ int ucb_select(const View& v, const uint32_t* node, int L, float cpuct, int lane) {
+template <bool CONST_ROWS, int W>
+__device__ __forceinline__ int ucb_select(const View& v, const uint32_t* node, int L, float cpuct, const Team<W>& tm) {
+    const int sub = tm.sub;
     const uint32_t visits = node[N_VISITS];
     const uint32_t* row = v.arena + node[N_PRIOR];
     const float sq_new = (float)sqrt((double)visits + 1e-8);       // math.sqrt(Ns + EPS), rounded when it meets float32
@@ -145,12 +177,20 @@ __device__ __forceinline__ int ucb_select(const View& v, const uint32_t* node, i
     float best = -CUDART_INF_F;
     int besti = 0x7FFFFFFF;
     const int n_edges = (int)node[N_NEDGE];
+    auto team_argmax = [&] {                                        // (u desc, index asc) over the team
+#pragma unroll
+        for (int o = W / 2; o; o >>= 1) {
+            float ou = tm.xor_(best, o);
+            int oi = tm.xor_(besti, o);
+            if (ou > best || (ou == best && oi < besti)) { best = ou; besti = oi; }
+        }
+    };
     if (CONST_ROWS && node[N_KIND]) {
         // constant prior p: every unvisited child has the same u, so the lowest unvisited index wins among them
         const float cp = __fmul_rn(cpuct, __uint_as_float(node[N_PCONST]));
         if (n_edges > 0) {
             const Edges ed = edges_at(v.arena + node[N_EDGES], edge_cap(n_edges));
-            for (int e = lane; e < n_edges; e += 32) {
+            for (int e = sub; e < n_edges; e += W) {
                 const int ai = (int)ed.idx[e];
                 float x = __fdiv_rn(__fmul_rn(cp, sq_old), (float)(1u + (ed.nsa[e] & 0x7FFFFFFFu)));
                 float u = __fadd_rn((float)ed.q[e], x);
@@ -158,35 +198,30 @@ __device__ __forceinline__ int ucb_select(const View& v, const uint32_t* node, i
             }
         }
         int first = 0x7FFFFFFF;
-        for (int b = lane; b < ((L + 31) >> 5) && first == 0x7FFFFFFF; b += 32) {
+        for (int b = sub; b < ((L + 31) >> 5) && first == 0x7FFFFFFF; b += W) {
             const int nbits = min(32, L - 32 * b);
             const uint32_t open = ~row[b] & (nbits == 32 ? 0xFFFFFFFFu : ((1u << nbits) - 1u));
             if (open) first = 32 * b + __ffs(open) - 1;
         }
 #pragma unroll
-        for (int o = 16; o; o >>= 1) first = min(first, __shfl_xor_sync(0xFFFFFFFFu, first, o));
+        for (int o = W / 2; o; o >>= 1) first = min(first, tm.xor_(first, o));
         if (first != 0x7FFFFFFF) {
             const float u = __fmul_rn(cp, sq_new);
             if (u > best || (u == best && first < besti)) { best = u; besti = first; }
         }
-#pragma unroll
-        for (int o = 16; o; o >>= 1) {
-            float ou = __shfl_xor_sync(0xFFFFFFFFu, best, o);
-            int oi = __shfl_xor_sync(0xFFFFFFFFu, besti, o);
-            if (ou > best || (ou == best && oi < besti)) { best = ou; besti = oi; }
-        }
+        team_argmax();
         return besti;
     }
     // visited edges: u = Q + cpuct * P * sqrt(Ns) / (1 + Nsa); two edges per lane in flight
     if (n_edges > 0) {
         const Edges ed = edges_at(v.arena + node[N_EDGES], edge_cap(n_edges));
-        for (int e0 = 0; e0 < n_edges; e0 += 64) {
+        for (int e0 = 0; e0 < n_edges; e0 += 2 * W) {
             int ai[2];
             uint32_t nsa[2], pb[2];
             double q[2];
 #pragma unroll
             for (int t = 0; t < 2; ++t) {
-                const int e = e0 + 32 * t + lane;
+                const int e = e0 + W * t + sub;
                 const bool ok = e < n_edges;
                 ai[t] = ok ? (int)ed.idx[e] : 0;
                 nsa[t] = ok ? ed.nsa[e] & 0x7FFFFFFFu : 0u;
@@ -196,7 +231,7 @@ __device__ __forceinline__ int ucb_select(const View& v, const uint32_t* node, i
             for (int t = 0; t < 2; ++t) pb[t] = row[ai[t]];
 #pragma unroll
             for (int t = 0; t < 2; ++t) {
-                if (e0 + 32 * t + lane < n_edges) {
+                if (e0 + W * t + sub < n_edges) {
                     float p = __uint_as_float(pb[t] & 0x7FFFFFFFu);
                     float x = __fmul_rn(__fmul_rn(cpuct, p), sq_old);
                     x = __fdiv_rn(x, (float)(1u + nsa[t]));
@@ -213,7 +248,7 @@ __device__ __forceinline__ int ucb_select(const View& v, const uint32_t* node, i
         const int ngroups = (L + 31) >> 5;
         float gu = -CUDART_INF_F;
         int gb = 0x7FFFFFFF;
-        for (int b = lane; b < ngroups; b += 32) {                  // <= 3 words per lane
+        for (int b = sub; b < ngroups; b += W) {
             uint32_t e = gmax[b];
             if (e) {
                 float u = __fmul_rn(__fmul_rn(cpuct, __uint_as_float(e - 1u)), sq_new);
@@ -221,34 +256,35 @@ __device__ __forceinline__ int ucb_select(const View& v, const uint32_t* node, i
             }
         }
 #pragma unroll
-        for (int o = 16; o; o >>= 1) {
-            float ou = __shfl_xor_sync(0xFFFFFFFFu, gu, o);
-            int ob = __shfl_xor_sync(0xFFFFFFFFu, gb, o);
+        for (int o = W / 2; o; o >>= 1) {
+            float ou = tm.xor_(gu, o);
+            int ob = tm.xor_(gb, o);
             if (ou > gu || (ou == gu && ob < gb)) { gu = ou; gb = ob; }
         }
         if (gb != 0x7FFFFFFF) {
-            int i = (gb << 5) + lane;
-            if (i < L) {
-                uint32_t bits = row[i];
-                if (!(bits >> 31)) {
-                    float u = __fmul_rn(__fmul_rn(cpuct, __uint_as_float(bits)), sq_new);
-                    if (u > best || (u == best && i < besti)) { best = u; besti = i; }
+#pragma unroll
+            for (int t = 0; t < 32 / W; ++t) {                      // the 32 priors of that group
+                int i = (gb << 5) + t * W + sub;
+                if (i < L) {
+                    uint32_t bits = row[i];
+                    if (!(bits >> 31)) {
+                        float u = __fmul_rn(__fmul_rn(cpuct, __uint_as_float(bits)), sq_new);
+                        if (u > best || (u == best && i < besti)) { best = u; besti = i; }
+                    }
                 }
             }
         }
     }
-#pragma unroll
-    for (int o = 16; o; o >>= 1) {
-        float ou = __shfl_xor_sync(0xFFFFFFFFu, best, o);
-        int oi = __shfl_xor_sync(0xFFFFFFFFu, besti, o);
-        if (ou > best || (ou == best && oi < besti)) { best = ou; besti = oi; }
-    }
+    team_argmax();
     return besti;
 }
 
 // ---------------------------------------------------------------- backup (MCTS.py:152-164)
 // Returns false if the arena overflowed.
-__device__ __forceinline__ bool backup_edge(const View& v, uint32_t* node, int ai, const Val& val, uint32_t& arena_top, int lane) {
+template <int W>
+__device__ __forceinline__ bool backup_edge(const View& v, uint32_t* node, int ai, const Val& val, uint32_t& arena_top,
+                                            const Team<W>& tm) {
+    const int sub = tm.sub;
     int failed = 0, fresh = 0;
     // locate the edge
     const int n_edges = (int)node[N_NEDGE];
@@ -257,12 +293,12 @@ __device__ __forceinline__ bool backup_edge(const View& v, uint32_t* node, int a
     int found = -1;
     if (n_edges > 0) {
         const Edges ed = edges_at(base, cap);
-        for (int e0 = 0; e0 < n_edges && found < 0; e0 += 64) {
-            const int ea = e0 + lane, eb = e0 + 32 + lane;
+        for (int e0 = 0; e0 < n_edges && found < 0; e0 += 2 * W) {
+            const int ea = e0 + sub, eb = e0 + W + sub;
             const int ia = ea < n_edges ? (int)ed.idx[ea] : -1, ib = eb < n_edges ? (int)ed.idx[eb] : -1;
-            const uint32_t ma = __ballot_sync(0xFFFFFFFFu, ia == ai), mb = __ballot_sync(0xFFFFFFFFu, ib == ai);
+            const uint32_t ma = tm.ballot(ia == ai), mb = tm.ballot(ib == ai);
             if (ma) found = e0 + __ffs(ma) - 1;
-            else if (mb) found = e0 + 32 + __ffs(mb) - 1;
+            else if (mb) found = e0 + W + __ffs(mb) - 1;
         }
     }
     // a first visit appends; a full array moves to one of twice the capacity first (all lanes copy)
@@ -275,15 +311,15 @@ __device__ __forceinline__ bool backup_edge(const View& v, uint32_t* node, int a
             uint32_t* nb = v.arena + top;
             if (n_edges > 0) {
                 const Edges from = edges_at(base, cap), to = edges_at(nb, new_cap);
-                for (int e = lane; e < n_edges; e += 32) { to.idx[e] = from.idx[e]; to.nsa[e] = from.nsa[e]; to.q[e] = from.q[e]; }
+                for (int e = sub; e < n_edges; e += W) { to.idx[e] = from.idx[e]; to.nsa[e] = from.nsa[e]; to.q[e] = from.q[e]; }
             }
-            __syncwarp();
-            if (lane == 0) node[N_EDGES] = top;
+            tm.sync();
+            if (sub == 0) node[N_EDGES] = top;
             arena_top = top + (uint32_t)edge_words(new_cap);
             base = nb;
         }
     }
-    if (lane == 0) {
+    if (sub == 0) {
         if (found >= 0) {
             const Edges ed = edges_at(base, cap);
             uint32_t raw = ed.nsa[found];
@@ -317,26 +353,30 @@ __device__ __forceinline__ bool backup_edge(const View& v, uint32_t* node, int a
         }
         node[N_VISITS] += 1;                                         // Ns[s] += 1
     }
-    fresh = __shfl_sync(0xFFFFFFFFu, fresh, 0);
-    __syncwarp();
+    fresh = tm.bcast(fresh, 0);
+    tm.sync();
     if (fresh) {                                                     // the child's group lost an unvisited prior
         const int L = ya_legal_count(node[N_DESC]);
         uint32_t* row = v.arena + node[N_PRIOR];
-        const int i = (ai & ~31) + lane;
         uint32_t e = 0;
-        if (i < L) { uint32_t b = row[i]; if (!(b >> 31)) e = b + 1u; }
-        e = __reduce_max_sync(0xFFFFFFFFu, e);
-        if (lane == 0) row[group_max_at(L) + (ai >> 5)] = e;
-        __syncwarp();
+#pragma unroll
+        for (int t = 0; t < 32 / W; ++t) {
+            const int i = (ai & ~31) + t * W + sub;
+            if (i < L) { uint32_t b = row[i]; if (!(b >> 31)) e = max(e, b + 1u); }
+        }
+        e = tm.reduce_max(e);
+        if (sub == 0) row[group_max_at(L) + (ai >> 5)] = e;
+        tm.sync();
     }
     return !failed;
 }
 
-__device__ __forceinline__ bool backup_path(const View& v, int depth, Val ret, uint32_t& arena_top, int lane) {
+template <int W>
+__device__ __forceinline__ bool backup_path(const View& v, int depth, Val ret, uint32_t& arena_top, const Team<W>& tm) {
     for (int d = depth - 1; d >= 0; --d) {
         uint32_t pe = v.cur[C_PATH + d];
         uint32_t* node = v.nodes + (int64_t)(pe & 0xFFFFu) * kNodeWords;
-        if (!backup_edge(v, node, (int)(pe >> 16), ret, arena_top, lane)) return false;
+        if (!backup_edge(v, node, (int)(pe >> 16), ret, arena_top, tm)) return false;
         ret.d = -ret.d;                                              // return -v
     }
     return true;
@@ -352,16 +392,18 @@ struct Walk {
 
 // Lazy pruning at round boundaries: inside rounds >= 2 the search never leaves the root's round
 // (quirk Q3), so nothing stored for an earlier round >= 2 can be reached again.
-__device__ __forceinline__ void prune_on_new_round(const View& v, const YaState& root, Walk& w, int lane) {
+template <int W>
+__device__ __forceinline__ void prune_on_new_round(const View& v, const YaState& root, Walk& w, const Team<W>& tm) {
     uint32_t old_round = v.meta[M_ROUND], new_round = (uint32_t)ya_round(root);
     if (old_round == new_round) return;
     if (old_round >= 2 || new_round < old_round) {
-        for (int i = lane; i < v.ht_size / 2; i += 32) reinterpret_cast<uint32_t*>(v.ht)[i] = 0u;
+        for (int i = tm.sub; i < v.ht_size / 2; i += W) reinterpret_cast<uint32_t*>(v.ht)[i] = 0u;
         w.node_count = 0;
         w.arena_top = 4;
     }
-    if (lane == 0) v.meta[M_ROUND] = new_round;
-    __syncwarp();
+    tm.sync();                                                       // every lane has read the old round
+    if (tm.sub == 0) v.meta[M_ROUND] = new_round;
+    tm.sync();
 }
 
 // One descent from the canonical root.  On return: kind == KIND_NEED_EVAL (leaf allocated, w.leaf holds its
@@ -377,10 +419,11 @@ struct DrawSource {
 // state), KIND_DONE (terminal / dead end: w.ret is the value returned by the deepest call), KIND_NEED_DRAW
 // (injected mode only: the chosen transition needs dice the host has not supplied yet; w.leaf / w.depth /
 // w.pending describe where to resume) or KIND_ERROR.
-template <bool FEATURES, bool INJECT, bool CONST_ROWS = false>
+template <bool FEATURES, bool INJECT, bool CONST_ROWS, int W>
 __device__ __forceinline__ void descend(const View& v, YaState cur, Walk& w, uint64_t seed, uint32_t gid, uint32_t ep,
-                                        uint32_t pl, uint32_t sim, float cpuct, float* __restrict__ feat_row, int lane,
-                                        DrawSource src = DrawSource{nullptr, 0}) {
+                                        uint32_t pl, uint32_t sim, float cpuct, float* __restrict__ feat_row,
+                                        const Team<W>& tm, DrawSource src = DrawSource{nullptr, 0}) {
+    const int lane = tm.sub;                                        // index inside the team
     w.depth = 0; w.kind = KIND_DONE; w.err = 0; w.leaf_node = -1; w.pending = 0;
     w.ret.d = 0.0; w.ret.is_f32 = false;
     bool pending = false;
@@ -418,10 +461,10 @@ __device__ __forceinline__ void descend(const View& v, YaState cur, Walk& w, uin
                 w.node_count += 1;
                 w.arena_top = row_at + words;
                 if (FEATURES)
-                    for (int f = lane; f < YA_N_FEATURE; f += 32) feat_row[f] = ya_feature(cur, f);
+                    for (int f = lane; f < YA_N_FEATURE; f += W) feat_row[f] = ya_feature(cur, f);
                 w.leaf_node = idx;
                 w.kind = KIND_NEED_EVAL;
-                __syncwarp();
+                tm.sync();
                 break;
             }
             uint32_t* node = v.nodes + (int64_t)idx * kNodeWords;
@@ -429,7 +472,7 @@ __device__ __forceinline__ void descend(const View& v, YaState cur, Walk& w, uin
             int L = ya_legal_count(desc);
             if (L == 0) { w.ret.d = 0.0; w.ret.is_f32 = false; break; }    // MCTS.py:138-147: `return 0`, not negated
             if (w.depth >= kMaxDepth) { w.err = E_DEPTH; w.kind = KIND_ERROR; break; }
-            int ai = ucb_select<CONST_ROWS>(v, node, L, cpuct, lane);
+            int ai = ucb_select<CONST_ROWS>(v, node, L, cpuct, tm);
             a = ya_nth_legal(desc, ai);
             if (lane == 0) v.cur[C_PATH + w.depth] = (uint32_t)idx | ((uint32_t)ai << 16);
         }
@@ -460,7 +503,7 @@ __device__ __forceinline__ void descend(const View& v, YaState cur, Walk& w, uin
         ++w.depth;
     }
     w.leaf = cur;
-    __syncwarp();
+    tm.sync();
 }
 
 template <bool WRITE_LEAF_STATE, bool INJECT>
@@ -470,9 +513,10 @@ ya_k_mcts_select(ya_mcts_tree tree, const uint4* __restrict__ states, int64_t st
                  uint32_t sim, const uint32_t* __restrict__ sim_ptr, float cpuct, const uint8_t* __restrict__ active,
                  float* __restrict__ features, uint8_t* __restrict__ need_eval, uint32_t* __restrict__ leaf_states,
                  int32_t* __restrict__ err_flag, const uint8_t* __restrict__ injected, int resume) {
-    const int lane = threadIdx.x & 31;
+    const Team<kSelectTeam> tm = Team<kSelectTeam>::make();          // four games per warp
+    const int lane = tm.sub;
     if (sim_ptr) sim = *sim_ptr;                                     // CUDA-graph replay: the counter lives in HBM
-    const int64_t g = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    const int64_t g = ((int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5)) * (32 / kSelectTeam) + (tm.shift / kSelectTeam);
     if (g >= tree.n) return;
     if (active && !active[g]) { if (lane == 0) need_eval[g] = 0; return; }
     View v = make_view(tree, g);
@@ -483,11 +527,11 @@ ya_k_mcts_select(ya_mcts_tree tree, const uint4* __restrict__ states, int64_t st
     Walk w;
     w.node_count = v.meta[M_NODES];
     w.arena_top = v.meta[M_TOP];
-    if (sim == 0 && !(INJECT && resume)) prune_on_new_round(v, root, w, lane);
+    if (sim == 0 && !(INJECT && resume)) prune_on_new_round(v, root, w, tm);
     DrawSource src{INJECT ? injected + g * 12 : nullptr, INJECT ? resume : 0};
-    descend<true, INJECT>(v, root, w, seed, gid, ep, pl, sim, cpuct, features + g * YA_N_FEATURE, lane, src);
+    descend<true, INJECT, false>(v, root, w, seed, gid, ep, pl, sim, cpuct, features + g * YA_N_FEATURE, tm, src);
     if (w.kind == KIND_DONE) {
-        if (!backup_path(v, w.depth, w.ret, w.arena_top, lane)) { w.err = E_ARENA_FULL; w.kind = KIND_ERROR; }
+        if (!backup_path(v, w.depth, w.ret, w.arena_top, tm)) { w.err = E_ARENA_FULL; w.kind = KIND_ERROR; }
     }
     if (lane == 0) {
         v.meta[M_NODES] = w.node_count;
@@ -639,7 +683,7 @@ ya_k_mcts_expand(ya_mcts_tree tree, const float* __restrict__ pi_all, const floa
     ret.d = -(double)(MODE == 1 ? uniform_v : value[g]);             // return -v (numpy float32)
     ret.is_f32 = true;
     uint32_t arena_top = v.meta[M_TOP];
-    bool ok = backup_path(v, (int)v.cur[C_DEPTH], ret, arena_top, lane);
+    bool ok = backup_path(v, (int)v.cur[C_DEPTH], ret, arena_top, Team<32>::make());
     if (lane == 0) {
         v.meta[M_TOP] = arena_top;
         v.cur[C_KIND] = KIND_DONE;
@@ -825,7 +869,7 @@ ya_k_mcts_expand_logits(ya_mcts_tree tree, const __nv_bfloat16* __restrict__ log
     ret.d = -(double)value[g];
     ret.is_f32 = true;
     uint32_t arena_top = v.meta[M_TOP];
-    bool ok = backup_path(v, (int)v.cur[C_DEPTH], ret, arena_top, lane);
+    bool ok = backup_path(v, (int)v.cur[C_DEPTH], ret, arena_top, Team<32>::make());
     if (lane == 0) {
         v.meta[M_TOP] = arena_top;
         v.cur[C_KIND] = KIND_DONE;
@@ -854,10 +898,11 @@ ya_k_mcts_search_uniform(ya_mcts_tree tree, const uint4* __restrict__ states, in
     Walk w;
     w.node_count = v.meta[M_NODES];
     w.arena_top = v.meta[M_TOP];
-    prune_on_new_round(v, root, w, lane);
+    const Team<32> tm = Team<32>::make();
+    prune_on_new_round(v, root, w, tm);
     int err = 0;
     for (int sim = 0; sim < num_sims; ++sim) {
-        descend<false, false, true>(v, root, w, seed, gid, ep, pl, (uint32_t)sim, cpuct, nullptr, lane);
+        descend<false, false, true>(v, root, w, seed, gid, ep, pl, (uint32_t)sim, cpuct, nullptr, tm);
         if (w.kind == KIND_ERROR) { err = w.err; break; }
         Val ret = w.ret;
         if (w.kind == KIND_NEED_EVAL) {
@@ -877,7 +922,7 @@ ya_k_mcts_search_uniform(ya_mcts_tree tree, const uint4* __restrict__ states, in
             ret.d = -(double)uniform_v;
             ret.is_f32 = true;
         }
-        if (!backup_path(v, w.depth, ret, w.arena_top, lane)) { err = E_ARENA_FULL; break; }
+        if (!backup_path(v, w.depth, ret, w.arena_top, tm)) { err = E_ARENA_FULL; break; }
     }
     if (lane == 0) {
         v.meta[M_NODES] = w.node_count;
@@ -1016,6 +1061,10 @@ __global__ void ya_k_mcts_reset(ya_mcts_tree tree, const uint8_t* __restrict__ w
 }
 
 inline int warp_blocks(int64_t n) { return (int)((n + kWarpsPerBlock - 1) / kWarpsPerBlock); }
+inline int select_blocks(int64_t n) {                                 // 32 / kSelectTeam games per warp
+    const int64_t per_block = kWarpsPerBlock * (32 / kSelectTeam);
+    return (int)((n + per_block - 1) / per_block);
+}
 
 bool tree_ok(const ya_mcts_tree* t) {
     return t && t->n > 0 && t->max_nodes > 0 && t->max_nodes < 65535 && t->ht_size >= 2 * t->max_nodes &&
@@ -1042,11 +1091,11 @@ int ya_mcts_select(const ya_mcts_tree* tree, const uint32_t* states, int64_t str
                    uint32_t* leaf_states, int32_t* err_flag, void* stream) {
     if (!tree_ok(tree) || !(cpuct >= 0.0f)) return (int)cudaErrorInvalidValue;   // group maxima rely on u monotone in P
     if (leaf_states)
-        ya_k_mcts_select<true, false><<<warp_blocks(tree->n), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
+        ya_k_mcts_select<true, false><<<select_blocks(tree->n), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
             *tree, reinterpret_cast<const uint4*>(states), stride, players, ply, episode, seed, game_base, sim, sim_ptr,
             cpuct, active, features, need_eval, leaf_states, err_flag, nullptr, 0);
     else
-        ya_k_mcts_select<false, false><<<warp_blocks(tree->n), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
+        ya_k_mcts_select<false, false><<<select_blocks(tree->n), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
             *tree, reinterpret_cast<const uint4*>(states), stride, players, ply, episode, seed, game_base, sim, sim_ptr,
             cpuct, active, features, need_eval, leaf_states, err_flag, nullptr, 0);
     return (int)cudaGetLastError();
@@ -1056,7 +1105,7 @@ int ya_mcts_select_injected(const ya_mcts_tree* tree, const uint32_t* states, in
                             uint32_t sim, float cpuct, const uint8_t* injected, int resume, float* features,
                             uint8_t* need_eval, uint32_t* leaf_states, int32_t* err_flag, void* stream) {
     if (!tree_ok(tree) || !injected || !leaf_states || !(cpuct >= 0.0f)) return (int)cudaErrorInvalidValue;
-    ya_k_mcts_select<true, true><<<warp_blocks(tree->n), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
+    ya_k_mcts_select<true, true><<<select_blocks(tree->n), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
         *tree, reinterpret_cast<const uint4*>(states), stride, players, nullptr, nullptr, 0, 0, sim, nullptr,
         cpuct, nullptr, features, need_eval, leaf_states, err_flag, injected, resume);
     return (int)cudaGetLastError();
