@@ -389,23 +389,40 @@ __device__ __forceinline__ int ya_transition(YaState& s, int player, int action,
 }
 
 // ------------------------------------------------------------------ features (yacht/NNet.py:50-86)
-// (d - 3.5) / 3.5 evaluated in double then rounded to float, as numpy does for the reference.
+// state_to_vec computes (d - 3.5) / 3.5 and round / 13 in Python doubles and numpy rounds them to float32.  Those
+// are twenty distinct numbers: they are spelled out below as the float32 bit patterns of exactly that computation
+// (float32((d - 3.5) / 3.5) for d = 1..6 is +-{5, 3, 1} / 7; float32(r / 13.0) for r = 0..13), so a feature costs a
+// few selects instead of a double-precision division, and the lanes of a team writing different features of one
+// state do not diverge into a dozen branches.
 __device__ __forceinline__ float ya_die_feature(uint32_t d) {
-    return d ? (float)(((double)d - 3.5) / 3.5) : -1.0f;
+    const int a = abs(2 * (int)d - 7);                                // 5, 3, 1 for d = 1|6, 2|5, 3|4
+    const uint32_t mag = a == 5 ? 0x3F36DB6Eu : (a == 3 ? 0x3EDB6DB7u : 0x3E124925u);
+    const float v = __uint_as_float(mag | (d < 4u ? 0x80000000u : 0u));
+    return d ? v : -1.0f;                                             // empty slot
+}
+
+__device__ __forceinline__ float ya_round_feature(int r) {           // float32(r / 13.0)
+    constexpr uint32_t k[16] = {0x00000000u, 0x3D9D89D9u, 0x3E1D89D9u, 0x3E6C4EC5u, 0x3E9D89D9u, 0x3EC4EC4Fu, 0x3EEC4EC5u, 0x3F09D89Eu,
+                                0x3F1D89D9u, 0x3F313B14u, 0x3F44EC4Fu, 0x3F589D8Au, 0x3F6C4EC5u, 0x3F800000u, 0x3F800000u, 0x3F800000u};
+    uint32_t bits = 0;
+#pragma unroll
+    for (int i = 0; i < 14; ++i) bits = r == i ? k[i] : bits;
+    return __uint_as_float(bits);
 }
 
 __device__ __forceinline__ float ya_feature(const YaState& s, int f) {
-    if (f == 0) return (float)((double)ya_round(s) / 13.0);
-    if (f == 1) return ya_phase(s) == 0 ? 1.0f : 0.0f;
-    if (f == 2) return ya_phase(s) == 1 ? 1.0f : 0.0f;
-    if (f < 13) return ya_die_feature((s.w[2] >> (3 * (f - 3))) & 7u);
-    if (f < 23) return ya_die_feature((s.w[3] >> (3 * (f - 13))) & 7u);
-    if (f < 33) {
-        if (!ya_bidding(s)) return -1.0f;
-        return ya_die_feature((s.w[1] >> (3 * (f - 23))) & 7u);
-    }
-    if (f < 45) return (float)((s.w[4] >> (f - 33)) & 1u);
-    if (f < 57) return (float)((s.w[6] >> (f - 45)) & 1u);
-    int bank = ya_bank(f == 57 ? s.w[4] : s.w[6]) * 500;
-    return (float)((double)bank * 1e-5);
+    // dice features 3..32: ten dice of each carry, then the five dice of each open bundle (bidding phases only)
+    const bool pool = f >= 23;
+    const uint32_t dice_word = f < 13 ? s.w[2] : (pool ? s.w[1] : s.w[3]);
+    const int dice_idx = f < 13 ? f - 3 : (pool ? f - 23 : f - 13);
+    uint32_t d = (dice_word >> (3 * (dice_idx & 15))) & 7u;
+    if (pool && !ya_bidding(s)) d = 0u;
+    const float die = ya_die_feature(d);
+    // used-category bits 33..56
+    const uint32_t used_word = f < 45 ? s.w[4] : s.w[6];
+    const float bit = (float)((used_word >> ((f < 45 ? f - 33 : f - 45) & 15)) & 1u);
+    float out = f < 33 ? die : bit;
+    if (f >= 57) out = (float)((double)(ya_bank(f == 57 ? s.w[4] : s.w[6]) * 500) * 1e-5);
+    if (f < 3) out = f == 0 ? ya_round_feature(ya_round(s)) : (ya_phase(s) == f - 1 ? 1.0f : 0.0f);
+    return out;
 }
