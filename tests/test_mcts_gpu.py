@@ -533,3 +533,32 @@ def test_full_size_mcts_properties():
         assert int(mcts.pool.node_counts().max().item()) <= mcts.pool.max_nodes
         del mcts, ref, env, small
         torch.cuda.empty_cache()
+
+
+def test_expand_falls_back_to_uniform_when_every_legal_move_underflows():
+    """MCTS.py:92-101: if the masked policy sums to 0 (here: softmax underflows on every legal move because an
+    illegal move carries all the mass), the reference falls back to Ps = valids / sum(valids)."""
+    from nypc_yacht_auction_b200.mcts import BatchedMCTS
+
+    class Underflow:
+        uniform = False
+        returns_logits = True
+
+        def __init__(self, n):
+            self.logits = torch.zeros((n, 3232), dtype=torch.bfloat16, device="cuda")
+            self.logits[:, :202] = -200.0                    # every bid far below the (illegal) score moves
+            self.v = torch.zeros(n, device="cuda")
+
+        def __call__(self, features, need_eval, leaf_states):
+            return self.logits, self.v
+
+    n = 5
+    env = _engine(n, 2, 9)                                   # ply 0: bid rows, 202 legal moves
+    mcts = BatchedMCTS(env, 4, 1.5, evaluator=Underflow(n))
+    mcts.simulate(0)
+    mcts.check_errors()
+    arena = mcts.pool.arena.cpu().numpy().view(np.float32)
+    nodes = mcts.pool.nodes.cpu().numpy()
+    for g in range(n):
+        off = int(nodes[g, 0, 10])
+        assert (arena[g, off:off + 202] == np.float32(1.0) / np.float32(202)).all()
