@@ -36,9 +36,10 @@ class TreePool:
         assert self.max_nodes < 65535
         self.ht_size = _next_pow2(2 * self.max_nodes)
         if arena_mb_per_game is None:
-            # measured peak (random-init net, 100 sims): 33 KB per simulation of the longest-lived tree
-            # (rounds 1+2); 40 KB/sim leaves ~20 % head-room, overflow is detected and raised.
-            arena_mb_per_game = max(num_sims * 40.0 / 1024.0, 0.25)
+            # measured peak (random-init net, 100 sims, profiles/tools/arena_peak.py): 39 KB per simulation of the
+            # longest-lived tree (rounds 1+2: six plies without pruning); 48 KB/sim leaves ~20 % head-room,
+            # overflow is detected and raised.
+            arena_mb_per_game = max(num_sims * 48.0 / 1024.0, 0.25)
         words = int(arena_mb_per_game * 2 ** 20) // 4
         self.arena_words = words - (words % 4)
         d = self.device
