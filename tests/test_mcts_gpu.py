@@ -562,3 +562,28 @@ def test_expand_falls_back_to_uniform_when_every_legal_move_underflows():
     for g in range(n):
         off = int(nodes[g, 0, 10])
         assert (arena[g, off:off + 202] == np.float32(1.0) / np.float32(202)).all()
+
+
+@pytest.mark.parametrize("nblocks", [1, 3])
+def test_whole_forward_kernel_other_depths(nblocks):
+    """The forward kernel loops over the residual blocks it is given: shallower trunks against the float32 module."""
+    from nypc_yacht_auction_b200.mcts import FusedYachtEvaluator
+    from nypc_yacht_auction_b200.nnet import YachtPolicyValueNet
+    torch.manual_seed(10 + nblocks)
+    net = YachtPolicyValueNet(nblocks=nblocks).cuda().eval()
+    with torch.no_grad():
+        for p in net.parameters():
+            if p.ndim == 1:
+                p.add_(0.1 * torch.randn_like(p))
+    env = _engine(300, 4, 4)
+    for _ in range(9):
+        env.play_ply(masks=None, auto_reset=False)
+    x = env.features()
+    ev = FusedYachtEvaluator(net, 300)
+    assert ev.whole_forward and ev.nblocks == nblocks
+    logits, values = ev(x)
+    with torch.no_grad():
+        ref_logits, ref_v = net(x)
+    tv = 0.5 * (torch.softmax(logits[:, :3226].float(), 1) - torch.softmax(ref_logits, 1)).abs().sum(1).max().item()
+    assert (logits[:, :3226].float() - ref_logits).abs().max().item() < 0.15 and tv < 0.02
+    assert (values - ref_v.reshape(-1)).abs().max().item() < 0.05
