@@ -37,7 +37,7 @@ enum { N_KEY = 0, N_DESC = 8, N_VISITS = 9, N_PRIOR = 10, N_EDGES = 11, N_NEDGE 
 // N_KIND 0: N_PRIOR -> float32 prior row + group maxima.  N_KIND 1 (uniform evaluator): every legal move has the SAME prior
 // (bits in N_PCONST), so N_PRIOR -> just a visited bitmask of ceil(L / 32) words: 0.4 KB instead of 12 KB per node.
 // cursor words
-enum { C_LEAF = 0, C_DEPTH = 8, C_KIND = 9, C_NODE = 10, C_PENDING = 11, C_PATH = 12 };
+enum { C_LEAF = 0, C_DEPTH = 8, C_KIND = 9, C_NODE = 10, C_PENDING = 11, C_PATH = 12, C_LEAF_DESC = 28, C_LEAF_ROW = 29 };   // C_PATH: kMaxDepth words
 enum { KIND_DONE = 0, KIND_NEED_EVAL = 1, KIND_ERROR = 2, KIND_NEED_DRAW = 3 };
 // meta words
 enum { M_NODES = 0, M_TOP = 1, M_ROUND = 2 };
@@ -386,6 +386,7 @@ __device__ __forceinline__ bool backup_path(const View& v, int depth, Val ret, u
 struct Walk {
     uint32_t node_count, arena_top, pending;
     int depth, kind, err, leaf_node;
+    uint32_t leaf_desc, leaf_row;        // mask descriptor and prior-row offset of the new leaf (for the expand kernel)
     Val ret;
     YaState leaf;
 };
@@ -463,6 +464,8 @@ __device__ __forceinline__ void descend(const View& v, YaState cur, Walk& w, uin
                 if (FEATURES)
                     for (int f = lane; f < YA_N_FEATURE; f += W) feat_row[f] = ya_feature(cur, f);
                 w.leaf_node = idx;
+                w.leaf_desc = desc;
+                w.leaf_row = row_at;
                 w.kind = KIND_NEED_EVAL;
                 tm.sync();
                 break;
@@ -539,6 +542,7 @@ ya_k_mcts_select(ya_mcts_tree tree, const uint4* __restrict__ states, int64_t st
         v.cur[C_DEPTH] = (uint32_t)w.depth;
         v.cur[C_KIND] = (uint32_t)w.kind;
         v.cur[C_NODE] = (uint32_t)w.leaf_node;
+        if (w.kind == KIND_NEED_EVAL) { v.cur[C_LEAF_DESC] = w.leaf_desc; v.cur[C_LEAF_ROW] = w.leaf_row; }
         uint8_t code = w.kind == KIND_NEED_EVAL ? 1 : 0;
         if (INJECT && w.kind == KIND_NEED_DRAW) {                    // park the descent; tell the host what to draw
             v.cur[C_PENDING] = w.pending;
@@ -713,8 +717,8 @@ ya_k_mcts_expand_logits(ya_mcts_tree tree, const __nv_bfloat16* __restrict__ log
     if (g >= tree.n) return;
     View v = make_view(tree, g);
     if (v.cur[C_KIND] != KIND_NEED_EVAL) return;
-    uint32_t* node = v.nodes + (int64_t)v.cur[C_NODE] * kNodeWords;
-    const uint32_t desc = node[N_DESC];
+    const uint32_t desc = v.cur[C_LEAF_DESC];                          // left by the descent next to the path: the leaf's
+    const uint32_t leaf_row = v.cur[C_LEAF_ROW];                       // node record is not needed before the logits load
     const int L = ya_legal_count(desc);
     if (L > 0) {
         const uint32_t* lg = reinterpret_cast<const uint32_t*>(logits_all + g * ld);   // two logits per word (ld is even)
@@ -808,7 +812,7 @@ ya_k_mcts_expand_logits(ya_mcts_tree tree, const __nv_bfloat16* __restrict__ log
         }
 #pragma unroll
         for (int o = 16; o; o >>= 1) total += __shfl_xor_sync(0xFFFFFFFFu, total, o);
-        float* row = reinterpret_cast<float*>(v.arena + node[N_PRIOR]);
+        float* row = reinterpret_cast<float*>(v.arena + leaf_row);
         if (total > 0.0f) {
             const float off_p = off_sum - __log2f(total);
             if (quads) {
