@@ -7,11 +7,12 @@ from nypc_yacht_auction_b200.coach import BatchedSelfPlay
 from nypc_yacht_auction_b200.mcts import FusedYachtEvaluator, UniformEvaluator
 from nypc_yacht_auction_b200.nnet import YachtPolicyValueNet
 dev = torch.device('cuda', 0)
-n = int(sys.argv[1]); sims = int(sys.argv[2]); uniform = len(sys.argv) > 3
+n = int(sys.argv[1]); sims = int(sys.argv[2]); uniform = len(sys.argv) > 3 and sys.argv[3] == "uniform"
+arena_mb = float(sys.argv[4]) if len(sys.argv) > 4 else None
 torch.manual_seed(0)
 net = YachtPolicyValueNet().to(dev)
 ev = UniformEvaluator() if uniform else FusedYachtEvaluator(net, n)
-sp = BatchedSelfPlay(n, sims, evaluator=ev, seed=2, device=dev, record_examples=False)
+sp = BatchedSelfPlay(n, sims, evaluator=ev, seed=2, device=dev, record_examples=False, arena_mb_per_game=arena_mb)
 m = sp.mcts; env = sp.env; lib = m.lib; grp = m.groups[0]
 def pair():
     return torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
