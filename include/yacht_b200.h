@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define YA_ABI_VERSION 1
+#define YA_ABI_VERSION 2
 #define YA_ACTION_SIZE 3226
 #define YA_FEATURE_SIZE 59
 #define YA_SCORE_TABLE_SIZE 3024
@@ -130,13 +130,15 @@ int ya_mcts_reset(const ya_mcts_tree* tree, const uint8_t* which, void* stream);
  * state_to_vec row in features[g][59] and (optionally) their packed state in leaf_states; all other
  * paths (terminal, dead end) are backed up inside this call.  err_flag bits: 0x100 node pool full,
  * 0x200 arena full, 0x400 path deeper than 16, 0x800 | (1 << status) rule error.  If sim_ptr (device)
- * is not NULL the simulation index is read from it, so one captured CUDA graph can be replayed.
+ * is not NULL the simulation index is read from it, and if game_base_ptr (device) is not NULL the global id of game 0
+ * is read from it instead of `game_base`, so one captured CUDA graph can be replayed for every simulation and for
+ * every wave of games that shares the pool (a captured launch freezes its by-value arguments).
  * cpuct must be >= 0 (main.py:25 uses 1.5): the unvisited arg-max goes through per-group maxima of the priors,
  * which needs cpuct * P * sqrt(Ns + EPS) to be monotone in P; a negative value is rejected (invalid value). */
 int ya_mcts_select(const ya_mcts_tree* tree, const uint32_t* states, int64_t stride, const int8_t* players,
                    const int32_t* ply, const uint32_t* episode, uint64_t seed, uint64_t game_base, uint32_t sim,
-                   const uint32_t* sim_ptr, float cpuct, const uint8_t* active, float* features, uint8_t* need_eval,
-                   uint32_t* leaf_states, int32_t* err_flag, void* stream);
+                   const uint32_t* sim_ptr, const uint64_t* game_base_ptr, float cpuct, const uint8_t* active,
+                   float* features, uint8_t* need_eval, uint32_t* leaf_states, int32_t* err_flag, void* stream);
 
 /* The same descent with the dice of in-search transitions supplied by the HOST (the reference rolls them
  * from the global numpy / random streams through roll_five / tiebreak_uniform, yacht/YachtGame.py:154-159,
@@ -155,13 +157,13 @@ int ya_mcts_select_injected(const ya_mcts_tree* tree, const uint32_t* states, in
 int ya_mcts_expand(const ya_mcts_tree* tree, const float* pi, const float* value, int uniform, float uniform_p,
                    float uniform_v, uint32_t* sim_counter, int32_t* err_flag, void* stream);
 
-/* Same as ya_mcts_expand, fed with the raw policy-head output: bf16 logits [n][ld] (ld >= 3232 and a multiple of 8,
- * e.g. the head padded to 3232 columns; base 16-byte aligned).  The softmax of NNetWrapper.predict
+/* Same as ya_mcts_expand, fed with the raw policy-head output: 16-bit logits [n][ld] (IEEE half if fp16 != 0, else
+ * bfloat16; ld >= 3232 and a multiple of 8, e.g. the head padded to 3232 columns; base 16-byte aligned).  The softmax of NNetWrapper.predict
  * (yacht/NNet.py:193), masking and renormalisation (MCTS.py:88-101) are fused:
  * P[a] = exp(l[a] - max) / sum over legal a' of exp(l[a'] - max), float32, max taken over all 3,226 logits;
  * only the legal logits are read, neither float32 logits nor pi are ever written to HBM.
  * row_max float32[n] = that per-row maximum (written by ya_nn_forward), or NULL: the kernel scans the row. */
-int ya_mcts_expand_logits(const ya_mcts_tree* tree, const void* logits_bf16, int64_t ld, const float* row_max,
+int ya_mcts_expand_logits(const ya_mcts_tree* tree, const void* logits16, int fp16, int64_t ld, const float* row_max,
                           const float* value, uint32_t* sim_counter, int32_t* err_flag, void* stream);
 
 /* getActionProb's whole simulation loop (MCTS.py:37-38) in ONE launch for the uniform evaluator
@@ -192,34 +194,21 @@ int ya_mcts_root_sparse(const ya_mcts_tree* tree, const uint32_t* states, int64_
 int ya_mcts_pick_action(const int32_t* counts, const int32_t* ply, const uint32_t* episode, int64_t n, uint64_t seed,
                         uint64_t game_base, int temp_threshold, int32_t* actions, void* stream);
 
-/* ---- leaf-evaluator epilogues (YachtNNet.forward, yacht/pytorch/YachtNNet.py:17-21,62-70) ----
- * Everything between two GEMMs of the yacht NNet in one pass over bf16 [n][256] rows:
- * mode 0: out = SiLU(LN(x)); 1: out = LN(SiLU(x)); 2: out = residual + LN(SiLU(x));
- * 3: out = SiLU(LN(x; gamma, beta)), out2 = SiLU(LN(x; gamma2, beta2)) (both heads).  hidden must be 256. */
-int ya_nn_ln_act(int mode, const void* x, const void* gamma, const void* beta, const void* residual,
-                 const void* gamma2, const void* beta2, void* out, void* out2, int64_t n, int64_t hidden,
-                 float eps, void* stream);
-
-/* The residual trunk of YachtNNet (yacht/pytorch/YachtNNet.py:8-21,64-66) as one persistent tcgen05 kernel:
- * x, out: bf16 [n][256]; weight_images: `layers` x 128 KB, each the [256 out][256 in] bf16 weight of a
- * Linear in the 128-byte-swizzled K-major image the tensor core reads (4 K-blocks of [256][64]; the 16-byte
- * chunk c of row r is stored at chunk c ^ (r & 7)); params: float32 [layers][3][256] = bias, LayerNorm
- * gamma, beta; kinds[l] = 1: act = LN(SiLU(act W^T + b)), 2: act = skip + LN(SiLU(act W^T + b)), skip = act
- * (skip starts as x).  Activations stay in shared memory, the skip connection in TMEM. */
-int ya_nn_trunk(const void* x, void* out, const void* weight_images, const float* params, const int32_t* kinds,
-                int layers, int64_t n, int64_t hidden, float eps, void* stream);
-
+/* ---- leaf evaluator (YachtNNet.forward, yacht/pytorch/YachtNNet.py:62-70) ---- */
 /* The whole YachtNNet.forward (yacht/pytorch/YachtNNet.py:62-70) for a wave of leaves as one persistent
- * tcgen05 kernel: features float32 [n][59] (state_to_vec rows) -> logits bf16 [n][3232] (columns >= 3226 are
- * padding) and values float32 [n] (tanh).  weight_blob / param_blob are built once on the host
+ * tcgen05 kernel: features float32 [n][59] (state_to_vec rows) -> 16-bit logits [n][3232] (columns >= 3226 are
+ * padding) and values float32 [n] (tanh).  fp16 != 0: operands (activations, weight images) and logits are IEEE half,
+ * the precision of the reference's CUDA predict (fp16 autocast, yacht/NNet.py:186-193); fp16 == 0: bfloat16.
+ * Accumulation, LayerNorm statistics and the skip connection are float32 in both modes.  weight_blob / param_blob are built once on the host
  * (mcts.FusedYachtEvaluator): 128-byte-swizzled K-major images of W_in (K padded to 64), the 2*nblocks trunk
  * weights, the value head's first Linear and 26 policy-head tiles of 128 columns; biases and LayerNorm
  * parameters as float32.  offsets (HOST pointer, int64[9]) = byte offsets {w_in, w_trunk, w_v, w_pi} and float
  * offsets {p_in, p_trunk, p_v, p_pi_ln, p_pi_bias}.  hidden width 256 only.  Rows are independent of the
  * batch they sit in (batch-invariant evaluator).  row_max float32[n] (may be NULL) receives each row's largest
  * logit over the 3,226 real columns, for ya_mcts_expand_logits. */
-int ya_nn_forward(const float* features, void* logits_bf16, float* values, float* row_max, const void* weight_blob,
-                  const float* param_blob, const int64_t* offsets, int nblocks, int64_t n, float eps, void* stream);
+int ya_nn_forward(const float* features, void* logits16, float* values, float* row_max, const void* weight_blob,
+                  const float* param_blob, const int64_t* offsets, int nblocks, int64_t n, float eps, int fp16,
+                  void* stream);
 
 /* ---- host-buffer variants (end-to-end path for callers that keep boards in host memory) ----
  * ya_host_create allocates the device mirror for n games once (no allocation per call);

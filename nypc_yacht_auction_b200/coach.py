@@ -69,7 +69,8 @@ class BatchedSelfPlay:
             self.ex_actions = torch.zeros((self.PLIES, n, self.k), dtype=torch.int16, device=d)
             self.ex_counts = torch.zeros((self.PLIES, n, self.k), dtype=torch.int32, device=d)
             self.ex_players = torch.zeros((self.PLIES, n), dtype=torch.int8, device=d)
-            self.ex_overflow = torch.zeros(n, dtype=torch.int32, device=d)
+            self.ex_overflow = torch.zeros(n, dtype=torch.int32, device=d)       # per ply (rewritten by every root_sparse)
+            self.ex_overflow_max = torch.zeros(n, dtype=torch.int32, device=d)   # largest edge count that did not fit k, per game
             if self.record_states:
                 self.ex_states = torch.zeros((self.PLIES, 2, n, 4), dtype=torch.int32, device=d)
 
@@ -85,6 +86,7 @@ class BatchedSelfPlay:
         m.root_counts()
         if self.record:                                              # the visited root edges, sorted by action
             m.root_sparse(self.ex_actions[t], self.ex_counts[t], self.ex_overflow)
+            torch.maximum(self.ex_overflow_max, self.ex_overflow, out=self.ex_overflow_max)
         actions = m.pick_actions()
         env.next_state(actions, check=False)
         return actions
@@ -92,9 +94,18 @@ class BatchedSelfPlay:
     def execute_episodes(self):
         """One full episode for every game.  Returns dict(features[T,n,59], actions[T,n,k], counts[T,n,k],
         value[T,n]) with value = +-1 / 1e-4 from the mover's view (Coach.py:69-72)."""
+        if self.record:
+            self.ex_overflow_max.zero_()
         for t in range(self.PLIES):
             self.play_ply(t)
         self.mcts.check_errors()
+        if self.record:
+            # a root keeps the edges earlier searches of the same round visited, so it can hold more than numMCTSSims of
+            # them; a pi target cut to the k lowest actions would be silently wrong -> refuse it
+            worst = int(self.ex_overflow_max.max().item())
+            if worst:
+                raise ValueError("a root had %d visited edges but the example buffers hold max_edges=%d per ply: "
+                                 "construct BatchedSelfPlay with a larger max_edges" % (worst, self.k))
         env = self.env
         ones = torch.ones_like(env.players)
         result_p1 = env.game_ended(players=ones)                     # from player 1's view
@@ -193,7 +204,8 @@ def self_play_in_waves(total_games, wave_games, num_sims, evaluator, first_game=
     for w in range(total_games // wave_games):
         if w:
             base = first_game + w * wave_games
-            sp.env.game_base = base                              # same pool, next slice of global game ids
+            sp.env.game_base = base                              # same pool, next slice of global game ids (the captured
+                                                                 # graph reads them from device memory: mcts.sync_game_base)
             sp.mcts.pool.reset()
             sp.env.episode.zero_()
             sp.env.reset()

@@ -6,6 +6,8 @@
 // stream it is given and returns a cudaError_t as int.  No allocation, no host sync.
 #include "ya_common.cuh"
 #include "../../include/yacht_b200.h"
+#include <atomic>
+#include <mutex>
 
 namespace {
 
@@ -265,18 +267,27 @@ __global__ void ya_k_build_score_table() {
     g_score_table[0][slot] = w[0]; g_score_table[1][slot] = w[1]; g_score_table[2][slot] = w[2];
 }
 
+// The table is per device (a __device__ array).  Thread-safe and stream-safe: the first caller on a device builds it
+// under a mutex and waits for the build, so every later launch -- on any stream, from any thread -- finds it complete.
+// ya_set_device builds it eagerly, which keeps the wait out of CUDA-graph captures.
 int ya_ensure_score_table(cudaStream_t stream) {
-    static bool built[64] = {};
+    static std::atomic<bool> built[64];
+    static std::mutex mu;
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return (int)e;
     if (dev < 0 || dev >= 64) return (int)cudaErrorInvalidDevice;
-    if (!built[dev]) {
-        ya_k_build_score_table<<<(7776 + 255) / 256, 256, 0, stream>>>();   // stream-ordered before its first user
-        e = cudaGetLastError();
-        if (e != cudaSuccess) return (int)e;
-        built[dev] = true;
-    }
+    if (built[dev].load(std::memory_order_acquire)) return 0;
+    std::lock_guard<std::mutex> lock(mu);
+    if (built[dev].load(std::memory_order_relaxed)) return 0;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(stream, &cap) != cudaSuccess) return (int)cudaGetLastError();
+    if (cap != cudaStreamCaptureStatusNone) return (int)cudaErrorStreamCaptureUnsupported;   // call ya_set_device first
+    ya_k_build_score_table<<<(7776 + 255) / 256, 256, 0, stream>>>();
+    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) return (int)e;
+    built[dev].store(true, std::memory_order_release);
     return 0;
 }
 
@@ -620,7 +631,11 @@ extern "C" {
 
 int ya_abi_version(void) { return YA_ABI_VERSION; }
 
-int ya_set_device(int device) { return (int)cudaSetDevice(device); }
+int ya_set_device(int device) {
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) return (int)e;
+    return ya_ensure_score_table(cudaStreamPerThread);
+}
 
 int ya_init_states(uint32_t* states, int64_t stride, int8_t* players, int32_t* ply, const uint32_t* episode,
                    int64_t n, uint64_t seed, uint64_t game_base, void* stream) {

@@ -19,6 +19,7 @@
 // -DYA_FWD_TIMELINE builds the profiling variant used by profiles/tools/forward_timeline.py.
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <atomic>
 #include <cstdint>
 #include "../../include/yacht_b200.h"
 #include "ya_tc.cuh"
@@ -57,21 +58,23 @@ __device__ __forceinline__ uint32_t a_tile_offset(int r, int c8) {
     return (uint32_t)(kb * (kRows * 128) + r * 128 + ((chunk ^ (r & 7)) << 4));
 }
 
+template <bool F16>
 __device__ __forceinline__ void pack_store_a(uint8_t* a_tile, int row, int c8_first, const uint32_t (&r)[32]) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         uint32_t p[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(r[q * 8 + 2 * i]), __uint_as_float(r[q * 8 + 2 * i + 1]));
-            p[i] = *reinterpret_cast<uint32_t*>(&h);
-        }
+        for (int i = 0; i < 4; ++i) p[i] = pack2<F16>(__uint_as_float(r[q * 8 + 2 * i]), __uint_as_float(r[q * 8 + 2 * i + 1]));
         *reinterpret_cast<uint4*>(a_tile + a_tile_offset(row, c8_first + q)) = make_uint4(p[0], p[1], p[2], p[3]);
     }
 }
 
+// F16: operands (activations, weights) and logits in IEEE half -- the precision of the reference's CUDA predict (fp16
+// autocast, yacht/NNet.py:186-193) -- instead of bfloat16; accumulation, LayerNorm and the skip connection are float32
+// either way.  tcgen05.mma kind::f16 runs both formats at the same rate.
+template <bool F16>
 __global__ void __launch_bounds__(kThreads, 1)
-ya_k_forward(const float* __restrict__ features, __nv_bfloat16* __restrict__ logits, float* __restrict__ values,
+ya_k_forward(const float* __restrict__ features, uint16_t* __restrict__ logits, float* __restrict__ values,
              float* __restrict__ row_max, const uint8_t* __restrict__ wblob, const float* __restrict__ pblob, Blob off, int nblocks, int64_t n, float eps) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -140,7 +143,7 @@ ya_k_forward(const float* __restrict__ features, __nv_bfloat16* __restrict__ log
         if (producer) {
             tc_fence_after();
             const uint64_t da = umma_desc(smem_u32(a_tile)), db = umma_desc(smem_u32(w_src));
-            const uint32_t idesc = umma_idesc(n_cols);
+            const uint32_t idesc = umma_idesc(n_cols, F16);
             if (elect_one()) {
                 for (int kb = 0; kb < n_kb; ++kb)
 #pragma unroll
@@ -184,10 +187,7 @@ ya_k_forward(const float* __restrict__ features, __nv_bfloat16* __restrict__ log
         for (int q = 0; q < 2; ++q) {
             uint32_t p[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(f[q * 8 + 2 * i]), __uint_as_float(f[q * 8 + 2 * i + 1]));
-                p[i] = *reinterpret_cast<uint32_t*>(&h);
-            }
+            for (int i = 0; i < 4; ++i) p[i] = pack2<F16>(__uint_as_float(f[q * 8 + 2 * i]), __uint_as_float(f[q * 8 + 2 * i + 1]));
             *reinterpret_cast<uint4*>(a_tile + a_tile_offset(row, part * 2 + q)) = make_uint4(p[0], p[1], p[2], p[3]);
         }
     }
@@ -227,7 +227,7 @@ ya_k_forward(const float* __restrict__ features, __nv_bfloat16* __restrict__ log
                 r[i] = __float_as_uint(silu_from_half(0.5f * y));
             }
             tmem_st32(t_skip + colv[c], r);
-            pack_store_a(a_tile, row, colv[c] / 8, r);
+            pack_store_a<F16>(a_tile, row, colv[c] / 8, r);
         }
         tmem_st_wait();
     }
@@ -250,7 +250,7 @@ ya_k_forward(const float* __restrict__ features, __nv_bfloat16* __restrict__ log
         if (producer) {
             tc_fence_after();
             const uint64_t da = umma_desc(smem_u32(a_tile)), db = umma_desc(smem_u32(w_tile));
-            const uint32_t idesc = umma_idesc(128);
+            const uint32_t idesc = umma_idesc(128, F16);
             if (elect_one()) {
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
@@ -317,22 +317,22 @@ ya_k_forward(const float* __restrict__ features, __nv_bfloat16* __restrict__ log
             for (int i = 0; i < 32; ++i)
                 v0[i] = __float_as_uint(fmaf(fmaf(__uint_as_float(v0[i]), rstd, nm), gamma[colv[0] + i], beta[colv[0] + i]) + __uint_as_float(sk[i]));
             tmem_st32(t_skip + colv[0], v0);
-            pack_store_a(a_tile, row, colv[0] / 8, v0);
+            pack_store_a<F16>(a_tile, row, colv[0] / 8, v0);
             tmem_ld32(t_skip + colv[1], sk);
             tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < 32; ++i)
                 v1[i] = __float_as_uint(fmaf(fmaf(__uint_as_float(v1[i]), rstd, nm), gamma[colv[1] + i], beta[colv[1] + i]) + __uint_as_float(sk[i]));
             tmem_st32(t_skip + colv[1], v1);
-            pack_store_a(a_tile, row, colv[1] / 8, v1);
+            pack_store_a<F16>(a_tile, row, colv[1] / 8, v1);
             tmem_st_wait();
         } else {
 #pragma unroll
             for (int i = 0; i < 32; ++i) v0[i] = __float_as_uint(fmaf(fmaf(__uint_as_float(v0[i]), rstd, nm), gamma[colv[0] + i], beta[colv[0] + i]));
-            pack_store_a(a_tile, row, colv[0] / 8, v0);
+            pack_store_a<F16>(a_tile, row, colv[0] / 8, v0);
 #pragma unroll
             for (int i = 0; i < 32; ++i) v1[i] = __float_as_uint(fmaf(fmaf(__uint_as_float(v1[i]), rstd, nm), gamma[colv[1] + i], beta[colv[1] + i]));
-            pack_store_a(a_tile, row, colv[1] / 8, v1);
+            pack_store_a<F16>(a_tile, row, colv[1] / 8, v1);
         }
     }
 
@@ -364,13 +364,10 @@ ya_k_forward(const float* __restrict__ features, __nv_bfloat16* __restrict__ log
                 a[i] = __float_as_uint(silu_from_half(0.5f * fmaf(x, gv[colv[c] + i], bv[colv[c] + i])));
                 r[i] = __float_as_uint(silu_from_half(0.5f * fmaf(x, gp[colv[c] + i], bp[colv[c] + i])));
             }
-            pack_store_a(a_tile, row, colv[c] / 8, a);
+            pack_store_a<F16>(a_tile, row, colv[c] / 8, a);
             uint32_t pk[16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
-                pk[i] = *reinterpret_cast<uint32_t*>(&h);
-            }
+            for (int i = 0; i < 16; ++i) pk[i] = pack2<F16>(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
             tmem_st16(t_lane + (uint32_t)(colv[c] / 2), pk);           // K elements colv[c].. = packed columns colv[c] / 2..
         }
         tmem_st_wait();
@@ -436,7 +433,7 @@ ya_k_forward(const float* __restrict__ features, __nv_bfloat16* __restrict__ log
         };
         auto issue_tile = [&](int j) {                                // producer thread: tile j's 16 MMAs
             const uint64_t db = umma_desc(smem_u32(base + policy_slot(j) * 65536));
-            const uint32_t idesc = umma_idesc(kPolicyTile);
+            const uint32_t idesc = umma_idesc(kPolicyTile, F16);
 #pragma unroll
             for (int kb = 0; kb < 4; ++kb)
 #pragma unroll
@@ -503,11 +500,8 @@ ya_k_forward(const float* __restrict__ features, __nv_bfloat16* __restrict__ log
                         if (grow < n) {
                             uint32_t p[16];
 #pragma unroll
-                            for (int i = 0; i < 16; ++i) {
-                                __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
-                                p[i] = *reinterpret_cast<uint32_t*>(&h);
-                            }
-                            __nv_bfloat16* dst = logits + grow * kPolicyCols + col0;    // 64 bytes, 32-byte aligned
+                            for (int i = 0; i < 16; ++i) p[i] = pack2<F16>(f[2 * i], f[2 * i + 1]);
+                            uint16_t* dst = logits + grow * kPolicyCols + col0;         // 64 bytes, 32-byte aligned
 #pragma unroll
                             for (int h2 = 0; h2 < 2; ++h2)            // 256-bit stores: half the LSU work of 4 x 16 bytes
                                 asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + 16 * h2),
@@ -520,11 +514,11 @@ ya_k_forward(const float* __restrict__ features, __nv_bfloat16* __restrict__ log
             for (int q = 0; q < n_my; ++q) xchg[(part + q) * kRows + row].x = row_mx[q];
         }
         YA_STAMP();
-        // the row's largest logit as the expand kernel will see it (bf16 rounding is monotone)
+        // the row's largest logit as the expand kernel will see it (rounding to 16 bits is monotone)
         __syncthreads();
         if (part == 0 && grow < n && row_max) {
             float m = fmaxf(fmaxf(row_mx[0], xchg[1 * kRows + row].x), fmaxf(xchg[2 * kRows + row].x, xchg[3 * kRows + row].x));
-            row_max[grow] = __bfloat162float(__float2bfloat16_rn(m));
+            row_max[grow] = round16<F16>(m);
         }
     }
     tc_fence_before();
@@ -540,21 +534,34 @@ extern "C" int ya_debug_forward_timeline(unsigned long long* host_out) {
 }
 #endif
 
-extern "C" int ya_nn_forward(const float* features, void* logits_bf16, float* values, float* row_max, const void* weight_blob,
-                             const float* param_blob, const int64_t* offsets, int nblocks, int64_t n, float eps, void* stream) {
+extern "C" int ya_nn_forward(const float* features, void* logits16, float* values, float* row_max, const void* weight_blob,
+                             const float* param_blob, const int64_t* offsets, int nblocks, int64_t n, float eps, int fp16,
+                             void* stream) {
     if (n <= 0) return 0;
-    if ((reinterpret_cast<uintptr_t>(logits_bf16) | reinterpret_cast<uintptr_t>(weight_blob) |
+    if ((reinterpret_cast<uintptr_t>(logits16) | reinterpret_cast<uintptr_t>(weight_blob) |
          reinterpret_cast<uintptr_t>(param_blob)) & 31u) return (int)cudaErrorMisalignedAddress;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(ya_k_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    // the opt-in to > 48 KB of dynamic shared memory is a per-DEVICE function attribute: one flag per device and
+    // kernel variant (set twice by racing threads is harmless; the flag is only published after the call succeeded)
+    static std::atomic<bool> configured[2][64];
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return (int)e;
+    if (dev < 0 || dev >= 64) return (int)cudaErrorInvalidDevice;
+    if (!configured[fp16 ? 1 : 0][dev].load(std::memory_order_acquire)) {
+        e = fp16 ? cudaFuncSetAttribute(ya_k_forward<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes)
+                 : cudaFuncSetAttribute(ya_k_forward<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
         if (e != cudaSuccess) return (int)e;
-        configured = true;
+        configured[fp16 ? 1 : 0][dev].store(true, std::memory_order_release);
     }
     Blob off{offsets[0], offsets[1], offsets[2], offsets[3], offsets[4], offsets[5], offsets[6], offsets[7], offsets[8]};
     int blocks = (int)((n + kRows - 1) / kRows);
-    ya_k_forward<<<blocks, kThreads, kSmemBytes, (cudaStream_t)stream>>>(
-        features, static_cast<__nv_bfloat16*>(logits_bf16), values, row_max, static_cast<const uint8_t*>(weight_blob), param_blob, off,
-        nblocks, n, eps);
+    if (fp16)
+        ya_k_forward<true><<<blocks, kThreads, kSmemBytes, (cudaStream_t)stream>>>(
+            features, static_cast<uint16_t*>(logits16), values, row_max, static_cast<const uint8_t*>(weight_blob), param_blob, off,
+            nblocks, n, eps);
+    else
+        ya_k_forward<false><<<blocks, kThreads, kSmemBytes, (cudaStream_t)stream>>>(
+            features, static_cast<uint16_t*>(logits16), values, row_max, static_cast<const uint8_t*>(weight_blob), param_blob, off,
+            nblocks, n, eps);
     return (int)cudaGetLastError();
 }

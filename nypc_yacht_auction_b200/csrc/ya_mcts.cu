@@ -16,6 +16,7 @@
 #include "../../include/yacht_b200.h"
 #include <math_constants.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 namespace {
 
@@ -513,12 +514,13 @@ template <bool WRITE_LEAF_STATE, bool INJECT>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, YA_MCTS_MIN_BLOCKS)
 ya_k_mcts_select(ya_mcts_tree tree, const uint4* __restrict__ states, int64_t stride, const int8_t* __restrict__ players,
                  const int32_t* __restrict__ ply, const uint32_t* __restrict__ episode, uint64_t seed, uint64_t game_base,
-                 uint32_t sim, const uint32_t* __restrict__ sim_ptr, float cpuct, const uint8_t* __restrict__ active,
-                 float* __restrict__ features, uint8_t* __restrict__ need_eval, uint32_t* __restrict__ leaf_states,
+                 uint32_t sim, const uint32_t* __restrict__ sim_ptr, const uint64_t* __restrict__ game_base_ptr, float cpuct,
+                 const uint8_t* __restrict__ active, float* __restrict__ features, uint8_t* __restrict__ need_eval, uint32_t* __restrict__ leaf_states,
                  int32_t* __restrict__ err_flag, const uint8_t* __restrict__ injected, int resume) {
     const Team<kSelectTeam> tm = Team<kSelectTeam>::make();          // four games per warp
     const int lane = tm.sub;
-    if (sim_ptr) sim = *sim_ptr;                                     // CUDA-graph replay: the counter lives in HBM
+    if (sim_ptr) sim = *sim_ptr;                                     // CUDA-graph replay: the counter lives in HBM,
+    if (game_base_ptr) game_base = *game_base_ptr;                   // and so does the global id of this slice's first game
     const int64_t g = ((int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5)) * (32 / kSelectTeam) + (tm.shift / kSelectTeam);
     if (g >= tree.n) return;
     if (active && !active[g]) { if (lane == 0) need_eval[g] = 0; return; }
@@ -705,8 +707,16 @@ ya_k_mcts_expand(ya_mcts_tree tree, const float* __restrict__ pi_all, const floa
 // (row_max) or, for other evaluators, from one pass over the row.
 constexpr int kLogitWarps = 4;
 constexpr int kLogitCols = 3232;
+// 16-bit logit -> float32: bfloat16 is the upper half of a float32; IEEE half goes through the converter
+template <bool F16> __device__ __forceinline__ float lo16(uint32_t w) {
+    return F16 ? __half2float(__ushort_as_half((unsigned short)(w & 0xFFFFu))) : __uint_as_float(w << 16);
+}
+template <bool F16> __device__ __forceinline__ float hi16(uint32_t w) {
+    return F16 ? __half2float(__ushort_as_half((unsigned short)(w >> 16))) : __uint_as_float(w & 0xFFFF0000u);
+}
+template <bool F16>
 __global__ void __launch_bounds__(kLogitWarps * 32)
-ya_k_mcts_expand_logits(ya_mcts_tree tree, const __nv_bfloat16* __restrict__ logits_all, int64_t ld,
+ya_k_mcts_expand_logits(ya_mcts_tree tree, const uint16_t* __restrict__ logits_all, int64_t ld,
                         const float* __restrict__ row_max, const float* __restrict__ value,
                         uint32_t* __restrict__ sim_counter, int32_t* __restrict__ err_flag) {
     __shared__ __align__(16) uint32_t raw_all[kLogitWarps][kLogitCols / 2];
@@ -772,7 +782,7 @@ ya_k_mcts_expand_logits(ya_mcts_tree tree, const __nv_bfloat16* __restrict__ log
             mx = -CUDART_INF_F;
             for (int j = lane; j < YA_N_ACTION / 2; j += 32) {
                 uint32_t w = lg[j];
-                mx = fmaxf(mx, fmaxf(__uint_as_float(w << 16), __uint_as_float(w & 0xFFFF0000u)));
+                mx = fmaxf(mx, fmaxf(lo16<F16>(w), hi16<F16>(w)));
             }
 #pragma unroll
             for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, o));
@@ -793,22 +803,22 @@ ya_k_mcts_expand_logits(ya_mcts_tree tree, const __nv_bfloat16* __restrict__ log
             const uint2* raw2 = reinterpret_cast<const uint2*>(raw);
             for (int j = lane; j < (L >> 2); j += 32) {
                 const uint2 w = raw2[j];
-                total += ex2(fmaf(__uint_as_float(w.x << 16), kLog2e, off_sum));
-                t1 += ex2(fmaf(__uint_as_float(w.x & 0xFFFF0000u), kLog2e, off_sum));
-                t2 += ex2(fmaf(__uint_as_float(w.y << 16), kLog2e, off_sum));
-                t3 += ex2(fmaf(__uint_as_float(w.y & 0xFFFF0000u), kLog2e, off_sum));
+                total += ex2(fmaf(lo16<F16>(w.x), kLog2e, off_sum));
+                t1 += ex2(fmaf(hi16<F16>(w.x), kLog2e, off_sum));
+                t2 += ex2(fmaf(lo16<F16>(w.y), kLog2e, off_sum));
+                t3 += ex2(fmaf(hi16<F16>(w.y), kLog2e, off_sum));
             }
             total = (total + t1) + (t2 + t3);
         } else if (pairs) {
             float t1 = 0.0f;
             for (int j = lane; j < nw; j += 32) {
                 const uint32_t w = raw[j];
-                total += ex2(fmaf(__uint_as_float(w << 16), kLog2e, off_sum));
-                t1 += ex2(fmaf(__uint_as_float(w & 0xFFFF0000u), kLog2e, off_sum));
+                total += ex2(fmaf(lo16<F16>(w), kLog2e, off_sum));
+                t1 += ex2(fmaf(hi16<F16>(w), kLog2e, off_sum));
             }
             total += t1;
         } else {
-            for (int k = lane; k < L; k += 32) total += ex2(fmaf(__uint_as_float((uint32_t)rc[k] << 16), kLog2e, off_sum));
+            for (int k = lane; k < L; k += 32) total += ex2(fmaf(lo16<F16>((uint32_t)rc[k]), kLog2e, off_sum));
         }
 #pragma unroll
         for (int o = 16; o; o >>= 1) total += __shfl_xor_sync(0xFFFFFFFFu, total, o);
@@ -827,10 +837,10 @@ ya_k_mcts_expand_logits(ya_mcts_tree tree, const __nv_bfloat16* __restrict__ log
                     if (j < nq) {
                         const uint2 w = raw2[j];
                         float4 p;
-                        p.x = ex2(fmaf(__uint_as_float(w.x << 16), kLog2e, off_p));
-                        p.y = ex2(fmaf(__uint_as_float(w.x & 0xFFFF0000u), kLog2e, off_p));
-                        p.z = ex2(fmaf(__uint_as_float(w.y << 16), kLog2e, off_p));
-                        p.w = ex2(fmaf(__uint_as_float(w.y & 0xFFFF0000u), kLog2e, off_p));
+                        p.x = ex2(fmaf(lo16<F16>(w.x), kLog2e, off_p));
+                        p.y = ex2(fmaf(hi16<F16>(w.x), kLog2e, off_p));
+                        p.z = ex2(fmaf(lo16<F16>(w.y), kLog2e, off_p));
+                        p.w = ex2(fmaf(hi16<F16>(w.y), kLog2e, off_p));
                         reinterpret_cast<float4*>(row)[j] = p;
                         e = __float_as_uint(fmaxf(fmaxf(p.x, p.y), fmaxf(p.z, p.w))) + 1u;
                     }
@@ -847,8 +857,8 @@ ya_k_mcts_expand_logits(ya_mcts_tree tree, const __nv_bfloat16* __restrict__ log
                     uint32_t e = 0;
                     if (j < nw) {
                         const uint32_t w = raw[j];
-                        const float p0 = ex2(fmaf(__uint_as_float(w << 16), kLog2e, off_p));
-                        const float p1 = ex2(fmaf(__uint_as_float(w & 0xFFFF0000u), kLog2e, off_p));
+                        const float p0 = ex2(fmaf(lo16<F16>(w), kLog2e, off_p));
+                        const float p1 = ex2(fmaf(hi16<F16>(w), kLog2e, off_p));
                         reinterpret_cast<float2*>(row)[j] = make_float2(p0, p1);
                         e = max(__float_as_uint(p0), __float_as_uint(p1)) + 1u;
                     }
@@ -860,7 +870,7 @@ ya_k_mcts_expand_logits(ya_mcts_tree tree, const __nv_bfloat16* __restrict__ log
             } else {
                 for (int k0 = 0; k0 < L; k0 += 32) {
                     const int k = k0 + lane;
-                    store_prior_group(row, L, k0, k < L ? ex2(fmaf(__uint_as_float((uint32_t)rc[k] << 16), kLog2e, off_p)) : 0.0f, lane);
+                    store_prior_group(row, L, k0, k < L ? ex2(fmaf(lo16<F16>((uint32_t)rc[k]), kLog2e, off_p)) : 0.0f, lane);
                 }
             }
         } else {                                                       // every legal move underflowed: MCTS.py:97-101
@@ -1091,17 +1101,17 @@ int ya_mcts_reset(const ya_mcts_tree* tree, const uint8_t* which, void* stream) 
 
 int ya_mcts_select(const ya_mcts_tree* tree, const uint32_t* states, int64_t stride, const int8_t* players,
                    const int32_t* ply, const uint32_t* episode, uint64_t seed, uint64_t game_base, uint32_t sim,
-                   const uint32_t* sim_ptr, float cpuct, const uint8_t* active, float* features, uint8_t* need_eval,
-                   uint32_t* leaf_states, int32_t* err_flag, void* stream) {
+                   const uint32_t* sim_ptr, const uint64_t* game_base_ptr, float cpuct, const uint8_t* active,
+                   float* features, uint8_t* need_eval, uint32_t* leaf_states, int32_t* err_flag, void* stream) {
     if (!tree_ok(tree) || !(cpuct >= 0.0f)) return (int)cudaErrorInvalidValue;   // group maxima rely on u monotone in P
     if (leaf_states)
         ya_k_mcts_select<true, false><<<select_blocks(tree->n), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
             *tree, reinterpret_cast<const uint4*>(states), stride, players, ply, episode, seed, game_base, sim, sim_ptr,
-            cpuct, active, features, need_eval, leaf_states, err_flag, nullptr, 0);
+            game_base_ptr, cpuct, active, features, need_eval, leaf_states, err_flag, nullptr, 0);
     else
         ya_k_mcts_select<false, false><<<select_blocks(tree->n), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
             *tree, reinterpret_cast<const uint4*>(states), stride, players, ply, episode, seed, game_base, sim, sim_ptr,
-            cpuct, active, features, need_eval, leaf_states, err_flag, nullptr, 0);
+            game_base_ptr, cpuct, active, features, need_eval, leaf_states, err_flag, nullptr, 0);
     return (int)cudaGetLastError();
 }
 
@@ -1110,7 +1120,7 @@ int ya_mcts_select_injected(const ya_mcts_tree* tree, const uint32_t* states, in
                             uint8_t* need_eval, uint32_t* leaf_states, int32_t* err_flag, void* stream) {
     if (!tree_ok(tree) || !injected || !leaf_states || !(cpuct >= 0.0f)) return (int)cudaErrorInvalidValue;
     ya_k_mcts_select<true, true><<<select_blocks(tree->n), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
-        *tree, reinterpret_cast<const uint4*>(states), stride, players, nullptr, nullptr, 0, 0, sim, nullptr,
+        *tree, reinterpret_cast<const uint4*>(states), stride, players, nullptr, nullptr, 0, 0, sim, nullptr, nullptr,
         cpuct, nullptr, features, need_eval, leaf_states, err_flag, injected, resume);
     return (int)cudaGetLastError();
 }
@@ -1127,13 +1137,17 @@ int ya_mcts_expand(const ya_mcts_tree* tree, const float* pi, const float* value
     return (int)cudaGetLastError();
 }
 
-int ya_mcts_expand_logits(const ya_mcts_tree* tree, const void* logits_bf16, int64_t ld, const float* row_max,
+int ya_mcts_expand_logits(const ya_mcts_tree* tree, const void* logits16, int fp16, int64_t ld, const float* row_max,
                           const float* value, uint32_t* sim_counter, int32_t* err_flag, void* stream) {
-    if (!tree_ok(tree) || ld < kLogitCols || (ld % 8) != 0 || (reinterpret_cast<uintptr_t>(logits_bf16) & 15u))
+    if (!tree_ok(tree) || ld < kLogitCols || (ld % 8) != 0 || (reinterpret_cast<uintptr_t>(logits16) & 15u))
         return (int)cudaErrorInvalidValue;
     int blocks = (int)((tree->n + kLogitWarps - 1) / kLogitWarps);
-    ya_k_mcts_expand_logits<<<blocks, kLogitWarps * 32, 0, (cudaStream_t)stream>>>(
-        *tree, static_cast<const __nv_bfloat16*>(logits_bf16), ld, row_max, value, sim_counter, err_flag);
+    if (fp16)
+        ya_k_mcts_expand_logits<true><<<blocks, kLogitWarps * 32, 0, (cudaStream_t)stream>>>(
+            *tree, static_cast<const uint16_t*>(logits16), ld, row_max, value, sim_counter, err_flag);
+    else
+        ya_k_mcts_expand_logits<false><<<blocks, kLogitWarps * 32, 0, (cudaStream_t)stream>>>(
+            *tree, static_cast<const uint16_t*>(logits16), ld, row_max, value, sim_counter, err_flag);
     return (int)cudaGetLastError();
 }
 

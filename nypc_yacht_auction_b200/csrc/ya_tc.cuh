@@ -4,6 +4,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cstdint>
 
 namespace ya_tc {
@@ -57,9 +58,24 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
 // descriptor of the same tile `bytes` further on (same swizzle atom row: K steps of 32 bytes, K-blocks, halves)
 __device__ __forceinline__ uint64_t umma_desc_advance(uint64_t desc, uint32_t bytes) { return desc + (uint64_t)(bytes >> 4); }
 
-// instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=n_cols
-__host__ __device__ constexpr uint32_t umma_idesc(int n_cols) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n_cols >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+// instruction descriptor (kind::f16): D=f32, A=B=bf16 (format 1) or fp16 (format 0), both K-major, M=128, N=n_cols
+__host__ __device__ constexpr uint32_t umma_idesc(int n_cols, bool fp16 = false) {
+    return (1u << 4) | (fp16 ? 0u : ((1u << 7) | (1u << 10))) | ((uint32_t)(n_cols >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+// two float32 -> one packed 16-bit pair (low half = first element), round to nearest even
+template <bool F16>
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+    uint32_t r;
+    if (F16) asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    else asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
+}
+// the float32 value of a 16-bit operand after rounding (what a reader of the packed value will see)
+template <bool F16>
+__device__ __forceinline__ float round16(float x) {
+    if (F16) return __half2float(__float2half_rn(x));
+    return __bfloat162float(__float2bfloat16_rn(x));
 }
 
 __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate, uint32_t idesc) {

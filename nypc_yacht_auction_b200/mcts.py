@@ -72,203 +72,103 @@ class UniformEvaluator:
     v = 0.0
 
 
-class TorchEvaluator:
-    """One batched forward of a policy/value net for all leaves (the only dense contraction).
-    predict semantics of yacht/NNet.py:177-195: pi = softmax(logits) over all 3226 actions.
-
-    dtype=torch.bfloat16 runs the whole forward in bf16 from a bf16 copy of the weights (no autocast
-    cast kernels per call; LayerNorm still accumulates in fp32 inside its kernel); dtype=None keeps the
-    module's own precision (fp32, what the CPU reference computes).
-    fused_logits=True (bf16 only) pads the policy head to 3232 outputs (16-byte aligned rows -> the fast
-    GEMM path) and hands the raw bf16 logits to ya_mcts_expand_logits, which fuses softmax, masking and
-    renormalisation: neither float32 logits nor pi are written to HBM."""
-    uniform = False
-    PADDED = 3232
-
-    def __init__(self, net, dtype=None, autocast_dtype=None, fused_logits=False):
-        import copy
-        self.dtype = dtype
-        self.autocast_dtype = autocast_dtype
-        self.returns_logits = bool(fused_logits)
-        self.net = (copy.deepcopy(net).to(dtype) if dtype is not None else net).eval()
-        if self.returns_logits:
-            assert dtype == torch.bfloat16, "fused logits need the bf16 forward"
-            head = self.net.pi_head[2]
-            padded = torch.nn.Linear(head.in_features, self.PADDED, device=head.weight.device, dtype=head.weight.dtype)
-            with torch.no_grad():
-                padded.weight.zero_()
-                padded.bias.zero_()
-                padded.weight[:head.out_features].copy_(head.weight)
-                padded.bias[:head.out_features].copy_(head.bias)
-            self.net.pi_head[2] = padded
-
-    @torch.no_grad()
-    def __call__(self, features, need_eval=None, leaf_states=None):
-        if self.dtype is not None:
-            logits, v = self.net(features.to(self.dtype))
-        elif self.autocast_dtype is not None:
-            with torch.autocast("cuda", dtype=self.autocast_dtype):
-                logits, v = self.net(features)
-        else:
-            logits, v = self.net(features)
-        v = v.float().reshape(-1).contiguous()
-        if self.returns_logits:
-            return logits.contiguous(), v
-        return torch.softmax(logits.float(), dim=1).contiguous(), v
-
-
 class FusedYachtEvaluator:
-    """The yacht NNet forward (yacht/pytorch/YachtNNet.py:62-70) for a whole wave of leaves.  Default: ONE
-    hand-written tcgen05 kernel for the whole network (csrc/ya_forward.cu): features in, bf16 logits padded to
-    3232 columns + tanh value + per-row max logit out, consumed by ya_mcts_expand_logits; rows do not depend on
-    the batch they sit in.  whole_forward=False keeps the earlier composition -- bf16 GEMMs through PyTorch
-    (cuBLASLt) for the input layer and the heads, the trunk as one tcgen05 kernel (csrc/ya_trunk.cu) or, with
-    trunk_kernel=False too, a GEMM + fused SiLU / LayerNorm / residual pass (csrc/ya_nn.cu) per layer -- which
-    the tests use as cross-checks.  Weights come from any module with YachtNNet's state dict (:25-52)."""
+    """The yacht NNet forward (yacht/pytorch/YachtNNet.py:62-70) for a whole wave of leaves as ONE hand-written
+    tcgen05 kernel (csrc/ya_forward.cu): features in, 16-bit logits padded to 3232 columns + tanh value + per-row
+    max logit out, consumed by ya_mcts_expand_logits; rows do not depend on the batch they sit in.
+
+    precision="fp16" (default): activations, weights and logits in IEEE half with float32 accumulation, LayerNorm
+    and skip connection -- the arithmetic of the reference's CUDA predict (fp16 autocast, yacht/NNet.py:186-193).
+    precision="bf16": the same kernel with bfloat16 operands (same tensor-core rate, 8-bit mantissa).
+    Weights come from any module with YachtNNet's state dict (:25-52), hidden width 256 (main.py:40)."""
     uniform = False
     returns_logits = True
     PADDED = 3232
 
-    def __init__(self, net, max_batch, trunk_kernel=True, whole_forward=True):
+    def __init__(self, net, max_batch, precision="fp16"):
+        if precision not in ("fp16", "bf16"):
+            raise ValueError("precision must be 'fp16' or 'bf16', got %r" % (precision,))
+        self.precision = precision
+        self.fp16 = precision == "fp16"
+        self.op_dtype = torch.float16 if self.fp16 else torch.bfloat16
         self.last_row_max = None
         sd = {k: v.detach() for k, v in net.state_dict().items()}
         dev = next(net.parameters()).device
-        bf = lambda t: t.to(device=dev, dtype=torch.bfloat16).contiguous()
         self.hidden = sd["inp.0.weight"].shape[0]
-        if self.hidden != 256:
-            raise ValueError("FusedYachtEvaluator handles hidden=256 (main.py:40); use TorchEvaluator otherwise")
         self.nblocks = len({k.split(".")[1] for k in sd if k.startswith("blocks.")})
-        self.w_in, self.b_in = bf(sd["inp.0.weight"]).t().contiguous(), bf(sd["inp.0.bias"])
-        self.ln_in = (bf(sd["inp.1.weight"]), bf(sd["inp.1.bias"]))
-        self.blocks = []
-        for i in range(self.nblocks):
-            p = "blocks.%d." % i
-            self.blocks.append((bf(sd[p + "fc1.weight"]).t().contiguous(), bf(sd[p + "fc1.bias"]),
-                                bf(sd[p + "ln1.weight"]), bf(sd[p + "ln1.bias"]),
-                                bf(sd[p + "fc2.weight"]).t().contiguous(), bf(sd[p + "fc2.bias"]),
-                                bf(sd[p + "ln2.weight"]), bf(sd[p + "ln2.bias"])))
-        self.ln_pi = (bf(sd["pi_head.0.weight"]), bf(sd["pi_head.0.bias"]))
-        self.ln_v = (bf(sd["v_head.0.weight"]), bf(sd["v_head.0.bias"]))
         a = sd["pi_head.2.weight"].shape[0]
-        w = torch.zeros((self.PADDED, self.hidden), dtype=torch.bfloat16, device=dev)
-        b = torch.zeros(self.PADDED, dtype=torch.bfloat16, device=dev)
-        w[:a].copy_(sd["pi_head.2.weight"])
-        b[:a].copy_(sd["pi_head.2.bias"])
-        self.w_pi, self.b_pi = w.t().contiguous(), b
-        self.w_v1, self.b_v1 = bf(sd["v_head.2.weight"]).t().contiguous(), bf(sd["v_head.2.bias"])
-        self.w_v2, self.b_v2 = bf(sd["v_head.4.weight"]).t().contiguous(), bf(sd["v_head.4.bias"])
+        if self.hidden != 256 or sd["v_head.2.weight"].shape[0] != 128 or a > self.PADDED or sd["inp.0.weight"].shape[1] > 64:
+            raise ValueError("FusedYachtEvaluator handles YachtNNet(hidden=256) with <= 64 inputs, a 128-wide value head and "
+                             "<= 3232 actions (main.py:40-42)")
         self.lib = _lib.load()
         self.eps = 1e-5
-        # the 2 * nblocks trunk layers for the persistent tcgen05 kernel (csrc/ya_trunk.cu)
-        self.trunk_kernel = bool(trunk_kernel) and self.nblocks > 0
-        if self.trunk_kernel:
-            images, params, kinds = [], [], []
-            for i in range(self.nblocks):
-                p = "blocks.%d." % i
-                for fc, ln, kind in (("fc1", "ln1", 1), ("fc2", "ln2", 2)):
-                    images.append(self.swizzled_image(sd[p + fc + ".weight"].to(dev)))
-                    params.append(torch.stack([sd[p + fc + ".bias"], sd[p + ln + ".weight"], sd[p + ln + ".bias"]]).float())
-                    kinds.append(kind)
-            self.trunk_w = torch.cat(images).contiguous()
-            self.trunk_p = torch.stack(params).to(dev).contiguous()
-            self.trunk_kinds = torch.tensor(kinds, dtype=torch.int32, device=dev)
-
-        # everything (input layer, trunk, both heads) for the single-kernel forward (csrc/ya_forward.cu)
-        self.whole_forward = bool(whole_forward) and self.trunk_kernel and sd["v_head.2.weight"].shape[0] == 128 \
-            and sd["pi_head.2.weight"].shape[0] <= self.PADDED and sd["inp.0.weight"].shape[1] <= 64
-        if self.whole_forward:
-            f32 = lambda t: t.to(device=dev, dtype=torch.float32).reshape(-1)
-            w_in = torch.zeros((256, 64), dtype=torch.bfloat16, device=dev)
-            w_in[:, :sd["inp.0.weight"].shape[1]].copy_(sd["inp.0.weight"])
-            w_pi = torch.zeros((26 * 128, 256), dtype=torch.bfloat16, device=dev)
-            w_pi[:a].copy_(sd["pi_head.2.weight"])
-            b_pi = torch.zeros(26 * 128, dtype=torch.float32, device=dev)
-            b_pi[:a].copy_(sd["pi_head.2.bias"])
-            wparts = [self.swizzled_image(w_in), self.trunk_w, self.swizzled_image(sd["v_head.2.weight"].to(dev))] + \
-                     [self.swizzled_image(w_pi[128 * j:128 * (j + 1)]) for j in range(26)]
-            trunk_p = self.trunk_p.clone()                              # [layer][bias | gamma | beta][256]
-            trunk_p[:, 0] *= 0.5                                        # the kernel's SiLU works on (z + b) / 2
-            pparts = [f32(sd["inp.0.bias"]), f32(sd["inp.1.weight"]), f32(sd["inp.1.bias"]), trunk_p.reshape(-1),
-                      f32(sd["v_head.0.weight"]), f32(sd["v_head.0.bias"]), f32(sd["v_head.2.bias"]), f32(sd["v_head.4.weight"]),
-                      torch.cat([f32(sd["v_head.4.bias"]), torch.zeros(3, device=dev)]),
-                      f32(sd["pi_head.0.weight"]), f32(sd["pi_head.0.bias"]), b_pi]
-            wsizes = [p.numel() for p in wparts]
-            psizes = [p.numel() for p in pparts]
-            self.fw_w = torch.cat(wparts).contiguous()
-            self.fw_p = torch.cat(pparts).contiguous()
-            w_off = [0, wsizes[0], wsizes[0] + wsizes[1], wsizes[0] + wsizes[1] + wsizes[2]]
-            p_in, p_trunk = 0, sum(psizes[:3])
-            p_v = p_trunk + psizes[3]
-            p_pi_ln = p_v + sum(psizes[4:9])
-            self.fw_off = (ctypes.c_int64 * 9)(*w_off, p_in, p_trunk, p_v, p_pi_ln, p_pi_ln + 512)
-            assert sum(psizes[4:9]) == 772 and psizes[3] == 768 * 2 * self.nblocks
+        f32 = lambda t: t.to(device=dev, dtype=torch.float32).reshape(-1)
+        images, params = [], []
+        for i in range(self.nblocks):
+            p = "blocks.%d." % i
+            for fc, ln in (("fc1", "ln1"), ("fc2", "ln2")):
+                images.append(self.swizzled_image(sd[p + fc + ".weight"].to(dev)))
+                params.append(torch.stack([0.5 * sd[p + fc + ".bias"], sd[p + ln + ".weight"], sd[p + ln + ".bias"]]).float())
+        # params[layer] = bias / 2 | gamma | beta: the kernel's SiLU works on (z + b) / 2
+        trunk_w = torch.cat(images) if images else torch.zeros(0, dtype=torch.uint8, device=dev)
+        trunk_p = torch.stack(params).to(dev).reshape(-1) if params else torch.zeros(0, device=dev)
+        w_in = torch.zeros((256, 64), dtype=torch.float32, device=dev)
+        w_in[:, :sd["inp.0.weight"].shape[1]].copy_(sd["inp.0.weight"])
+        w_pi = torch.zeros((26 * 128, 256), dtype=torch.float32, device=dev)
+        w_pi[:a].copy_(sd["pi_head.2.weight"])
+        b_pi = torch.zeros(26 * 128, dtype=torch.float32, device=dev)
+        b_pi[:a].copy_(sd["pi_head.2.bias"])
+        wparts = [self.swizzled_image(w_in), trunk_w, self.swizzled_image(sd["v_head.2.weight"].to(dev))] + \
+                 [self.swizzled_image(w_pi[128 * j:128 * (j + 1)]) for j in range(26)]
+        pparts = [f32(sd["inp.0.bias"]), f32(sd["inp.1.weight"]), f32(sd["inp.1.bias"]), trunk_p,
+                  f32(sd["v_head.0.weight"]), f32(sd["v_head.0.bias"]), f32(sd["v_head.2.bias"]), f32(sd["v_head.4.weight"]),
+                  torch.cat([f32(sd["v_head.4.bias"]), torch.zeros(3, device=dev)]),
+                  f32(sd["pi_head.0.weight"]), f32(sd["pi_head.0.bias"]), b_pi]
+        wsizes = [p.numel() for p in wparts]
+        psizes = [p.numel() for p in pparts]
+        self.fw_w = torch.cat(wparts).contiguous()
+        self.fw_p = torch.cat(pparts).contiguous()
+        w_off = [0, wsizes[0], wsizes[0] + wsizes[1], wsizes[0] + wsizes[1] + wsizes[2]]
+        p_in, p_trunk = 0, sum(psizes[:3])
+        p_v = p_trunk + psizes[3]
+        p_pi_ln = p_v + sum(psizes[4:9])
+        self.fw_off = (ctypes.c_int64 * 9)(*w_off, p_in, p_trunk, p_v, p_pi_ln, p_pi_ln + 512)
+        assert sum(psizes[4:9]) == 772 and psizes[3] == 768 * 2 * self.nblocks
+        self.device = dev
         self._alloc(int(max_batch), dev)
 
-    @staticmethod
-    def swizzled_image(w):
-        """[rows][K] weight (K a multiple of 64) -> shared-memory image for tcgen05.mma: K-blocks of [rows][64 bf16],
-        16-byte chunk c of row r stored at chunk c ^ (r & 7) (128-byte swizzle)."""
+    def swizzled_image(self, w):
+        """[rows][K] weight (K a multiple of 64) -> shared-memory image for tcgen05.mma in the operand format: K-blocks
+        of [rows][64 x 16 bit], 16-byte chunk c of row r stored at chunk c ^ (r & 7) (128-byte swizzle)."""
         rows, k = w.shape
-        w = w.to(torch.bfloat16).contiguous().view(rows, k // 64, 8, 8)
+        w = w.to(self.op_dtype).contiguous().view(rows, k // 64, 8, 8)
         r = torch.arange(rows, device=w.device).view(rows, 1, 1)
         src_chunk = (torch.arange(8, device=w.device).view(1, 1, 8) ^ (r & 7)).expand(rows, k // 64, 8)
         img = torch.gather(w, 2, src_chunk.unsqueeze(-1).expand(rows, k // 64, 8, 8))
         return img.permute(1, 0, 2, 3).contiguous().view(torch.uint8).reshape(-1)
 
     def _alloc(self, n, dev):
-        h = self.hidden
-        mk = lambda *shape: torch.empty(shape, dtype=torch.bfloat16, device=dev)
-        self.logits = mk(n, self.PADDED)
-        if self.whole_forward:
-            self.values = torch.empty(n, dtype=torch.float32, device=dev)
-            self.row_max = torch.empty(n, dtype=torch.float32, device=dev)
-        else:                                                             # activations between the layer-by-layer launches
-            self.z, self.h, self.a, self.p, self.q = mk(n, h), mk(n, h), mk(n, h), mk(n, h), mk(n, h)
+        self.logits = torch.empty((n, self.PADDED), dtype=self.op_dtype, device=dev)
+        self.values = torch.empty(n, dtype=torch.float32, device=dev)
+        self.row_max = torch.empty(n, dtype=torch.float32, device=dev)
 
     def with_private_buffers(self, max_batch):
         """Same weights, own activation buffers (one instance per concurrently running game group)."""
         import copy
         other = copy.copy(self)
-        other._alloc(int(max_batch), self.w_in.device)
+        other._alloc(int(max_batch), self.device)
         return other
-
-    def _ln(self, mode, x, ln, out, residual=None, ln2=None, out2=None):
-        _lib.check(self.lib.ya_nn_ln_act(mode, _lib.ptr(x), _lib.ptr(ln[0]), _lib.ptr(ln[1]), _lib.ptr(residual),
-                                         _lib.ptr(ln2[0]) if ln2 else None, _lib.ptr(ln2[1]) if ln2 else None,
-                                         _lib.ptr(out), _lib.ptr(out2), x.shape[0], self.hidden, self.eps,
-                                         _lib.current_stream()), "ya_nn_ln_act")
 
     @torch.no_grad()
     def __call__(self, features, need_eval=None, leaf_states=None):
         n = features.shape[0]
-        if self.whole_forward:                                            # one tcgen05 kernel: features -> logits, values
-            logits, values = self.logits[:n], self.values[:n]
-            self.last_row_max = self.row_max[:n]                          # consumed by ya_mcts_expand_logits
-            _lib.check(self.lib.ya_nn_forward(_lib.ptr(features), _lib.ptr(logits), _lib.ptr(values),
-                                              _lib.ptr(self.last_row_max), _lib.ptr(self.fw_w),
-                                              _lib.ptr(self.fw_p), self.fw_off, self.nblocks, n, self.eps,
-                                              _lib.current_stream()), "ya_nn_forward")
-            return logits, values
-        z, h, a, p, q = self.z[:n], self.h[:n], self.a[:n], self.p[:n], self.q[:n]
-        x = features.to(torch.bfloat16)
-        torch.addmm(self.b_in, x, self.w_in, out=z)
-        self._ln(0, z, self.ln_in, h)                                     # inp: Linear -> LN -> SiLU
-        if self.trunk_kernel:                                             # all residual blocks in one tcgen05 kernel
-            _lib.check(self.lib.ya_nn_trunk(_lib.ptr(h), _lib.ptr(a), _lib.ptr(self.trunk_w), _lib.ptr(self.trunk_p),
-                                            _lib.ptr(self.trunk_kinds), 2 * self.nblocks, n, self.hidden, self.eps,
-                                            _lib.current_stream()), "ya_nn_trunk")
-            h = a
-        for (w1, b1, g1, be1, w2, b2, g2, be2) in (() if self.trunk_kernel else self.blocks):
-            torch.addmm(b1, h, w1, out=z)
-            self._ln(1, z, (g1, be1), a)                                  # ln1(silu(fc1(x)))
-            torch.addmm(b2, a, w2, out=z)
-            self._ln(2, z, (g2, be2), h, residual=h)                      # x + ln2(silu(fc2(h)))  (in place: row-local)
-        self._ln(3, h, self.ln_pi, p, ln2=self.ln_v, out2=q)              # both heads' LN -> SiLU
-        logits = self.logits[:n]
-        torch.addmm(self.b_pi, p, self.w_pi, out=logits)
-        t = torch.nn.functional.silu(torch.addmm(self.b_v1, q, self.w_v1))
-        v = torch.tanh(torch.addmm(self.b_v2, t, self.w_v2))
-        return logits, v.float().reshape(-1).contiguous()
+        logits, values = self.logits[:n], self.values[:n]
+        self.last_row_max = self.row_max[:n]                              # consumed by ya_mcts_expand_logits
+        _lib.check(self.lib.ya_nn_forward(_lib.ptr(features), _lib.ptr(logits), _lib.ptr(values),
+                                          _lib.ptr(self.last_row_max), _lib.ptr(self.fw_w),
+                                          _lib.ptr(self.fw_p), self.fw_off, self.nblocks, n, self.eps,
+                                          1 if self.fp16 else 0, _lib.current_stream()), "ya_nn_forward")
+        return logits, values
 
 
 class _Group:
@@ -285,6 +185,9 @@ class _Group:
         self.players, self.ply, self.episode = env.players[g0:g1], env.ply[g0:g1], env.episode[g0:g1]
         self.features, self.need_eval = mcts.features[g0:g1], mcts.need_eval[g0:g1]
         self.sim_counter = torch.zeros(1, dtype=torch.int32, device=env.device)
+        # global id of this slice's first game, in device memory: a captured launch freezes by-value arguments, so the
+        # graph reads the base from here and stays valid when the pool moves on to the next wave of games
+        self.base_dev = torch.full((1,), env.game_base + g0, dtype=torch.int64, device=env.device)
         self.evaluator = evaluator
         self.stream = stream
 
@@ -338,11 +241,26 @@ class BatchedMCTS:
             stream = torch.cuda.Stream(device=d) if groups > 1 else None
             self.groups.append(_Group(self, g0, g1, ev, stream))
         self.sim_counter = self.groups[0].sim_counter
+        self._base_on_device = env.game_base
+
+    def sync_game_base(self):
+        """Publishes env.game_base to the device scalars the select kernel reads (call-free for the user: search()
+        does it whenever env.game_base changed, e.g. coach.self_play_in_waves moving to the next wave)."""
+        if self._base_on_device != self.env.game_base:
+            for grp in self.groups:
+                grp.base_dev.fill_(self.env.game_base + grp.g0)
+            self._base_on_device = self.env.game_base
 
     def capture_graph(self):
         """Capture ONE simulation wave (select, evaluator forward, expand of every group) as a CUDA graph;
         the simulation index is a device counter the expand kernel bumps, so the same graph is replayed
-        numMCTSSims times per move without any host-side launch work in between."""
+        numMCTSSims times per move without any host-side launch work in between.  The global game ids come from
+        device memory too (grp.base_dev), so the graph survives env.game_base changes (waves on one pool).
+        Capture on EMPTY trees only: the warm-up simulations are rolled back by restoring the node tables, not the
+        arena (edge statistics), which is only consistent when there was nothing in the arena before."""
+        if int(self.pool.meta[:, 0].max().item()) != 0:
+            raise _lib.YachtB200Error("capture_graph needs empty trees (call pool.reset() first, or capture before the first search)")
+        self.sync_game_base()
         side = torch.cuda.Stream(device=self.env.device)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):                 # warm-up outside capture (lazy inits of the evaluator)
@@ -368,7 +286,7 @@ class BatchedMCTS:
         _lib.check(self.lib.ya_mcts_select(
             grp.ref, grp.states_ptr, env.n, _lib.ptr(grp.players), _lib.ptr(grp.ply), _lib.ptr(grp.episode),
             env.seed, env.game_base + grp.g0, 0 if sim is None else sim, _lib.ptr(grp.sim_counter) if sim is None else None,
-            self.cpuct, None, _lib.ptr(grp.features), _lib.ptr(grp.need_eval),
+            _lib.ptr(grp.base_dev) if sim is None else None, self.cpuct, None, _lib.ptr(grp.features), _lib.ptr(grp.need_eval),
             _lib.ptr(leaf), _lib.ptr(self.err_flag), s), "ya_mcts_select")
         counter = _lib.ptr(grp.sim_counter) if sim is None else None
         ev = grp.evaluator
@@ -379,10 +297,11 @@ class BatchedMCTS:
         pi, v = ev(grp.features, grp.need_eval, leaf)
         assert v.dtype == torch.float32 and v.is_contiguous() and v.shape == (grp.n,)
         if getattr(ev, "returns_logits", False):
-            assert pi.dtype == torch.bfloat16 and pi.is_contiguous() and pi.shape[0] == grp.n
+            assert pi.dtype in (torch.bfloat16, torch.float16) and pi.is_contiguous() and pi.shape[0] == grp.n
             row_max = getattr(ev, "last_row_max", None)               # per-row max logit, if the evaluator has it
             assert row_max is None or (row_max.dtype == torch.float32 and row_max.shape == (grp.n,))
-            _lib.check(self.lib.ya_mcts_expand_logits(grp.ref, _lib.ptr(pi), pi.shape[1], _lib.ptr(row_max), _lib.ptr(v),
+            _lib.check(self.lib.ya_mcts_expand_logits(grp.ref, _lib.ptr(pi), 1 if pi.dtype == torch.float16 else 0,
+                                                      pi.shape[1], _lib.ptr(row_max), _lib.ptr(v),
                                                       counter, _lib.ptr(self.err_flag), s), "ya_mcts_expand_logits")
             return
         assert pi.dtype == torch.float32 and pi.is_contiguous() and pi.shape == (grp.n, ACTION_SIZE)
@@ -405,6 +324,7 @@ class BatchedMCTS:
     def search(self):
         """getActionProb's simulation loop (MCTS.py:37-38) for every game."""
         ev = self.evaluator
+        self.sync_game_base()
         if getattr(ev, "uniform", False) and self.fuse_uniform:
             env = self.env                  # no network between select and expand: the whole loop is one launch
             _lib.check(self.lib.ya_mcts_search_uniform(
@@ -533,7 +453,7 @@ class MCTS:
             self.ply.fill_(self.root_index)
             _lib.check(self.lib.ya_mcts_select(
                 self.pool.ref, _lib.ptr(self.states), 1, _lib.ptr(self.players), _lib.ptr(self.ply), None,
-                self.seed, self.tree_id, self.sim_index, None, float(self.args.cpuct), None, _lib.ptr(self.features),
+                self.seed, self.tree_id, self.sim_index, None, None, float(self.args.cpuct), None, _lib.ptr(self.features),
                 _lib.ptr(self.need_eval), _lib.ptr(self.leaf_states), _lib.ptr(self.err_flag), s), "ya_mcts_select")
             code = int(self.need_eval.item())
         else:

@@ -1,4 +1,5 @@
-"""Multi-GPU check (run under torchrun on a box with >= 2 GPUs; not collected by pytest):
+"""Multi-GPU check (run under torchrun on a box with >= 2 GPUs; tests/test_dist_gpu.py launches it from pytest -m gpu
+and skips below 2 GPUs):
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29577 tests/dist_gpu_check.py
 
@@ -56,8 +57,21 @@ def main():
         rex = ref.execute_episodes()
         for k in ("features", "actions", "counts", "value", "result_p1"):
             assert torch.equal(full_nn[k], rex[k]), "sharded network run differs from the single-process run in %s" % k
-        print("dist ok: %d games over %d GPUs == 1 process, bitwise, for the uniform AND the network evaluator; NCCL "
-              "all-gather %s, weight broadcast verified" % (total, world, tuple(full["counts"].shape)))
+    # C. the configs[4] shape: every rank plays its shard as TWO waves on one tree pool with the simulation wave replayed
+    # as a CUDA graph (global game ids read from device memory); still bitwise the single-process batch
+    from nypc_yacht_auction_b200.coach import self_play_in_waves
+    per = last - first
+    assert per % 2 == 0
+    parts = []
+    self_play_in_waves(per, per // 2, sims, FusedYachtEvaluator(net, per // 2), first_game=first, use_graph=True, seed=seed,
+                       device=dev, on_wave=lambda w, ex: parts.append({k: v.clone() for k, v in ex.items()}))
+    mine = {k: torch.cat([p[k] for p in parts], dim=0 if parts[0][k].dim() == 1 else 1) for k in ("features", "actions", "counts", "value", "result_p1")}
+    full_w = allgather_examples(mine)
+    if rank == 0:
+        for k in ("features", "actions", "counts", "value", "result_p1"):
+            assert torch.equal(full_w[k], rex[k]), "sharded + waved + graphed network run differs from the single-process run in %s" % k
+        print("dist ok: %d games over %d GPUs == 1 process, bitwise, for the uniform AND the network evaluator (eager, and as "
+              "2 graphed waves per rank); NCCL all-gather %s, weight broadcast verified" % (total, world, tuple(full["counts"].shape)))
     dist.barrier()
     dist.destroy_process_group()
 

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, s), "libyacht_b200.so does not export %s" % s
     assert syms == set(_lib.SIGNATURES), "ctypes table and header disagree: %r" % (syms ^ set(_lib.SIGNATURES))
     lib.ya_abi_version.restype = ctypes.c_int
-    assert lib.ya_abi_version() == 1
+    assert lib.ya_abi_version() == 2
 
 
 def test_no_cpu_fallback_without_cuda():
