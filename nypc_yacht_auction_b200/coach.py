@@ -124,6 +124,40 @@ class BatchedSelfPlay:
     def next_episode(self):
         self.mcts.new_episode()
 
+    # ------------------------------------------------------------------ host-buffer form (the end-to-end call)
+    def host_buffers(self):
+        """Pinned HOST buffers for execute_episodes_host: the start boards (two uint4 planes, int32[2, n, 4]) + movers in,
+        the training examples of Coach.executeEpisode (Coach.py:66-72) out."""
+        n, k, pin = self.n, self.k, dict(pin_memory=True)
+        return {
+            "boards": torch.zeros((2, n, 4), dtype=torch.int32, **pin), "players": torch.ones(n, dtype=torch.int8, **pin),
+            "features": torch.zeros((self.PLIES, n, FEATURE_SIZE), dtype=torch.float32, **pin),
+            "actions": torch.zeros((self.PLIES, n, k), dtype=torch.int16, **pin),
+            "counts": torch.zeros((self.PLIES, n, k), dtype=torch.int32, **pin),
+            "value": torch.zeros((self.PLIES, n), dtype=torch.float32, **pin),
+            "result_p1": torch.zeros(n, dtype=torch.float32, **pin),
+        }
+
+    def execute_episodes_host(self, host, new_trees=True):
+        """One self-play episode for every game with HOST-resident inputs and outputs: the start boards in
+        host["boards"] / host["players"] (e.g. getInitBoard positions the caller keeps) go host -> device, the 48
+        plies run, and the examples (feature rows, sparse root visit counts, outcome labels) come back into the
+        pinned buffers of `host`.  Returns (h2d_bytes, d2h_bytes).  Synchronises."""
+        env = self.env
+        if new_trees:
+            self.mcts.pool.reset()
+        env.states.copy_(host["boards"], non_blocking=True)
+        env.players.copy_(host["players"], non_blocking=True)
+        env.ply.zero_()
+        ex = self.execute_episodes()
+        names = ("features", "actions", "counts", "value", "result_p1")
+        for name in names:
+            host[name].copy_(ex[name], non_blocking=True)
+        torch.cuda.synchronize(env.device)
+        h2d = host["boards"].numel() * 4 + host["players"].numel()
+        d2h = sum(host[name].numel() * host[name].element_size() for name in names)
+        return h2d, d2h
+
     @staticmethod
     def dense_policy(actions, counts):
         """Sparse (actions, counts) rows -> float64 pi[.., 3226] = counts / sum (MCTS.py:51-54, temp 1)."""

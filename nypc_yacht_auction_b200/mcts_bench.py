@@ -1,86 +1,223 @@
-"""MCTS self-play throughput lines for bench.py (BASELINE.json configs[2] and configs[3])."""
+"""MCTS self-play blocks of bench.py: BASELINE.json configs[2] (uniform prior, 25 sims, 4,096 games), configs[3]
+(AlphaZero self-play, random-init YachtNNet, 100 sims, 16,384 games) and configs[4] (1,048,576 games, 100 sims, sharded
+over the ranks and played in waves on one tree pool per GPU -- strong scaling).
+
+A bench "step" of these blocks is ONE FULL 48-ply episode of every game (Coach.executeEpisode, Coach.py:34-72): per ply
+numMCTSSims simulations, example recording, move sampling, transition.  Device time = CUDA events on the launch stream,
+barrier + synchronize on both sides, max over ranks.  The e2e figures go through the host-buffer call
+(BatchedSelfPlay.execute_episodes_host: start boards in pinned host memory -> examples in pinned host memory).
+"""
 from __future__ import annotations
 
 import time
 
+PLIES = 48
+# SURVEY.md section 8(d), algorithmic bytes per simulation: ~7.5 KB (uniform prior: prior rows + edges on a depth-2 path),
+# ~33 KB with the network (+ features + float32 logits written and read once).  The 16-bit figure is what THIS engine moves
+# by design: 236 B features + 3232 x 2 B logits written + 2 x L legal logits read (L ~ 910 on average) + 4 x L row write.
+ALGO_BYTES_UNIFORM = 7500
+ALGO_BYTES_NN_F32 = 33000
+ALGO_BYTES_NN_16 = 236 + 3232 * 2 + 2 * 910 + 4 * 910 + 3600 + 200
 
-def _run_selfplay(torch, dev, n, sims, evaluator, plies, warm_plies, seed, game_base, use_graph, arena_mb=None,
-                  dist=None, world=1):
-    from .coach import BatchedSelfPlay
-    sp = BatchedSelfPlay(n, sims, cpuct=1.5, evaluator=evaluator, temp_threshold=15, seed=seed, game_base=game_base,
-                         device=dev, arena_mb_per_game=arena_mb, record_examples=True)
-    if use_graph:
-        sp.mcts.capture_graph()
-    t = 0
-    for _ in range(warm_plies):
-        sp.play_ply(t)
-        t += 1
+
+def _fence(torch, dev, dist, world):
     torch.cuda.synchronize(dev)
     if world > 1:
         dist.barrier()
         torch.cuda.synchronize(dev)
+
+
+def _max_ranks(torch, dev, dist, world, x):
+    if world == 1:
+        return x
+    t = torch.tensor([x], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def _launches_per_episode(per_sim, sims):
+    # per move: features (+ canonical form), root counts, sparse root policy, overflow max, pick, transition, ply bump ~ 8
+    # small launches, plus the search: ONE launch (uniform prior, whole search fused: per_sim = 0), 2 per simulation
+    # (select, expand: uniform prior on the general path) or 3 (select, forward, expand: network)
+    return PLIES * (8 + (per_sim * sims if per_sim else 1))
+
+
+def selfplay_block(torch, dev, dist, rank, world, n, sims, evaluator, seed, steps, warm, use_graph=True, fuse_uniform=True,
+                   e2e_steps=1, arena_mb=None):
+    """`steps` full episodes of n games per rank after `warm` warm-up episodes."""
+    from .coach import BatchedSelfPlay
+    sp = BatchedSelfPlay(n, sims, cpuct=1.5, evaluator=evaluator, temp_threshold=15, seed=seed, game_base=rank * n, device=dev,
+                         arena_mb_per_game=arena_mb, record_examples=True)
+    uniform = getattr(sp.mcts.evaluator, "uniform", False)
+    sp.mcts.fuse_uniform = bool(fuse_uniform)
+    if use_graph and not (uniform and fuse_uniform):
+        sp.mcts.capture_graph()
+
+    peak_nodes = [0]
+
+    def episode():
+        sp.execute_episodes()
+        peak_nodes[0] = max(peak_nodes[0], int(sp.mcts.pool.node_counts().max().item()))   # live nodes after the last ply (pruned per round)
+        sp.next_episode()
+
+    for _ in range(warm):
+        episode()
+    _fence(torch, dev, dist, world)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    w0 = time.perf_counter()
     e0.record()
-    for _ in range(plies):
-        sp.play_ply(t)
-        t += 1
+    for _ in range(steps):
+        episode()
     e1.record()
-    torch.cuda.synchronize(dev)
-    ms = e0.elapsed_time(e1)
-    if world > 1:
-        dist.barrier()
-        t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-        ms = float(t_ms.item())
-    wall = time.perf_counter() - w0
+    _fence(torch, dev, dist, world)
+    ms = _max_ranks(torch, dev, dist, world, e0.elapsed_time(e1))
+    nodes = peak_nodes[0]
+    out = {"ms_per_step": ms / steps, "steps": steps, "warmup": warm,
+           "sims_per_sec": world * n * sims * PLIES * steps / (ms * 1e-3),
+           "game_steps_per_sec": world * n * PLIES * steps / (ms * 1e-3),
+           "gpu_launches": steps * _launches_per_episode(0 if (uniform and fuse_uniform) else (2 if uniform else 3), sims),
+           "pool_gb": sp.mcts.pool.bytes() / 1e9, "max_nodes_in_use": nodes}
+    if e2e_steps:
+        host = sp.host_buffers()
+        host["boards"].copy_(sp.env.states)                         # getInitBoard positions of the next episode, kept on the host
+        host["players"].copy_(sp.env.players)
+        h2d, d2h = sp.execute_episodes_host(host)                   # warm (pinned buffers touched)
+        _fence(torch, dev, dist, world)
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            h2d, d2h = sp.execute_episodes_host(host)
+        dt = _max_ranks(torch, dev, dist, world, time.perf_counter() - t0)
+        out["e2e"] = {"value": world * n * sims * PLIES * e2e_steps / dt, "unit": "sims/s",
+                      "game_steps_per_sec": world * n * PLIES * e2e_steps / dt,
+                      "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                      "api": "BatchedSelfPlay.execute_episodes_host: start boards + movers from pinned host memory -> 48 plies of "
+                             "MCTS self-play -> feature rows, sparse root visit counts, labels, outcomes into pinned host memory",
+                      "timing": "host wall clock around synchronous calls, max over ranks"}
+        del host
     sp.mcts.check_errors()
-    nodes = sp.mcts.pool.node_counts()
-    return {"ms": ms, "wall_s": wall, "sims": world * n * sims * plies, "game_steps": world * n * plies,
-            "sims_per_sec": world * n * sims * plies / (ms * 1e-3), "steps_per_sec": world * n * plies / (ms * 1e-3),
-            "pool_gb": sp.mcts.pool.bytes() / 1e9, "max_nodes_in_use": int(nodes.max().item()),
-            # per move: features, root counts, sparse root policy, pick, transition + the search itself (uniform prior:
-            # ONE launch for all simulations; network: select, forward, expand per simulation)
-            "launches": plies * (5 + (1 if getattr(evaluator, "uniform", False) else 3 * sims))}
+    del sp
+    torch.cuda.empty_cache()
+    return out
 
 
-def run(args, torch, dev, rank=0, world=1, dist=None):
-    from .mcts import UniformEvaluator, FusedYachtEvaluator
-    from .nnet import YachtPolicyValueNet
-    out = {}
-    # configs[2]: MCTS self-play, numMCTSSims=25, uniform prior (no NN), 4,096 concurrent games
-    r = _run_selfplay(torch, dev, 4096, 25, UniformEvaluator(), plies=24, warm_plies=6, seed=args.seed + 1,
-                      game_base=rank * 4096, use_graph=True, dist=dist, world=world)
-    out["mcts_uniform"] = {
-        "workload": "configs[2]: MCTS self-play numMCTSSims=25, uniform prior, 4096 games/GPU, cpuct 1.5, plies 6..29 of the episode",
-        "sims_per_sec": r["sims_per_sec"], "game_steps_per_sec": r["steps_per_sec"], "ms": r["ms"], "gpu_launches": r["launches"],
-        "pool_gb": r["pool_gb"], "max_nodes_in_use": r["max_nodes_in_use"]}
-    # configs[3]: AlphaZero self-play, random-init yacht NNet (H=256, 6 blocks), numMCTSSims=100, 16,384 games
-    torch.manual_seed(0)
-    net = YachtPolicyValueNet().to(dev)
-    ev = FusedYachtEvaluator(net, 16384)
-    r = _run_selfplay(torch, dev, 16384, 100, ev, plies=4, warm_plies=4, seed=args.seed + 2, game_base=rank * 16384,
-                      use_graph=True, dist=dist, world=world)
-    # the leaf evaluator alone: one whole-network forward over 16,384 leaves (CUDA events, 50 launches)
-    x = torch.rand((16384, 59), device=dev)
+def wave_breakdown(torch, dev, n, sims, evaluator, seed, plies_before=6, waves=60):
+    """Device time of the three kernels of one network simulation wave (select, forward, expand), each bracketed by CUDA
+    events on the launch stream, at a mid-game ply with warm trees; the NN share of the wave follows."""
+    from . import _lib
+    from .engine import BatchedYacht
+    from .mcts import BatchedMCTS
+    env = BatchedYacht(n, seed=seed, game_base=0, device=dev)
+    m = BatchedMCTS(env, sims, 1.5, evaluator=evaluator)
+    for _ in range(plies_before):
+        m.play_ply()
+    grp, lib, s = m.groups[0], m.lib, _lib.current_stream()
+    ev = grp.evaluator
+    tot = [0.0, 0.0, 0.0]
+    marks = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(waves)]
+    for sim in range(waves):
+        a = marks[sim]
+        a[0].record()
+        _lib.check(lib.ya_mcts_select(grp.ref, grp.states_ptr, env.n, _lib.ptr(grp.players), _lib.ptr(grp.ply), _lib.ptr(grp.episode),
+                                      env.seed, env.game_base, sim, None, None, m.cpuct, None, _lib.ptr(grp.features),
+                                      _lib.ptr(grp.need_eval), None, _lib.ptr(m.err_flag), s), "ya_mcts_select")
+        a[1].record()
+        pi, v = ev(grp.features, grp.need_eval, None)
+        a[2].record()
+        _lib.check(lib.ya_mcts_expand_logits(grp.ref, _lib.ptr(pi), 1 if pi.dtype == torch.float16 else 0, pi.shape[1],
+                                             _lib.ptr(ev.last_row_max), _lib.ptr(v), None, _lib.ptr(m.err_flag), s), "ya_mcts_expand_logits")
+        a[3].record()
+    torch.cuda.synchronize(dev)
+    m.check_errors()
+    for a in marks[5:]:
+        for i in range(3):
+            tot[i] += a[i].elapsed_time(a[i + 1])
+    k = len(marks) - 5
+    sel, fwd, exp = (1e3 * t / k for t in tot)
+    del m, env
+    torch.cuda.empty_cache()
+    return {"select_us": sel, "forward_us": fwd, "expand_us": exp, "nn_share_of_wave": fwd / (sel + fwd + exp),
+            "how": "CUDA events around each launch, %d waves at ply %d, eager (the graphed wave has no gaps between them)" % (k, plies_before)}
+
+
+def forward_alone(torch, dev, evaluator, leaves, reps=50):
+    x = torch.rand((leaves, 59), device=dev)
     for _ in range(5):
-        ev(x)
+        evaluator(x)
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
-    for _ in range(50):
-        ev(x)
+    for _ in range(reps):
+        evaluator(x)
     f1.record()
     torch.cuda.synchronize(dev)
-    fwd_us = f0.elapsed_time(f1) * 1000.0 / 50
-    real_flops = 2.0 * YachtPolicyValueNet.num_macs() * 16384
-    out["nn_forward"] = {"kernel": "ya_k_forward (tcgen05, bf16 operands, float32 accumulation)", "leaves": 16384,
-                         "us_per_launch": fwd_us, "tflops": real_flops / fwd_us * 1e-6,
-                         "note": "3.32 MFLOP per leaf (unpadded); 128 CTAs of 128 leaves on 148 SMs"}
-    out["mcts_nn"] = {
-        "workload": "configs[3]: AlphaZero self-play, random-init YachtNNet (hidden 256, 6 blocks; the whole forward is one tcgen05 kernel, csrc/ya_forward.cu, bf16 operands / float32 accumulation), "
-                    "numMCTSSims=100, 16384 games/GPU, one batched forward per simulation wave (3 launches per wave: select, forward, expand), "
-                    "softmax+mask fused into the expand kernel, plies 4..7",
-        "sims_per_sec": r["sims_per_sec"], "game_steps_per_sec": r["steps_per_sec"], "ms": r["ms"], "gpu_launches": r["launches"],
-        "pool_gb": r["pool_gb"], "max_nodes_in_use": r["max_nodes_in_use"],
-        "nn_flops_per_leaf": 2 * YachtPolicyValueNet.num_macs()}
+    return f0.elapsed_time(f1) * 1000.0 / reps
+
+
+def selfplay_1m(torch, dev, dist, rank, world, evaluator_factory, total, sims, wave, seed):
+    """configs[4]: `total` games split over the ranks by global game id (dist.shard_range), every rank plays its shard as
+    consecutive waves of `wave` games on ONE tree pool (coach.self_play_in_waves; simulation wave replayed as a CUDA graph),
+    and copies every wave's examples to pinned host memory.  STRONG scaling: total work is fixed."""
+    from .coach import self_play_in_waves
+    from .dist import shard_range
+    first, last = shard_range(total, rank, world)
+    mine = last - first
+    assert mine % wave == 0, "games per rank must be a multiple of the wave size"
+    ev = evaluator_factory(wave)
+    host = {}
+    tally = {"d2h": 0, "waves": 0}
+
+    def on_wave(w, ex):
+        for name in ("features", "actions", "counts", "value", "result_p1"):
+            if name not in host:
+                host[name] = torch.empty(ex[name].shape, dtype=ex[name].dtype, pin_memory=True)
+            host[name].copy_(ex[name], non_blocking=True)
+            tally["d2h"] += host[name].numel() * host[name].element_size()
+        tally["waves"] += 1
+
+    _fence(torch, dev, dist, world)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    p1, p2, dr = self_play_in_waves(mine, wave, sims, ev, first_game=first, on_wave=on_wave, use_graph=True, seed=seed, device=dev)
+    e1.record()
+    _fence(torch, dev, dist, world)
+    wall = _max_ranks(torch, dev, dist, world, time.perf_counter() - t0)
+    ms = _max_ranks(torch, dev, dist, world, e0.elapsed_time(e1))
+    res = torch.tensor([p1, p2, dr], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(res)
+    res = [int(x) for x in res.tolist()]
+    assert sum(res) == total, "every game must finish"
+    out = {"games": total, "games_per_gpu": mine, "wave_games": wave, "waves_per_gpu": tally["waves"], "num_mcts_sims": sims,
+           "seconds": ms * 1e-3, "wall_seconds": wall, "sims_per_sec": total * PLIES * sims / (ms * 1e-3),
+           "game_steps_per_sec": total * PLIES / (ms * 1e-3), "scaling": "strong",
+           "outcomes_p1_p2_draw": res, "d2h_bytes_per_gpu": tally["d2h"],
+           "gpu_launches_per_gpu": tally["waves"] * _launches_per_episode(3, sims),
+           "includes": "pool reset + re-deal per wave, example recording, device->host copy of every wave's examples (pinned)"}
+    del host
+    torch.cuda.empty_cache()
     return out
+
+
+def shard_invariance_check(torch, dev, dist, rank, world, net, total=64, sims=16, seed=77):
+    """N > 1: `total` games sharded over the ranks, each shard played as two graphed waves with the network evaluator,
+    all-gathered over NCCL and compared on rank 0 with one single-process batch of all games.  Returns "ok" or raises."""
+    from .coach import BatchedSelfPlay, self_play_in_waves
+    from .dist import allgather_examples, shard_range
+    from .mcts import FusedYachtEvaluator
+    first, last = shard_range(total, rank, world)
+    per = last - first
+    assert per % 2 == 0
+    parts = []
+    self_play_in_waves(per, per // 2, sims, FusedYachtEvaluator(net, per // 2), first_game=first, use_graph=True, seed=seed, device=dev,
+                       on_wave=lambda w, ex: parts.append({k: v.clone() for k, v in ex.items()}))
+    names = ("features", "actions", "counts", "value", "result_p1")
+    mine = {k: torch.cat([p[k] for p in parts], dim=0 if parts[0][k].dim() == 1 else 1) for k in names}
+    full = allgather_examples(mine)
+    ok = torch.ones(1, dtype=torch.int32, device=dev)
+    if rank == 0:
+        ref = BatchedSelfPlay(total, sims, evaluator=FusedYachtEvaluator(net, total), seed=seed, game_base=0, device=dev).execute_episodes()
+        ok[0] = int(all(torch.equal(full[k], ref[k]) for k in names))
+    dist.broadcast(ok, src=0)
+    if int(ok.item()) != 1:
+        raise AssertionError("sharded self-play differs from the single-process run")
+    torch.cuda.empty_cache()
+    return "ok"

@@ -1,8 +1,9 @@
 """Leaf evaluator network: state-dict compatible with the reference's YachtNNet
 (/root/reference/yacht/pytorch/YachtNNet.py:8-70; keys inp.0/1, blocks.i.fc1/ln1/fc2/ln2, pi_head.0/2,
-v_head.0/2/4) so checkpoints written by yacht/NNet.py:198-205 load unchanged.  Inference only: this is
-the one dense contraction of the path and stays a single batched PyTorch (cuBLASLt) call per
-simulation wave, as BASELINE.json's north star prescribes; dropout is a no-op in eval mode.
+v_head.0/2/4) so checkpoints written by yacht/NNet.py:198-205 load unchanged.  This module only HOLDS the weights
+(and is the float32 yardstick of the tests): on the self-play path the forward of a whole simulation wave is the one
+hand-written tcgen05 kernel csrc/ya_forward.cu, fed from this state dict by mcts.FusedYachtEvaluator.  Dropout is a
+no-op in eval mode and is omitted.
 """
 from __future__ import annotations
 

@@ -5,7 +5,7 @@ Pure-Python restatement of the reference's Yacht-Auction rules (reference file
 independently (histogram-based scoring, index-pair boards, explicit draw objects) and is
 pinned against the reference itself by ``tests/golden/make_golden.py`` +
 ``tests/test_oracle_vs_golden.py`` and, when ``/root/reference`` is present, by the
-side-by-side test ``tests/test_oracle_vs_reference.py``.
+side-by-side test ``tests/test_reference_interop.py``.
 
 Small cases only (pure-Python loops).  The bulk oracle is ``oracle/yacht_oracle.c``.
 """

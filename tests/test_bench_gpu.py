@@ -30,6 +30,25 @@ def test_bench_json_line_has_every_contract_key():
     assert d["value"] > 1e8
 
 
+def test_bench_mcts_blocks_are_first_class():
+    """The MCTS half of the metric: configs[2], [3], [4] blocks each carry sims/s over full episodes, a roofline and an
+    end-to-end figure through host buffers (configs[4] shrunk to 32,768 games to keep the test short)."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "3", "--warmup", "3", "--no-cpu-baseline",
+                        "--games-1m", "32768"], capture_output=True, text=True, cwd=ROOT, timeout=900)
+    assert r.returncode == 0, r.stderr[-3000:]
+    d = json.loads([l for l in r.stdout.splitlines() if l.strip()][-1])
+    assert d["sustained"]["seconds"] >= 2.0 and d["sustained"]["clocks"]["samples"] >= 10
+    for name in ("mcts_uniform", "mcts_nn", "mcts_nn_1m"):
+        b = d[name]
+        assert b["sims_per_sec"] > 1e6 and b["unit"] == "sims/s", name
+        assert b["roofline"]["bound"] == "hbm" and 0 < b["roofline"]["frac"] < 1.2, name
+        assert b["e2e"]["value"] > 0 and b["e2e"]["d2h_bytes_per_step"] > 0, name
+    assert d["mcts_uniform"]["general_path"]["sims_per_sec"] > 1e6
+    assert 0 < d["mcts_nn"]["nn_share_of_time"] < 1 and d["mcts_nn"]["roofline_forward"]["bound"] == "tensor"
+    assert d["mcts_nn_1m"]["games"] == 32768 and sum(d["mcts_nn_1m"]["outcomes_p1_p2_draw"]) == 32768
+    assert d["dropin_mcts"]["sims_per_sec"] > 0
+
+
 def test_size_edge_cases():
     from nypc_yacht_auction_b200 import _lib
     from nypc_yacht_auction_b200.engine import BatchedYacht
