@@ -77,7 +77,7 @@ def test_bot_process_speaks_the_protocol():
         put = ask("SCORE", True).split()
         assert time.perf_counter() - t0 < 0.5
         assert put[0] == "PUT" and put[1] in jb.CATEGORIES and len(put[2]) == 5
-        ask("SET CHOICE 44421" if bid[1] else "", False)
+        ask("SET LARGE_STRAIGHT 23456", False)                     # the opponent holds round 2's bundle B whatever we bid
         ask("FINISH", False)
         assert proc.wait(timeout=30) == 0
     finally:
