@@ -119,6 +119,14 @@ typedef struct {
     int64_t arena_words;
 } ya_mcts_tree;
 
+/* Row storage of a pool (fixed for the life of its trees; ya_mcts_reset in between): float32 prior rows (any float32
+ * policy through ya_mcts_expand: the bit-exact reference arithmetic), or the leaf's legal policy-head logits kept as 16-bit
+ * values + one exponent offset per node (ya_mcts_expand_logits; half the bytes, priors evaluated on the fly with the same
+ * FMA + EX2 that would have produced the stored float32 value). */
+#define YA_ROWS_F32 0
+#define YA_ROWS_FP16 2
+#define YA_ROWS_BF16 3
+
 int ya_mcts_cursor_words(void);
 int ya_mcts_node_words(void);
 
@@ -133,12 +141,16 @@ int ya_mcts_reset(const ya_mcts_tree* tree, const uint8_t* which, void* stream);
  * is not NULL the simulation index is read from it, and if game_base_ptr (device) is not NULL the global id of game 0
  * is read from it instead of `game_base`, so one captured CUDA graph can be replayed for every simulation and for
  * every wave of games that shares the pool (a captured launch freezes its by-value arguments).
+ * rows = YA_ROWS_*: how this pool stores priors.  leaf_dst / leaf_desc (device, uint64[n] / uint32[n], both or neither;
+ * logit-row pools): for every leaf that needs the evaluator, the device address of its row's logit area and its legal-mask
+ * descriptor (0 / 0 otherwise) -- the scatter targets ya_nn_forward's policy-head epilogue writes the legal logits to.
  * cpuct must be >= 0 (main.py:25 uses 1.5): the unvisited arg-max goes through per-group maxima of the priors,
  * which needs cpuct * P * sqrt(Ns + EPS) to be monotone in P; a negative value is rejected (invalid value). */
 int ya_mcts_select(const ya_mcts_tree* tree, const uint32_t* states, int64_t stride, const int8_t* players,
                    const int32_t* ply, const uint32_t* episode, uint64_t seed, uint64_t game_base, uint32_t sim,
                    const uint32_t* sim_ptr, const uint64_t* game_base_ptr, float cpuct, const uint8_t* active,
-                   float* features, uint8_t* need_eval, uint32_t* leaf_states, int32_t* err_flag, void* stream);
+                   float* features, uint8_t* need_eval, uint32_t* leaf_states, int rows, uint64_t* leaf_dst,
+                   uint32_t* leaf_desc, int32_t* err_flag, void* stream);
 
 /* The same descent with the dice of in-search transitions supplied by the HOST (the reference rolls them
  * from the global numpy / random streams through roll_five / tiebreak_uniform, yacht/YachtGame.py:154-159,
@@ -157,12 +169,15 @@ int ya_mcts_select_injected(const ya_mcts_tree* tree, const uint32_t* states, in
 int ya_mcts_expand(const ya_mcts_tree* tree, const float* pi, const float* value, int uniform, float uniform_p,
                    float uniform_v, uint32_t* sim_counter, int32_t* err_flag, void* stream);
 
-/* Same as ya_mcts_expand, fed with the raw policy-head output: 16-bit logits [n][ld] (IEEE half if fp16 != 0, else
- * bfloat16; ld >= 3232 and a multiple of 8, e.g. the head padded to 3232 columns; base 16-byte aligned).  The softmax of NNetWrapper.predict
- * (yacht/NNet.py:193), masking and renormalisation (MCTS.py:88-101) are fused:
- * P[a] = exp(l[a] - max) / sum over legal a' of exp(l[a'] - max), float32, max taken over all 3,226 logits;
- * only the legal logits are read, neither float32 logits nor pi are ever written to HBM.
- * row_max float32[n] = that per-row maximum (written by ya_nn_forward), or NULL: the kernel scans the row. */
+/* Leaf expansion + backup for logit-row pools (ya_mcts_select with rows = YA_ROWS_FP16 / YA_ROWS_BF16, fp16 saying which).
+ * The softmax of NNetWrapper.predict (yacht/NNet.py:193), masking and renormalisation (MCTS.py:88-101) are fused:
+ * P[a] = exp(l[a] - max) / sum over legal a' of exp(l[a'] - max) = 2^(l[a] * log2(e) + off), max taken over all 3,226
+ * logits, off stored per node; neither float32 logits nor pi nor float32 priors are ever written to memory.
+ *   logits16 == NULL: the rows were filled by ya_nn_forward's epilogue (scatter targets from ya_mcts_select); row_max
+ *                     (written by the same forward) is required.
+ *   logits16 != NULL: a dense 16-bit logit matrix [n][ld] from any evaluator (ld >= 3232 and a multiple of 8, e.g. the
+ *                     head padded to 3232 columns; base 16-byte aligned); the legal entries are compacted into the rows
+ *                     here.  row_max float32[n] = per-row maximum over the 3,226 columns, or NULL: the kernel scans the row. */
 int ya_mcts_expand_logits(const ya_mcts_tree* tree, const void* logits16, int fp16, int64_t ld, const float* row_max,
                           const float* value, uint32_t* sim_counter, int32_t* err_flag, void* stream);
 
@@ -205,10 +220,14 @@ int ya_mcts_pick_action(const int32_t* counts, const int32_t* ply, const uint32_
  * parameters as float32.  offsets (HOST pointer, int64[9]) = byte offsets {w_in, w_trunk, w_v, w_pi} and float
  * offsets {p_in, p_trunk, p_v, p_pi_ln, p_pi_bias}.  hidden width 256 only.  Rows are independent of the
  * batch they sit in (batch-invariant evaluator).  row_max float32[n] (may be NULL) receives each row's largest
- * logit over the 3,226 real columns, for ya_mcts_expand_logits. */
+ * logit over the 3,226 real columns, for ya_mcts_expand_logits.
+ * scatter_dst / scatter_desc (device, uint64[n] / uint32[n], both or neither; written by ya_mcts_select): the policy-head
+ * epilogue writes row g's LEGAL logits (legal-mask descriptor scatter_desc[g]), in legal order, to the device address
+ * scatter_dst[g] -- the leaf's row in the tree pool -- and skips rows with address 0 (MCTS.py:86-101: the mask is applied
+ * where the logits are produced).  logits16 may then be NULL: no dense logit matrix is written at all. */
 int ya_nn_forward(const float* features, void* logits16, float* values, float* row_max, const void* weight_blob,
                   const float* param_blob, const int64_t* offsets, int nblocks, int64_t n, float eps, int fp16,
-                  void* stream);
+                  const uint64_t* scatter_dst, const uint32_t* scatter_desc, void* stream);
 
 /* ---- host-buffer variants (end-to-end path for callers that keep boards in host memory) ----
  * ya_host_create allocates the device mirror for n games once (no allocation per call);

@@ -35,7 +35,8 @@ SIGNATURES = {
     "ya_mcts_cursor_words": [],
     "ya_mcts_node_words": [],
     "ya_mcts_reset": [_vp, _vp, _vp],
-    "ya_mcts_select": [_vp, _vp, _i64, _vp, _vp, _vp, _u64, _u64, _u32, _vp, _vp, ctypes.c_float, _vp, _vp, _vp, _vp, _vp, _vp],
+    "ya_mcts_select": [_vp, _vp, _i64, _vp, _vp, _vp, _u64, _u64, _u32, _vp, _vp, ctypes.c_float, _vp, _vp, _vp, _vp, _int, _vp, _vp,
+                       _vp, _vp],
     "ya_mcts_select_injected": [_vp, _vp, _i64, _vp, _u32, ctypes.c_float, _vp, _int, _vp, _vp, _vp, _vp, _vp],
     "ya_mcts_expand": [_vp, _vp, _vp, _int, ctypes.c_float, ctypes.c_float, _vp, _vp, _vp],
     "ya_mcts_expand_logits": [_vp, _vp, _int, _i64, _vp, _vp, _vp, _vp, _vp],
@@ -44,7 +45,7 @@ SIGNATURES = {
     "ya_mcts_root_counts": [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp],
     "ya_mcts_root_sparse": [_vp, _vp, _i64, _vp, _int, _vp, _vp, _vp, _vp],
     "ya_mcts_pick_action": [_vp, _vp, _vp, _i64, _u64, _u64, _int, _vp, _vp],
-    "ya_nn_forward": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _int, _i64, ctypes.c_float, _int, _vp],
+    "ya_nn_forward": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _int, _i64, ctypes.c_float, _int, _vp, _vp, _vp],
     "ya_host_create": [_i64, _int, ctypes.POINTER(ctypes.c_void_p)],
     "ya_host_destroy": [_vp],
     "ya_host_play_ply": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _u64, _u64, _int],

@@ -75,7 +75,8 @@ __device__ __forceinline__ void pack_store_a(uint8_t* a_tile, int row, int c8_fi
 template <bool F16>
 __global__ void __launch_bounds__(kThreads, 1)
 ya_k_forward(const float* __restrict__ features, uint16_t* __restrict__ logits, float* __restrict__ values,
-             float* __restrict__ row_max, const uint8_t* __restrict__ wblob, const float* __restrict__ pblob, Blob off, int nblocks, int64_t n, float eps) {
+             float* __restrict__ row_max, const uint8_t* __restrict__ wblob, const float* __restrict__ pblob, Blob off, int nblocks, int64_t n, float eps,
+             const uint64_t* __restrict__ scatter_dst, const uint32_t* __restrict__ scatter_desc) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* a_tile = base;
@@ -447,6 +448,15 @@ ya_k_forward(const float* __restrict__ features, uint16_t* __restrict__ logits, 
         __syncthreads();                                              // the A tile (p) is complete
         tc_fence_after();
         float row_mx[2] = {-3.0e38f, -3.0e38f};
+        // Scatter mode (the MCTS path): this row's LEGAL logits go straight into its leaf's row in the tree pool, in legal
+        // order (the row layout ya_mcts_select allocated: csrc/ya_mcts.cu "ROWS_L16"), instead of a dense [n][3232] matrix.
+        // dst = 0: the row needs no evaluation (its descent ended in a terminal / dead-end node).
+        uint16_t* s_dst = nullptr;
+        uint32_t s_desc = 0;
+        if (scatter_dst && grow < n) {
+            s_dst = reinterpret_cast<uint16_t*>(scatter_dst[grow]);
+            s_desc = s_dst ? scatter_desc[grow] : 0u;
+        }
         if (producer) {
             // Producer: keeps the tensor pipe fed.  Weight slots, accumulators (TMEM columns 128 / 256 / 384) and their
             // barriers all cycle with period 3: tile j needs its weights (requested two tiles ago) and the accumulator
@@ -497,7 +507,46 @@ ya_k_forward(const float* __restrict__ features, uint16_t* __restrict__ logits, 
                             for (int i = 0; i < 32; ++i) if (col0 + i < kActions) m = fmaxf(m, f[i]);
                         }
                         row_mx[q] = m;
-                        if (grow < n) {
+                        if (s_desc) {
+                            // Runs of the action space: r = 0 bids [0, 202), r = c + 1 category c [202 + 252 c, +252).  A 32-column
+                            // chunk meets at most two runs; run starts are even, so a packed pair never straddles one.
+                            const int r0 = ((col0 + 50) * 4162) >> 20;
+                            const int end0 = 202 + 252 * r0;                               // first column of run r0 + 1
+                            const int start0 = r0 ? end0 - 252 : 0;
+                            if (s_desc & 1u) {                                             // bid row: legal index = column
+                                if (r0 == 0) {
+#pragma unroll
+                                    for (int i = 0; i < 16; ++i)
+                                        if (col0 + 2 * i < 202)
+                                            *reinterpret_cast<uint32_t*>(s_dst + col0 + 2 * i) = pack2<F16>(f[2 * i], f[2 * i + 1]);
+                                }
+                            } else if (s_desc >> 13) {                                     // ten dice: 252 subsets per open category
+                                const uint32_t open = (s_desc >> 1) & 0xFFFu;              // bit c = category c open
+                                const bool ok0 = r0 > 0 && ((open >> (r0 - 1)) & 1u);
+                                const bool ok1 = r0 < 12 && ((open >> r0) & 1u);
+                                const int base0 = r0 > 0 ? 252 * __popc(open & ((1u << (r0 - 1)) - 1u)) : 0;
+                                const int d0 = base0 - start0;                             // legal index = column + d0 inside run r0
+                                const int d1 = base0 + (ok0 ? 252 : 0) - end0;             // ... and inside run r0 + 1
+                                if (ok0 || (ok1 && end0 < col0 + 32)) {
+#pragma unroll
+                                    for (int i = 0; i < 16; ++i) {
+                                        const int c = col0 + 2 * i;
+                                        const bool first = c < end0;
+                                        if (first ? ok0 : ok1)
+                                            *reinterpret_cast<uint32_t*>(s_dst + c + (first ? d0 : d1)) = pack2<F16>(f[2 * i], f[2 * i + 1]);
+                                    }
+                                }
+                            } else {                                                       // five dice: subset 0 of every open category
+                                const uint32_t open = (s_desc >> 1) & 0xFFFu;
+                                if (end0 < col0 + 32 && r0 < 12 && ((open >> r0) & 1u)) {    // category r0 starts in this chunk (run starts are
+                                    uint16_t* one = s_dst + __popc(open & ((1u << r0) - 1u));   // never chunk-aligned: 202 + 252 c = 2 mod 4)
+#pragma unroll
+                                    for (int i = 0; i < 16; ++i)
+                                        if (col0 + 2 * i == end0) *one = (uint16_t)(pack2<F16>(f[2 * i], f[2 * i + 1]) & 0xFFFFu);
+                                }
+                            }
+                        }
+                        if (logits && grow < n) {
                             uint32_t p[16];
 #pragma unroll
                             for (int i = 0; i < 16; ++i) p[i] = pack2<F16>(f[2 * i], f[2 * i + 1]);
@@ -536,10 +585,11 @@ extern "C" int ya_debug_forward_timeline(unsigned long long* host_out) {
 
 extern "C" int ya_nn_forward(const float* features, void* logits16, float* values, float* row_max, const void* weight_blob,
                              const float* param_blob, const int64_t* offsets, int nblocks, int64_t n, float eps, int fp16,
-                             void* stream) {
+                             const uint64_t* scatter_dst, const uint32_t* scatter_desc, void* stream) {
     if (n <= 0) return 0;
     if ((reinterpret_cast<uintptr_t>(logits16) | reinterpret_cast<uintptr_t>(weight_blob) |
          reinterpret_cast<uintptr_t>(param_blob)) & 31u) return (int)cudaErrorMisalignedAddress;
+    if ((scatter_dst == nullptr) != (scatter_desc == nullptr) || (!logits16 && !scatter_dst)) return (int)cudaErrorInvalidValue;
     // the opt-in to > 48 KB of dynamic shared memory is a per-DEVICE function attribute: one flag per device and
     // kernel variant (set twice by racing threads is harmless; the flag is only published after the call succeeded)
     static std::atomic<bool> configured[2][64];
@@ -558,10 +608,10 @@ extern "C" int ya_nn_forward(const float* features, void* logits16, float* value
     if (fp16)
         ya_k_forward<true><<<blocks, kThreads, kSmemBytes, (cudaStream_t)stream>>>(
             features, static_cast<uint16_t*>(logits16), values, row_max, static_cast<const uint8_t*>(weight_blob), param_blob, off,
-            nblocks, n, eps);
+            nblocks, n, eps, scatter_dst, scatter_desc);
     else
         ya_k_forward<false><<<blocks, kThreads, kSmemBytes, (cudaStream_t)stream>>>(
             features, static_cast<uint16_t*>(logits16), values, row_max, static_cast<const uint8_t*>(weight_blob), param_blob, off,
-            nblocks, n, eps);
+            nblocks, n, eps, scatter_dst, scatter_desc);
     return (int)cudaGetLastError();
 }

@@ -94,6 +94,29 @@ __device__ __forceinline__ Edges edges_at(uint32_t* base, int cap) {
     return e;
 }
 
+// Row storage of a tree pool (one per pool, fixed by the caller):
+//   ROWS_F32    float32 prior rows as above (any float32 policy: ya_mcts_expand; the bit-exact reference path)
+//   ROWS_CONST  one prior value per node + a visited bitmask (ya_k_mcts_search_uniform)
+//   ROWS_L16F / ROWS_L16B   the leaf's LEGAL policy-head logits as they left the tensor core, 16 bits each (IEEE half /
+//               bfloat16), written straight into the row by the forward kernel's epilogue, + one exponent offset per node:
+//               P[a] = 2^(l[a] * log2(e) + off), off = -max * log2(e) - log2(sum over legal of 2^((l - max) * log2(e))),
+//               evaluated where a prior is needed (one FMA + one EX2, the same two instructions that would have produced
+//               a stored float32 prior, so the values are bit-identical to storing them); half the bytes of a float32 row.
+//               Layout from N_PRIOR: ceil(L / 2) words of logits padded to 4 words | ceil(L / 32) group maxima (1 + bits of
+//               the largest unvisited P, 0 = none) | ceil(L / 32) words of visited bits.  A leaf whose legal moves all
+//               underflowed (MCTS.py:97-101) becomes a constant-prior node (N_KIND 1, P = 1 / L) on the same visited bits.
+enum { ROWS_F32 = 0, ROWS_CONST = 1, ROWS_L16F = 2, ROWS_L16B = 3 };
+__device__ __forceinline__ int l16_logit_words(int L) { return (((L + 1) >> 1) + 3) & ~3; }
+__device__ __forceinline__ int l16_words(int L) { return l16_logit_words(L) + 2 * ((L + 31) >> 5); }
+template <int ROWS> __device__ __forceinline__ float l16_value(uint32_t h) {         // one 16-bit logit -> float32
+    return ROWS == ROWS_L16F ? __half2float(__ushort_as_half((unsigned short)h)) : __uint_as_float(h << 16);
+}
+constexpr float kLog2e = 1.4426950408889634f;
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+template <int ROWS> __device__ __forceinline__ float l16_prior(uint32_t h, float off) {
+    return ex2_approx(fmaf(l16_value<ROWS>(h), kLog2e, off));
+}
+
 // writes priors [k0, k0 + 32) of a fresh row (one per lane; lanes with k >= L idle) and the group's maximum
 __device__ __forceinline__ void store_prior_group(float* __restrict__ row, int L, int k0, float p, int lane) {
     const int k = k0 + lane;
@@ -166,9 +189,9 @@ __device__ __forceinline__ double es_as_double(float es) {       // getGameEnded
 }
 
 // ---------------------------------------------------------------- UCB argmax (MCTS.py:117-133)
-// CONST_ROWS: the walk may meet constant-prior nodes (only ya_k_mcts_search_uniform creates them, and a tree pool is
+// ROWS: the row storage of this pool (constant-prior nodes: only ya_k_mcts_search_uniform creates them, and a tree pool is
 // driven either by that kernel or by select / expand -- mcts.BatchedMCTS fixes the choice at construction).
-template <bool CONST_ROWS, int W>
+template <int ROWS, int W>
 __device__ __forceinline__ int ucb_select(const View& v, const uint32_t* node, int L, float cpuct, const Team<W>& tm) {
     const int sub = tm.sub;
     const uint32_t visits = node[N_VISITS];
@@ -186,7 +209,7 @@ __device__ __forceinline__ int ucb_select(const View& v, const uint32_t* node, i
             if (ou > best || (ou == best && oi < besti)) { best = ou; besti = oi; }
         }
     };
-    if (CONST_ROWS && node[N_KIND]) {
+    if (ROWS != ROWS_F32 && (ROWS == ROWS_CONST || node[N_KIND] == 1)) {
         // constant prior p: every unvisited child has the same u, so the lowest unvisited index wins among them
         const float cp = __fmul_rn(cpuct, __uint_as_float(node[N_PCONST]));
         if (n_edges > 0) {
@@ -209,6 +232,81 @@ __device__ __forceinline__ int ucb_select(const View& v, const uint32_t* node, i
         if (first != 0x7FFFFFFF) {
             const float u = __fmul_rn(cp, sq_new);
             if (u > best || (u == best && first < besti)) { best = u; besti = first; }
+        }
+        team_argmax();
+        return besti;
+    }
+    if (ROWS >= ROWS_L16F) {
+        // 16-bit logit row: the same arithmetic on P = 2^(l * log2(e) + off), evaluated on the fly
+        const int lw = l16_logit_words(L), nb = (L + 31) >> 5;
+        const uint16_t* lg = reinterpret_cast<const uint16_t*>(row);
+        const float off = __uint_as_float(node[N_PCONST]);
+        if (n_edges > 0) {
+            const Edges ed = edges_at(v.arena + node[N_EDGES], edge_cap(n_edges));
+            for (int e0 = 0; e0 < n_edges; e0 += 2 * W) {
+                int ai[2];
+                uint32_t nsa[2], lb[2];
+                double q[2];
+#pragma unroll
+                for (int t = 0; t < 2; ++t) {
+                    const int e = e0 + W * t + sub;
+                    const bool ok = e < n_edges;
+                    ai[t] = ok ? (int)ed.idx[e] : 0;
+                    nsa[t] = ok ? ed.nsa[e] & 0x7FFFFFFFu : 0u;
+                    q[t] = ok ? ed.q[e] : 0.0;
+                }
+#pragma unroll
+                for (int t = 0; t < 2; ++t) lb[t] = lg[ai[t]];
+#pragma unroll
+                for (int t = 0; t < 2; ++t) {
+                    if (e0 + W * t + sub < n_edges) {
+                        float x = __fmul_rn(__fmul_rn(cpuct, l16_prior<ROWS>(lb[t], off)), sq_old);
+                        x = __fdiv_rn(x, (float)(1u + nsa[t]));
+                        float u = __fadd_rn((float)q[t], x);
+                        if (u > best || (u == best && ai[t] < besti)) { best = u; besti = ai[t]; }
+                    }
+                }
+            }
+        }
+        const uint32_t* gmax = row + lw;
+        float gu = -CUDART_INF_F;
+        int gb = 0x7FFFFFFF;
+        for (int b = sub; b < nb; b += W) {
+            uint32_t e = gmax[b];
+            if (e) {
+                float u = __fmul_rn(__fmul_rn(cpuct, __uint_as_float(e - 1u)), sq_new);
+                if (u > gu) { gu = u; gb = b; }
+            }
+        }
+#pragma unroll
+        for (int o = W / 2; o; o >>= 1) {
+            float ou = tm.xor_(gu, o);
+            int ob = tm.xor_(gb, o);
+            if (ou > gu || (ou == gu && ob < gb)) { gu = ou; gb = ob; }
+        }
+        if (gb != 0x7FFFFFFF) {
+            const uint32_t seen = row[lw + nb + gb];
+            constexpr int kPer = 32 / W;                                // consecutive logits of the group per lane
+            const int i0 = (gb << 5) + sub * kPer;
+            auto consider = [&](int i, uint32_t h) {
+                if (i < L && !((seen >> (i & 31)) & 1u)) {
+                    float u = __fmul_rn(__fmul_rn(cpuct, l16_prior<ROWS>(h, off)), sq_new);
+                    if (u > best || (u == best && i < besti)) { best = u; besti = i; }
+                }
+            };
+            if (kPer == 1) {
+                if (i0 < L) consider(i0, lg[i0]);
+            } else {
+#pragma unroll
+                for (int t = 0; t < kPer / 2; ++t) {
+                    const int i = i0 + 2 * t;
+                    if (i < L) {                                        // the pair's word lies inside the logit area
+                        const uint32_t w2 = row[i >> 1];
+                        consider(i, w2 & 0xFFFFu);
+                        consider(i + 1, w2 >> 16);
+                    }
+                }
+            }
         }
         team_argmax();
         return besti;
@@ -282,7 +380,7 @@ __device__ __forceinline__ int ucb_select(const View& v, const uint32_t* node, i
 
 // ---------------------------------------------------------------- backup (MCTS.py:152-164)
 // Returns false if the arena overflowed.
-template <int W>
+template <int ROWS, int W>
 __device__ __forceinline__ bool backup_edge(const View& v, uint32_t* node, int ai, const Val& val, uint32_t& arena_top,
                                             const Team<W>& tm) {
     const int sub = tm.sub;
@@ -345,8 +443,12 @@ __device__ __forceinline__ bool backup_edge(const View& v, uint32_t* node, int a
             ed.nsa[n_edges] = 1u | (val.is_f32 ? 0u : 0x80000000u);        // Qsa = v, Nsa = 1
             ed.q[n_edges] = val.d;
             node[N_NEDGE] = (uint32_t)(n_edges + 1);
-            if (node[N_KIND]) {
+            if (ROWS != ROWS_F32 && (ROWS == ROWS_CONST || node[N_KIND] == 1)) {
                 v.arena[node[N_PRIOR] + (ai >> 5)] |= 1u << (ai & 31);      // constant-prior node: visited bitmask
+            } else if (ROWS >= ROWS_L16F) {
+                const int Ln = ya_legal_count(node[N_DESC]);
+                v.arena[node[N_PRIOR] + l16_logit_words(Ln) + ((Ln + 31) >> 5) + (ai >> 5)] |= 1u << (ai & 31);
+                fresh = 1;
             } else {
                 v.arena[node[N_PRIOR] + ai] |= 0x80000000u;                 // mark the prior entry as visited
                 fresh = 1;
@@ -360,24 +462,38 @@ __device__ __forceinline__ bool backup_edge(const View& v, uint32_t* node, int a
         const int L = ya_legal_count(node[N_DESC]);
         uint32_t* row = v.arena + node[N_PRIOR];
         uint32_t e = 0;
+        if (ROWS >= ROWS_L16F) {
+            const int lw = l16_logit_words(L), nb = (L + 31) >> 5;
+            const uint32_t seen = row[lw + nb + (ai >> 5)];
+            const float off = __uint_as_float(node[N_PCONST]);
+            const uint16_t* lg = reinterpret_cast<const uint16_t*>(row);
 #pragma unroll
-        for (int t = 0; t < 32 / W; ++t) {
-            const int i = (ai & ~31) + t * W + sub;
-            if (i < L) { uint32_t b = row[i]; if (!(b >> 31)) e = max(e, b + 1u); }
+            for (int t = 0; t < 32 / W; ++t) {
+                const int i = (ai & ~31) + t * W + sub;
+                if (i < L && !((seen >> (i & 31)) & 1u)) e = max(e, __float_as_uint(l16_prior<ROWS>(lg[i], off)) + 1u);
+            }
+            e = tm.reduce_max(e);
+            if (sub == 0) row[lw + (ai >> 5)] = e;
+        } else {
+#pragma unroll
+            for (int t = 0; t < 32 / W; ++t) {
+                const int i = (ai & ~31) + t * W + sub;
+                if (i < L) { uint32_t b = row[i]; if (!(b >> 31)) e = max(e, b + 1u); }
+            }
+            e = tm.reduce_max(e);
+            if (sub == 0) row[group_max_at(L) + (ai >> 5)] = e;
         }
-        e = tm.reduce_max(e);
-        if (sub == 0) row[group_max_at(L) + (ai >> 5)] = e;
         tm.sync();
     }
     return !failed;
 }
 
-template <int W>
+template <int ROWS, int W>
 __device__ __forceinline__ bool backup_path(const View& v, int depth, Val ret, uint32_t& arena_top, const Team<W>& tm) {
     for (int d = depth - 1; d >= 0; --d) {
         uint32_t pe = v.cur[C_PATH + d];
         uint32_t* node = v.nodes + (int64_t)(pe & 0xFFFFu) * kNodeWords;
-        if (!backup_edge(v, node, (int)(pe >> 16), ret, arena_top, tm)) return false;
+        if (!backup_edge<ROWS>(v, node, (int)(pe >> 16), ret, arena_top, tm)) return false;
         ret.d = -ret.d;                                              // return -v
     }
     return true;
@@ -421,7 +537,7 @@ struct DrawSource {
 // state), KIND_DONE (terminal / dead end: w.ret is the value returned by the deepest call), KIND_NEED_DRAW
 // (injected mode only: the chosen transition needs dice the host has not supplied yet; w.leaf / w.depth /
 // w.pending describe where to resume) or KIND_ERROR.
-template <bool FEATURES, bool INJECT, bool CONST_ROWS, int W>
+template <bool FEATURES, bool INJECT, int ROWS, int W>
 __device__ __forceinline__ void descend(const View& v, YaState cur, Walk& w, uint64_t seed, uint32_t gid, uint32_t ep,
                                         uint32_t pl, uint32_t sim, float cpuct, float* __restrict__ feat_row,
                                         const Team<W>& tm, DrawSource src = DrawSource{nullptr, 0}) {
@@ -449,7 +565,7 @@ __device__ __forceinline__ void descend(const View& v, YaState cur, Walk& w, uin
                 int L = ya_legal_count(desc);
                 uint32_t row_at = (w.arena_top + 3u) & ~3u;         // 16-byte aligned prior rows
                 if ((int)w.node_count >= v.max_nodes) { w.err = E_NODES_FULL; w.kind = KIND_ERROR; break; }
-                const uint32_t words = CONST_ROWS ? (uint32_t)((L + 31) >> 5) : (uint32_t)row_words(L);
+                const uint32_t words = ROWS == ROWS_CONST ? (uint32_t)((L + 31) >> 5) : ROWS >= ROWS_L16F ? (uint32_t)l16_words(L) : (uint32_t)row_words(L);
                 if (row_at + words > v.arena_words) { w.err = E_ARENA_FULL; w.kind = KIND_ERROR; break; }
                 idx = (int)w.node_count;
                 if (lane == 0) {
@@ -457,7 +573,7 @@ __device__ __forceinline__ void descend(const View& v, YaState cur, Walk& w, uin
 #pragma unroll
                     for (int i = 0; i < 8; ++i) nd[N_KEY + i] = cur.w[i];
                     nd[N_DESC] = desc; nd[N_VISITS] = 0; nd[N_PRIOR] = row_at; nd[N_EDGES] = 0; nd[N_NEDGE] = 0;
-                    nd[N_KIND] = CONST_ROWS ? 1u : 0u; nd[N_PCONST] = 0;
+                    nd[N_KIND] = ROWS == ROWS_CONST ? 1u : ROWS >= ROWS_L16F ? 2u : 0u; nd[N_PCONST] = 0;
                     v.ht[free_slot] = (uint16_t)(idx + 1);
                 }
                 w.node_count += 1;
@@ -476,7 +592,7 @@ __device__ __forceinline__ void descend(const View& v, YaState cur, Walk& w, uin
             int L = ya_legal_count(desc);
             if (L == 0) { w.ret.d = 0.0; w.ret.is_f32 = false; break; }    // MCTS.py:138-147: `return 0`, not negated
             if (w.depth >= kMaxDepth) { w.err = E_DEPTH; w.kind = KIND_ERROR; break; }
-            int ai = ucb_select<CONST_ROWS>(v, node, L, cpuct, tm);
+            int ai = ucb_select<ROWS>(v, node, L, cpuct, tm);
             a = ya_nth_legal(desc, ai);
             if (lane == 0) v.cur[C_PATH + w.depth] = (uint32_t)idx | ((uint32_t)ai << 16);
         }
@@ -510,20 +626,21 @@ __device__ __forceinline__ void descend(const View& v, YaState cur, Walk& w, uin
     tm.sync();
 }
 
-template <bool WRITE_LEAF_STATE, bool INJECT>
+template <bool WRITE_LEAF_STATE, bool INJECT, int ROWS>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, YA_MCTS_MIN_BLOCKS)
 ya_k_mcts_select(ya_mcts_tree tree, const uint4* __restrict__ states, int64_t stride, const int8_t* __restrict__ players,
                  const int32_t* __restrict__ ply, const uint32_t* __restrict__ episode, uint64_t seed, uint64_t game_base,
                  uint32_t sim, const uint32_t* __restrict__ sim_ptr, const uint64_t* __restrict__ game_base_ptr, float cpuct,
                  const uint8_t* __restrict__ active, float* __restrict__ features, uint8_t* __restrict__ need_eval, uint32_t* __restrict__ leaf_states,
-                 int32_t* __restrict__ err_flag, const uint8_t* __restrict__ injected, int resume) {
+                 int32_t* __restrict__ err_flag, const uint8_t* __restrict__ injected, int resume,
+                 uint64_t* __restrict__ leaf_dst, uint32_t* __restrict__ leaf_desc) {
     const Team<kSelectTeam> tm = Team<kSelectTeam>::make();          // four games per warp
     const int lane = tm.sub;
     if (sim_ptr) sim = *sim_ptr;                                     // CUDA-graph replay: the counter lives in HBM,
     if (game_base_ptr) game_base = *game_base_ptr;                   // and so does the global id of this slice's first game
     const int64_t g = ((int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5)) * (32 / kSelectTeam) + (tm.shift / kSelectTeam);
     if (g >= tree.n) return;
-    if (active && !active[g]) { if (lane == 0) need_eval[g] = 0; return; }
+    if (active && !active[g]) { if (lane == 0) { need_eval[g] = 0; if (leaf_dst) leaf_dst[g] = 0; } return; }
     View v = make_view(tree, g);
     YaState root = ya_load(states, stride, g);
     if (players[g] != 1) root = ya_flip(root);                       // getCanonicalForm of the root
@@ -534,9 +651,9 @@ ya_k_mcts_select(ya_mcts_tree tree, const uint4* __restrict__ states, int64_t st
     w.arena_top = v.meta[M_TOP];
     if (sim == 0 && !(INJECT && resume)) prune_on_new_round(v, root, w, tm);
     DrawSource src{INJECT ? injected + g * 12 : nullptr, INJECT ? resume : 0};
-    descend<true, INJECT, false>(v, root, w, seed, gid, ep, pl, sim, cpuct, features + g * YA_N_FEATURE, tm, src);
+    descend<true, INJECT, ROWS>(v, root, w, seed, gid, ep, pl, sim, cpuct, features + g * YA_N_FEATURE, tm, src);
     if (w.kind == KIND_DONE) {
-        if (!backup_path(v, w.depth, w.ret, w.arena_top, tm)) { w.err = E_ARENA_FULL; w.kind = KIND_ERROR; }
+        if (!backup_path<ROWS>(v, w.depth, w.ret, w.arena_top, tm)) { w.err = E_ARENA_FULL; w.kind = KIND_ERROR; }
     }
     if (lane == 0) {
         v.meta[M_NODES] = w.node_count;
@@ -553,6 +670,10 @@ ya_k_mcts_select(ya_mcts_tree tree, const uint4* __restrict__ states, int64_t st
             code = (uint8_t)(0x10 | (((w.pending >> 16) & YA_NEED_TIE) ? 1 : 0) | (((w.pending >> 16) & YA_NEED_ROLLS) ? 2 : 0));
         }
         need_eval[g] = code;
+        if (leaf_dst) {                                              // where the forward kernel's epilogue puts the legal logits
+            leaf_dst[g] = w.kind == KIND_NEED_EVAL ? reinterpret_cast<uint64_t>(v.arena + w.leaf_row) : 0ull;
+            leaf_desc[g] = w.kind == KIND_NEED_EVAL ? w.leaf_desc : 0u;
+        }
         if (w.err && err_flag) atomicOr(err_flag, w.err);
         if (WRITE_LEAF_STATE && leaf_states && w.kind == KIND_NEED_EVAL) {
             uint4* o = reinterpret_cast<uint4*>(leaf_states);
@@ -689,7 +810,7 @@ ya_k_mcts_expand(ya_mcts_tree tree, const float* __restrict__ pi_all, const floa
     ret.d = -(double)(MODE == 1 ? uniform_v : value[g]);             // return -v (numpy float32)
     ret.is_f32 = true;
     uint32_t arena_top = v.meta[M_TOP];
-    bool ok = backup_path(v, (int)v.cur[C_DEPTH], ret, arena_top, Team<32>::make());
+    bool ok = backup_path<ROWS_F32>(v, (int)v.cur[C_DEPTH], ret, arena_top, Team<32>::make());
     if (lane == 0) {
         v.meta[M_TOP] = arena_top;
         v.cur[C_KIND] = KIND_DONE;
@@ -697,28 +818,25 @@ ya_k_mcts_expand(ya_mcts_tree tree, const float* __restrict__ pi_all, const floa
     }
 }
 
-// bf16 logits [n][ld] straight from the policy head: softmax, mask and renormalisation fused (MCTS.py:86-101 after
-// NNetWrapper.predict's softmax, yacht/NNet.py:193), so neither float32 logits nor pi ever touch HBM:
-//     P[a] = exp(l[a] - max_all) / sum over legal a' of exp(l[a'] - max_all)
-// which is softmax -> mask -> divide by the masked sum with the softmax denominator cancelled.  Only the LEGAL
-// logits are read (202 of 3,226 on a bid ply, 252 per open category on a score ply): asynchronous 4-byte copies
-// compact them into shared memory in row order.  max_all (over all 3,226 logits: it decides when every legal
-// exp underflows and the reference falls back to the uniform row) comes from the forward kernel's epilogue
-// (row_max) or, for other evaluators, from one pass over the row.
+// 16-bit policy-head logits -> the leaf's logit row + exponent offset (MCTS.py:86-101 after NNetWrapper.predict's softmax,
+// yacht/NNet.py:193): softmax, mask and renormalisation collapse to
+//     P[a] = exp(l[a] - max_all) / sum over legal a' of exp(l[a'] - max_all) = 2^(l[a] * log2(e) + off)
+// with one offset per leaf, so neither float32 logits nor pi nor float32 priors ever exist in memory.
+// FROM_DENSE = false: the forward kernel's epilogue has already written the LEGAL logits into the row (ya_nn_forward with
+//   scatter targets); this kernel re-reads them (L2 hits: 2 * L bytes written a few microseconds ago), computes the offset
+//   and the per-32 group maxima and backs the value up.
+// FROM_DENSE = true: any evaluator that returns a dense [n][ld] 16-bit logit matrix; the legal entries are compacted into
+//   the row here (asynchronous 4-byte copies through shared memory).
+// max_all (over all 3,226 logits: it decides when every legal exp underflows and the reference falls back to the uniform
+// row) comes from the forward kernel's epilogue (row_max) or, FROM_DENSE only, from one pass over the dense row.
 constexpr int kLogitWarps = 4;
 constexpr int kLogitCols = 3232;
-// 16-bit logit -> float32: bfloat16 is the upper half of a float32; IEEE half goes through the converter
-template <bool F16> __device__ __forceinline__ float lo16(uint32_t w) {
-    return F16 ? __half2float(__ushort_as_half((unsigned short)(w & 0xFFFFu))) : __uint_as_float(w << 16);
-}
-template <bool F16> __device__ __forceinline__ float hi16(uint32_t w) {
-    return F16 ? __half2float(__ushort_as_half((unsigned short)(w >> 16))) : __uint_as_float(w & 0xFFFF0000u);
-}
-template <bool F16>
+template <bool F16, bool FROM_DENSE>
 __global__ void __launch_bounds__(kLogitWarps * 32)
-ya_k_mcts_expand_logits(ya_mcts_tree tree, const uint16_t* __restrict__ logits_all, int64_t ld,
-                        const float* __restrict__ row_max, const float* __restrict__ value,
-                        uint32_t* __restrict__ sim_counter, int32_t* __restrict__ err_flag) {
+ya_k_mcts_expand_rows(ya_mcts_tree tree, const uint16_t* __restrict__ logits_all, int64_t ld,
+                      const float* __restrict__ row_max, const float* __restrict__ value,
+                      uint32_t* __restrict__ sim_counter, int32_t* __restrict__ err_flag) {
+    constexpr int ROWS = F16 ? ROWS_L16F : ROWS_L16B;
     __shared__ __align__(16) uint32_t raw_all[kLogitWarps][kLogitCols / 2];
     const int lane = threadIdx.x & 31;
     uint32_t* raw = raw_all[threadIdx.x >> 5];
@@ -731,30 +849,37 @@ ya_k_mcts_expand_logits(ya_mcts_tree tree, const uint16_t* __restrict__ logits_a
     const uint32_t leaf_row = v.cur[C_LEAF_ROW];                       // node record is not needed before the logits load
     const int L = ya_legal_count(desc);
     if (L > 0) {
-        const uint32_t* lg = reinterpret_cast<const uint32_t*>(logits_all + g * ld);   // two logits per word (ld is even)
+        uint32_t* row = v.arena + leaf_row;
+        const int lw = l16_logit_words(L), nb = (L + 31) >> 5, nw_all = (L + 1) >> 1;
         const uint32_t raw_s = (uint32_t)__cvta_generic_to_shared(raw);
-        auto copy_word = [&](int dst_word, int src_word) {
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(raw_s + 4u * (uint32_t)dst_word), "l"(lg + src_word) : "memory");
-        };
-        if (desc & 1u) {                                               // bid row: actions 0..201
-            for (int j = lane; j < YA_N_BID / 2; j += 32) copy_word(j, j);
-        } else if (desc >> 13) {                                       // ten dice: 252 subsets per open category
-            int k0 = 0;
-            for (uint32_t open = (desc >> 1) & 0xFFFu; open; open &= open - 1, k0 += YA_N_SUBSET / 2) {
-                const int a0 = (YA_N_BID + (__ffs(open) - 1) * YA_N_SUBSET) / 2;
-                const uint32_t dst = raw_s + 4u * (uint32_t)(k0 + lane);
-                const uint32_t* src = lg + a0 + lane;                  // 126 words: lanes 0..29 take a fourth one
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n\t"
-                             "cp.async.ca.shared.global [%0 + 128], [%1 + 128], 4;\n\t"
-                             "cp.async.ca.shared.global [%0 + 256], [%1 + 256], 4;" ::"r"(dst), "l"(src) : "memory");
-                if (lane < YA_N_SUBSET / 2 - 96)
-                    asm volatile("cp.async.ca.shared.global [%0 + 384], [%1 + 384], 4;" ::"r"(dst), "l"(src) : "memory");
+        const uint32_t* lg = FROM_DENSE ? reinterpret_cast<const uint32_t*>(logits_all + g * ld) : nullptr;   // two logits per word
+        if (FROM_DENSE) {
+            auto copy_word = [&](int dst_word, int src_word) {
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(raw_s + 4u * (uint32_t)dst_word), "l"(lg + src_word) : "memory");
+            };
+            if (desc & 1u) {                                           // bid row: actions 0..201
+                for (int j = lane; j < YA_N_BID / 2; j += 32) copy_word(j, j);
+            } else if (desc >> 13) {                                   // ten dice: 252 subsets per open category
+                int k0 = 0;
+                for (uint32_t open = (desc >> 1) & 0xFFFu; open; open &= open - 1, k0 += YA_N_SUBSET / 2) {
+                    const int a0 = (YA_N_BID + (__ffs(open) - 1) * YA_N_SUBSET) / 2;
+                    const uint32_t dst = raw_s + 4u * (uint32_t)(k0 + lane);
+                    const uint32_t* src = lg + a0 + lane;              // 126 words: lanes 0..29 take a fourth one
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n\t"
+                                 "cp.async.ca.shared.global [%0 + 128], [%1 + 128], 4;\n\t"
+                                 "cp.async.ca.shared.global [%0 + 256], [%1 + 256], 4;" ::"r"(dst), "l"(src) : "memory");
+                    if (lane < YA_N_SUBSET / 2 - 96)
+                        asm volatile("cp.async.ca.shared.global [%0 + 384], [%1 + 384], 4;" ::"r"(dst), "l"(src) : "memory");
+                }
+            } else {                                                   // five dice: subset 0 of every open category
+                if (lane < L) reinterpret_cast<uint16_t*>(raw)[lane] = reinterpret_cast<const uint16_t*>(lg)[ya_nth_legal(desc, lane)];
             }
-        } else {                                                       // five dice: subset 0 of every open category
-            if (lane < L) reinterpret_cast<uint16_t*>(raw)[lane] = reinterpret_cast<const uint16_t*>(lg)[ya_nth_legal(desc, lane)];
+        } else {                                                       // the row the forward kernel filled: 16-byte chunks
+            for (int j = lane * 4; j < nw_all; j += 128)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(raw_s + 4u * (uint32_t)j), "l"(row + j) : "memory");
         }
         // While the logits are in flight: pull the lines the backup will walk (one lane per level of the path --
-        // the node, the head of its edge index array, the prior group and group maximum of the chosen child).
+        // the node, the head of its edge index array, the logit group and group maximum of the chosen child).
         {
             const int depth = (int)v.cur[C_DEPTH];
             if (lane < depth) {
@@ -763,8 +888,8 @@ ya_k_mcts_expand_logits(ya_mcts_tree tree, const uint16_t* __restrict__ logits_a
                 const int ne = (int)nd[N_NEDGE], ai = (int)(pe >> 16);
                 const uint32_t* prow = v.arena + nd[N_PRIOR];
                 const int Lp = ya_legal_count(nd[N_DESC]);
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(prow + (ai & ~31)));
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(prow + group_max_at(Lp) + (ai >> 5)));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(prow + ((ai & ~31) >> 1)));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(prow + l16_logit_words(Lp) + (ai >> 5)));
                 if (ne > 0) {
                     const uint32_t* eb = v.arena + nd[N_EDGES];
                     const int cap = edge_cap(ne);
@@ -778,22 +903,24 @@ ya_k_mcts_expand_logits(ya_mcts_tree tree, const uint16_t* __restrict__ logits_a
         float mx;
         if (row_max) {
             mx = row_max[g];
-        } else {
+        } else if (FROM_DENSE) {
             mx = -CUDART_INF_F;
             for (int j = lane; j < YA_N_ACTION / 2; j += 32) {
                 uint32_t w = lg[j];
-                mx = fmaxf(mx, fmaxf(lo16<F16>(w), hi16<F16>(w)));
+                mx = fmaxf(mx, fmaxf(l16_value<ROWS>(w & 0xFFFFu), l16_value<ROWS>(w >> 16)));
             }
 #pragma unroll
             for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, o));
+        } else {
+            mx = 0.0f;                                                 // not reachable: the entry point requires row_max
         }
         asm volatile("cp.async.wait_all;" ::: "memory");
         __syncwarp();
+        if (FROM_DENSE)                                                // the compacted legal logits become the node's row
+            for (int j = lane; j < nw_all; j += 32) row[j] = raw[j];
         // exp(l - max) = 2^(l * log2(e) - max * log2(e)): one FMA + one EX2 per logit; the normalisation is folded into
-        // the exponent as well (P = 2^(.. - log2(total))).  Two logits per lane and iteration (one 32-bit word).
-        constexpr float kLog2e = 1.4426950408889634f;
+        // the exponent as well (P = 2^(.. - log2(total))).
         const float off_sum = -mx * kLog2e;
-        auto ex2 = [](float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; };
         const uint16_t* rc = reinterpret_cast<const uint16_t*>(raw);
         const bool pairs = !(L & 1), quads = !(L & 3);                 // ten-dice rows: L = 252 * open categories
         const int nw = L >> 1;
@@ -803,32 +930,35 @@ ya_k_mcts_expand_logits(ya_mcts_tree tree, const uint16_t* __restrict__ logits_a
             const uint2* raw2 = reinterpret_cast<const uint2*>(raw);
             for (int j = lane; j < (L >> 2); j += 32) {
                 const uint2 w = raw2[j];
-                total += ex2(fmaf(lo16<F16>(w.x), kLog2e, off_sum));
-                t1 += ex2(fmaf(hi16<F16>(w.x), kLog2e, off_sum));
-                t2 += ex2(fmaf(lo16<F16>(w.y), kLog2e, off_sum));
-                t3 += ex2(fmaf(hi16<F16>(w.y), kLog2e, off_sum));
+                total += l16_prior<ROWS>(w.x & 0xFFFFu, off_sum);
+                t1 += l16_prior<ROWS>(w.x >> 16, off_sum);
+                t2 += l16_prior<ROWS>(w.y & 0xFFFFu, off_sum);
+                t3 += l16_prior<ROWS>(w.y >> 16, off_sum);
             }
             total = (total + t1) + (t2 + t3);
         } else if (pairs) {
             float t1 = 0.0f;
             for (int j = lane; j < nw; j += 32) {
                 const uint32_t w = raw[j];
-                total += ex2(fmaf(lo16<F16>(w), kLog2e, off_sum));
-                t1 += ex2(fmaf(hi16<F16>(w), kLog2e, off_sum));
+                total += l16_prior<ROWS>(w & 0xFFFFu, off_sum);
+                t1 += l16_prior<ROWS>(w >> 16, off_sum);
             }
             total += t1;
         } else {
-            for (int k = lane; k < L; k += 32) total += ex2(fmaf(lo16<F16>((uint32_t)rc[k]), kLog2e, off_sum));
+            for (int k = lane; k < L; k += 32) total += l16_prior<ROWS>(rc[k], off_sum);
         }
 #pragma unroll
         for (int o = 16; o; o >>= 1) total += __shfl_xor_sync(0xFFFFFFFFu, total, o);
-        float* row = reinterpret_cast<float*>(v.arena + leaf_row);
+        uint32_t* gm = row + lw;
+        uint32_t* seen = row + lw + nb;
+        uint32_t* node = v.nodes + (int64_t)v.cur[C_NODE] * kNodeWords;
+        for (int b = lane; b < nb; b += 32) seen[b] = 0u;
         if (total > 0.0f) {
             const float off_p = off_sum - __log2f(total);
+            if (lane == 0) node[N_PCONST] = __float_as_uint(off_p);
             if (quads) {
-                // 128 priors = four groups per iteration: a lane owns four consecutive priors (one 16-byte store),
-                // eight lanes own a group and reduce its maximum with three shuffles
-                uint32_t* gm = reinterpret_cast<uint32_t*>(row) + group_max_at(L);
+                // 128 priors = four groups per iteration: a lane owns four consecutive priors, eight lanes own a group
+                // and reduce its maximum with three shuffles
                 const uint2* raw2 = reinterpret_cast<const uint2*>(raw);
                 const int nq = L >> 2;
                 for (int j0 = 0; j0 < nq; j0 += 32) {
@@ -836,46 +966,27 @@ ya_k_mcts_expand_logits(ya_mcts_tree tree, const uint16_t* __restrict__ logits_a
                     uint32_t e = 0;
                     if (j < nq) {
                         const uint2 w = raw2[j];
-                        float4 p;
-                        p.x = ex2(fmaf(lo16<F16>(w.x), kLog2e, off_p));
-                        p.y = ex2(fmaf(hi16<F16>(w.x), kLog2e, off_p));
-                        p.z = ex2(fmaf(lo16<F16>(w.y), kLog2e, off_p));
-                        p.w = ex2(fmaf(hi16<F16>(w.y), kLog2e, off_p));
-                        reinterpret_cast<float4*>(row)[j] = p;
-                        e = __float_as_uint(fmaxf(fmaxf(p.x, p.y), fmaxf(p.z, p.w))) + 1u;
+                        const float pa = l16_prior<ROWS>(w.x & 0xFFFFu, off_p), pb = l16_prior<ROWS>(w.x >> 16, off_p);
+                        const float pc = l16_prior<ROWS>(w.y & 0xFFFFu, off_p), pd = l16_prior<ROWS>(w.y >> 16, off_p);
+                        e = __float_as_uint(fmaxf(fmaxf(pa, pb), fmaxf(pc, pd))) + 1u;
                     }
                     e = max(e, __shfl_xor_sync(0xFFFFFFFFu, e, 1));
                     e = max(e, __shfl_xor_sync(0xFFFFFFFFu, e, 2));
                     e = max(e, __shfl_xor_sync(0xFFFFFFFFu, e, 4));
                     if ((lane & 7) == 0 && j < nq) gm[j >> 3] = e;     // group of priors 4j .. 4j + 31
                 }
-            } else if (pairs) {
-                uint32_t* gm = reinterpret_cast<uint32_t*>(row) + group_max_at(L);
-                const int ngroups = (L + 31) >> 5;
-                for (int j0 = 0; j0 < nw; j0 += 32) {                  // 64 priors = two groups per iteration
-                    const int j = j0 + lane;
-                    uint32_t e = 0;
-                    if (j < nw) {
-                        const uint32_t w = raw[j];
-                        const float p0 = ex2(fmaf(lo16<F16>(w), kLog2e, off_p));
-                        const float p1 = ex2(fmaf(hi16<F16>(w), kLog2e, off_p));
-                        reinterpret_cast<float2*>(row)[j] = make_float2(p0, p1);
-                        e = max(__float_as_uint(p0), __float_as_uint(p1)) + 1u;
-                    }
-                    const uint32_t lo = __reduce_max_sync(0xFFFFFFFFu, lane < 16 ? e : 0u);
-                    const uint32_t hi = __reduce_max_sync(0xFFFFFFFFu, lane < 16 ? 0u : e);
-                    const int gi = (j0 >> 4) + (lane >> 4);
-                    if ((lane & 15) == 0 && gi < ngroups) gm[gi] = lane ? hi : lo;
-                }
             } else {
                 for (int k0 = 0; k0 < L; k0 += 32) {
                     const int k = k0 + lane;
-                    store_prior_group(row, L, k0, k < L ? ex2(fmaf(lo16<F16>((uint32_t)rc[k]), kLog2e, off_p)) : 0.0f, lane);
+                    uint32_t e = k < L ? __float_as_uint(l16_prior<ROWS>(rc[k], off_p)) + 1u : 0u;
+                    e = __reduce_max_sync(0xFFFFFFFFu, e);
+                    if (lane == 0) gm[k0 >> 5] = e;
                 }
             }
-        } else {                                                       // every legal move underflowed: MCTS.py:97-101
-            const float u = __fdiv_rn(1.0f, (float)L);
-            for (int k0 = 0; k0 < L; k0 += 32) store_prior_group(row, L, k0, u, lane);
+        } else if (lane == 0) {                                        // every legal move underflowed (MCTS.py:97-101): Ps = 1 / L,
+            node[N_KIND] = 1u;                                         // a constant-prior node on the row's visited bits
+            node[N_PRIOR] = leaf_row + (uint32_t)(lw + nb);
+            node[N_PCONST] = __float_as_uint(__fdiv_rn(1.0f, (float)L));
         }
     }
     __syncwarp();
@@ -883,7 +994,7 @@ ya_k_mcts_expand_logits(ya_mcts_tree tree, const uint16_t* __restrict__ logits_a
     ret.d = -(double)value[g];
     ret.is_f32 = true;
     uint32_t arena_top = v.meta[M_TOP];
-    bool ok = backup_path(v, (int)v.cur[C_DEPTH], ret, arena_top, Team<32>::make());
+    bool ok = backup_path<ROWS>(v, (int)v.cur[C_DEPTH], ret, arena_top, Team<32>::make());
     if (lane == 0) {
         v.meta[M_TOP] = arena_top;
         v.cur[C_KIND] = KIND_DONE;
@@ -916,7 +1027,7 @@ ya_k_mcts_search_uniform(ya_mcts_tree tree, const uint4* __restrict__ states, in
     prune_on_new_round(v, root, w, tm);
     int err = 0;
     for (int sim = 0; sim < num_sims; ++sim) {
-        descend<false, false, true>(v, root, w, seed, gid, ep, pl, (uint32_t)sim, cpuct, nullptr, tm);
+        descend<false, false, ROWS_CONST>(v, root, w, seed, gid, ep, pl, (uint32_t)sim, cpuct, nullptr, tm);
         if (w.kind == KIND_ERROR) { err = w.err; break; }
         Val ret = w.ret;
         if (w.kind == KIND_NEED_EVAL) {
@@ -936,7 +1047,7 @@ ya_k_mcts_search_uniform(ya_mcts_tree tree, const uint4* __restrict__ states, in
             ret.d = -(double)uniform_v;
             ret.is_f32 = true;
         }
-        if (!backup_path(v, w.depth, ret, w.arena_top, tm)) { err = E_ARENA_FULL; break; }
+        if (!backup_path<ROWS_CONST>(v, w.depth, ret, w.arena_top, tm)) { err = E_ARENA_FULL; break; }
     }
     if (lane == 0) {
         v.meta[M_NODES] = w.node_count;
@@ -1102,16 +1213,25 @@ int ya_mcts_reset(const ya_mcts_tree* tree, const uint8_t* which, void* stream) 
 int ya_mcts_select(const ya_mcts_tree* tree, const uint32_t* states, int64_t stride, const int8_t* players,
                    const int32_t* ply, const uint32_t* episode, uint64_t seed, uint64_t game_base, uint32_t sim,
                    const uint32_t* sim_ptr, const uint64_t* game_base_ptr, float cpuct, const uint8_t* active,
-                   float* features, uint8_t* need_eval, uint32_t* leaf_states, int32_t* err_flag, void* stream) {
+                   float* features, uint8_t* need_eval, uint32_t* leaf_states, int rows, uint64_t* leaf_dst,
+                   uint32_t* leaf_desc, int32_t* err_flag, void* stream) {
     if (!tree_ok(tree) || !(cpuct >= 0.0f)) return (int)cudaErrorInvalidValue;   // group maxima rely on u monotone in P
-    if (leaf_states)
-        ya_k_mcts_select<true, false><<<select_blocks(tree->n), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
-            *tree, reinterpret_cast<const uint4*>(states), stride, players, ply, episode, seed, game_base, sim, sim_ptr,
-            game_base_ptr, cpuct, active, features, need_eval, leaf_states, err_flag, nullptr, 0);
-    else
-        ya_k_mcts_select<false, false><<<select_blocks(tree->n), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
-            *tree, reinterpret_cast<const uint4*>(states), stride, players, ply, episode, seed, game_base, sim, sim_ptr,
-            game_base_ptr, cpuct, active, features, need_eval, leaf_states, err_flag, nullptr, 0);
+    if (rows != YA_ROWS_F32 && rows != YA_ROWS_FP16 && rows != YA_ROWS_BF16) return (int)cudaErrorInvalidValue;
+    if ((leaf_dst == nullptr) != (leaf_desc == nullptr)) return (int)cudaErrorInvalidValue;
+    const dim3 grid(select_blocks(tree->n)), block(kWarpsPerBlock * 32);
+    const cudaStream_t st = (cudaStream_t)stream;
+    const uint4* sp = reinterpret_cast<const uint4*>(states);
+#define YA_LAUNCH_SELECT(LEAF, ROWS)                                                                                      \
+    ya_k_mcts_select<LEAF, false, ROWS><<<grid, block, 0, st>>>(*tree, sp, stride, players, ply, episode, seed, game_base, sim,   \
+        sim_ptr, game_base_ptr, cpuct, active, features, need_eval, leaf_states, err_flag, nullptr, 0, leaf_dst, leaf_desc)
+    if (rows == YA_ROWS_F32) {
+        if (leaf_states) YA_LAUNCH_SELECT(true, ROWS_F32); else YA_LAUNCH_SELECT(false, ROWS_F32);
+    } else if (rows == YA_ROWS_FP16) {
+        if (leaf_states) YA_LAUNCH_SELECT(true, ROWS_L16F); else YA_LAUNCH_SELECT(false, ROWS_L16F);
+    } else {
+        if (leaf_states) YA_LAUNCH_SELECT(true, ROWS_L16B); else YA_LAUNCH_SELECT(false, ROWS_L16B);
+    }
+#undef YA_LAUNCH_SELECT
     return (int)cudaGetLastError();
 }
 
@@ -1119,9 +1239,9 @@ int ya_mcts_select_injected(const ya_mcts_tree* tree, const uint32_t* states, in
                             uint32_t sim, float cpuct, const uint8_t* injected, int resume, float* features,
                             uint8_t* need_eval, uint32_t* leaf_states, int32_t* err_flag, void* stream) {
     if (!tree_ok(tree) || !injected || !leaf_states || !(cpuct >= 0.0f)) return (int)cudaErrorInvalidValue;
-    ya_k_mcts_select<true, true><<<select_blocks(tree->n), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
+    ya_k_mcts_select<true, true, ROWS_F32><<<select_blocks(tree->n), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
         *tree, reinterpret_cast<const uint4*>(states), stride, players, nullptr, nullptr, 0, 0, sim, nullptr, nullptr,
-        cpuct, nullptr, features, need_eval, leaf_states, err_flag, injected, resume);
+        cpuct, nullptr, features, need_eval, leaf_states, err_flag, injected, resume, nullptr, nullptr);
     return (int)cudaGetLastError();
 }
 
@@ -1139,15 +1259,19 @@ int ya_mcts_expand(const ya_mcts_tree* tree, const float* pi, const float* value
 
 int ya_mcts_expand_logits(const ya_mcts_tree* tree, const void* logits16, int fp16, int64_t ld, const float* row_max,
                           const float* value, uint32_t* sim_counter, int32_t* err_flag, void* stream) {
-    if (!tree_ok(tree) || ld < kLogitCols || (ld % 8) != 0 || (reinterpret_cast<uintptr_t>(logits16) & 15u))
-        return (int)cudaErrorInvalidValue;
-    int blocks = (int)((tree->n + kLogitWarps - 1) / kLogitWarps);
-    if (fp16)
-        ya_k_mcts_expand_logits<true><<<blocks, kLogitWarps * 32, 0, (cudaStream_t)stream>>>(
-            *tree, static_cast<const uint16_t*>(logits16), ld, row_max, value, sim_counter, err_flag);
-    else
-        ya_k_mcts_expand_logits<false><<<blocks, kLogitWarps * 32, 0, (cudaStream_t)stream>>>(
-            *tree, static_cast<const uint16_t*>(logits16), ld, row_max, value, sim_counter, err_flag);
+    if (!tree_ok(tree) || !value) return (int)cudaErrorInvalidValue;
+    if (logits16 && (ld < kLogitCols || (ld % 8) != 0 || (reinterpret_cast<uintptr_t>(logits16) & 15u))) return (int)cudaErrorInvalidValue;
+    if (!logits16 && !row_max) return (int)cudaErrorInvalidValue;       // rows filled by ya_nn_forward: its row_max comes with them
+    const int blocks = (int)((tree->n + kLogitWarps - 1) / kLogitWarps);
+    const cudaStream_t st = (cudaStream_t)stream;
+    const uint16_t* lg = static_cast<const uint16_t*>(logits16);
+    if (fp16) {
+        if (lg) ya_k_mcts_expand_rows<true, true><<<blocks, kLogitWarps * 32, 0, st>>>(*tree, lg, ld, row_max, value, sim_counter, err_flag);
+        else ya_k_mcts_expand_rows<true, false><<<blocks, kLogitWarps * 32, 0, st>>>(*tree, lg, ld, row_max, value, sim_counter, err_flag);
+    } else {
+        if (lg) ya_k_mcts_expand_rows<false, true><<<blocks, kLogitWarps * 32, 0, st>>>(*tree, lg, ld, row_max, value, sim_counter, err_flag);
+        else ya_k_mcts_expand_rows<false, false><<<blocks, kLogitWarps * 32, 0, st>>>(*tree, lg, ld, row_max, value, sim_counter, err_flag);
+    }
     return (int)cudaGetLastError();
 }
 

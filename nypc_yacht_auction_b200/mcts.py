@@ -28,8 +28,9 @@ def _next_pow2(x):
 class TreePool:
     """Device storage of n per-game trees (include/yacht_b200.h: ya_mcts_tree)."""
 
-    def __init__(self, n, num_sims, device, arena_mb_per_game=None, max_nodes=None):
+    def __init__(self, n, num_sims, device, arena_mb_per_game=None, max_nodes=None, rows=0):
         self.n = int(n)
+        self.rows = int(rows)                       # YA_ROWS_F32 (0) / YA_ROWS_FP16 (2) / YA_ROWS_BF16 (3)
         self.device = torch.device(device)
         lib = _lib.load()
         self.max_nodes = int(max_nodes or (6 * num_sims + 16))
@@ -39,7 +40,10 @@ class TreePool:
             # measured peak (random-init net, 100 sims, profiles/tools/arena_peak.py): 39 KB per simulation of the
             # longest-lived tree (rounds 1+2: six plies without pruning); 48 KB/sim leaves ~20 % head-room,
             # overflow is detected and raised.
-            arena_mb_per_game = max(num_sims * 48.0 / 1024.0, 0.25)
+            # 16-bit logit rows (ROWS_FP16 / ROWS_BF16) take 2.25 instead of 4.1 bytes per legal move: measured peak 21.6 KB
+            # per simulation, 28 KB/sim allocated.
+            per_sim_kb = 48.0 if self.rows == 0 else 28.0
+            arena_mb_per_game = max(num_sims * per_sim_kb / 1024.0, 0.25)
         words = int(arena_mb_per_game * 2 ** 20) // 4
         self.arena_words = words - (words % 4)
         d = self.device
@@ -83,6 +87,7 @@ class FusedYachtEvaluator:
     Weights come from any module with YachtNNet's state dict (:25-52), hidden width 256 (main.py:40)."""
     uniform = False
     returns_logits = True
+    supports_scatter = True
     PADDED = 3232
 
     def __init__(self, net, max_batch, precision="fp16"):
@@ -148,7 +153,8 @@ class FusedYachtEvaluator:
         return img.permute(1, 0, 2, 3).contiguous().view(torch.uint8).reshape(-1)
 
     def _alloc(self, n, dev):
-        self.logits = torch.empty((n, self.PADDED), dtype=self.op_dtype, device=dev)
+        self.max_batch = n
+        self.logits = None                          # dense [n, 3232] logit matrix: only allocated if someone asks for it
         self.values = torch.empty(n, dtype=torch.float32, device=dev)
         self.row_max = torch.empty(n, dtype=torch.float32, device=dev)
 
@@ -160,14 +166,24 @@ class FusedYachtEvaluator:
         return other
 
     @torch.no_grad()
-    def __call__(self, features, need_eval=None, leaf_states=None):
+    def __call__(self, features, need_eval=None, leaf_states=None, scatter=None):
+        """scatter = (leaf_dst uint64[n], leaf_desc uint32[n]) from ya_mcts_select: the policy head's epilogue writes every
+        leaf's LEGAL logits straight into its row of the tree pool and no dense logit matrix exists (returns None for it);
+        otherwise the dense [n, 3232] 16-bit logits are returned."""
         n = features.shape[0]
-        logits, values = self.logits[:n], self.values[:n]
+        values = self.values[:n]
         self.last_row_max = self.row_max[:n]                              # consumed by ya_mcts_expand_logits
+        logits = None
+        if scatter is None:
+            if self.logits is None:
+                self.logits = torch.empty((self.max_batch, self.PADDED), dtype=self.op_dtype, device=self.device)
+            logits = self.logits[:n]
+        dst, desc = scatter if scatter is not None else (None, None)
         _lib.check(self.lib.ya_nn_forward(_lib.ptr(features), _lib.ptr(logits), _lib.ptr(values),
                                           _lib.ptr(self.last_row_max), _lib.ptr(self.fw_w),
                                           _lib.ptr(self.fw_p), self.fw_off, self.nblocks, n, self.eps,
-                                          1 if self.fp16 else 0, _lib.current_stream()), "ya_nn_forward")
+                                          1 if self.fp16 else 0, _lib.ptr(dst), _lib.ptr(desc), _lib.current_stream()),
+                   "ya_nn_forward")
         return logits, values
 
 
@@ -184,6 +200,8 @@ class _Group:
         self.states_ptr = ctypes.c_void_p(env.states.data_ptr() + 16 * g0)     # plane stride stays env.n
         self.players, self.ply, self.episode = env.players[g0:g1], env.ply[g0:g1], env.episode[g0:g1]
         self.features, self.need_eval = mcts.features[g0:g1], mcts.need_eval[g0:g1]
+        self.leaf_dst = mcts.leaf_dst[g0:g1] if mcts.leaf_dst is not None else None
+        self.leaf_desc = mcts.leaf_desc[g0:g1] if mcts.leaf_desc is not None else None
         self.sim_counter = torch.zeros(1, dtype=torch.int32, device=env.device)
         # global id of this slice's first game, in device memory: a captured launch freezes by-value arguments, so the
         # graph reads the base from here and stays valid when the pool moves on to the next wave of games
@@ -208,9 +226,19 @@ class BatchedMCTS:
         self.cpuct = float(cpuct)
         self.temp_threshold = int(temp_threshold)
         self.evaluator = evaluator or UniformEvaluator()
-        self.pool = TreePool(env.n, self.num_sims, env.device, arena_mb_per_game, max_nodes)
+        ev = self.evaluator
+        # how the pool stores priors: evaluators that hand over raw 16-bit logits get logit rows (the format of their logits),
+        # float32-policy evaluators and the uniform prior the float32 / constant rows of the bit-exact reference path
+        self.rows = 0
+        if getattr(ev, "returns_logits", False):
+            dt = getattr(ev, "op_dtype", None) or getattr(getattr(ev, "logits", None), "dtype", torch.bfloat16)
+            self.rows = 2 if dt == torch.float16 else 3
+        self.scatter = bool(self.rows and getattr(ev, "supports_scatter", False) and not want_leaf_states)
+        self.pool = TreePool(env.n, self.num_sims, env.device, arena_mb_per_game, max_nodes, rows=self.rows)
         d = env.device
         n = env.n
+        self.leaf_dst = torch.zeros(n, dtype=torch.int64, device=d) if self.scatter else None
+        self.leaf_desc = torch.zeros(n, dtype=torch.int32, device=d) if self.scatter else None
         self.features = torch.zeros((n, FEATURE_SIZE), dtype=torch.float32, device=d)
         self.need_eval = torch.zeros(n, dtype=torch.uint8, device=d)
         self.leaf_states = torch.zeros((2, n, 4), dtype=torch.int32, device=d) if want_leaf_states else None
@@ -287,21 +315,25 @@ class BatchedMCTS:
             grp.ref, grp.states_ptr, env.n, _lib.ptr(grp.players), _lib.ptr(grp.ply), _lib.ptr(grp.episode),
             env.seed, env.game_base + grp.g0, 0 if sim is None else sim, _lib.ptr(grp.sim_counter) if sim is None else None,
             _lib.ptr(grp.base_dev) if sim is None else None, self.cpuct, None, _lib.ptr(grp.features), _lib.ptr(grp.need_eval),
-            _lib.ptr(leaf), _lib.ptr(self.err_flag), s), "ya_mcts_select")
+            _lib.ptr(leaf), self.rows, _lib.ptr(grp.leaf_dst), _lib.ptr(grp.leaf_desc), _lib.ptr(self.err_flag), s), "ya_mcts_select")
         counter = _lib.ptr(grp.sim_counter) if sim is None else None
         ev = grp.evaluator
         if getattr(ev, "uniform", False):
             _lib.check(self.lib.ya_mcts_expand(grp.ref, None, None, 1, ev.p, ev.v, counter, _lib.ptr(self.err_flag), s),
                        "ya_mcts_expand")
             return
-        pi, v = ev(grp.features, grp.need_eval, leaf)
+        if self.scatter:                                              # legal logits go from the tensor core into the tree rows
+            pi, v = ev(grp.features, grp.need_eval, leaf, scatter=(grp.leaf_dst, grp.leaf_desc))
+        else:
+            pi, v = ev(grp.features, grp.need_eval, leaf)
         assert v.dtype == torch.float32 and v.is_contiguous() and v.shape == (grp.n,)
-        if getattr(ev, "returns_logits", False):
-            assert pi.dtype in (torch.bfloat16, torch.float16) and pi.is_contiguous() and pi.shape[0] == grp.n
+        if self.rows:
+            assert self.scatter or (pi.dtype == (torch.float16 if self.rows == 2 else torch.bfloat16) and pi.is_contiguous()
+                                    and pi.shape[0] == grp.n)
             row_max = getattr(ev, "last_row_max", None)               # per-row max logit, if the evaluator has it
             assert row_max is None or (row_max.dtype == torch.float32 and row_max.shape == (grp.n,))
-            _lib.check(self.lib.ya_mcts_expand_logits(grp.ref, _lib.ptr(pi), 1 if pi.dtype == torch.float16 else 0,
-                                                      pi.shape[1], _lib.ptr(row_max), _lib.ptr(v),
+            _lib.check(self.lib.ya_mcts_expand_logits(grp.ref, _lib.ptr(pi), 1 if self.rows == 2 else 0,
+                                                      0 if pi is None else pi.shape[1], _lib.ptr(row_max), _lib.ptr(v),
                                                       counter, _lib.ptr(self.err_flag), s), "ya_mcts_expand_logits")
             return
         assert pi.dtype == torch.float32 and pi.is_contiguous() and pi.shape == (grp.n, ACTION_SIZE)
@@ -454,7 +486,7 @@ class MCTS:
             _lib.check(self.lib.ya_mcts_select(
                 self.pool.ref, _lib.ptr(self.states), 1, _lib.ptr(self.players), _lib.ptr(self.ply), None,
                 self.seed, self.tree_id, self.sim_index, None, None, float(self.args.cpuct), None, _lib.ptr(self.features),
-                _lib.ptr(self.need_eval), _lib.ptr(self.leaf_states), _lib.ptr(self.err_flag), s), "ya_mcts_select")
+                _lib.ptr(self.need_eval), _lib.ptr(self.leaf_states), 0, None, None, _lib.ptr(self.err_flag), s), "ya_mcts_select")
             code = int(self.need_eval.item())
         else:
             # in-search dice through the reference's own hooks, drawn exactly when getNextState would draw them

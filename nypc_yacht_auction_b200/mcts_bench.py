@@ -118,12 +118,13 @@ def wave_breakdown(torch, dev, n, sims, evaluator, seed, plies_before=6, waves=6
         a[0].record()
         _lib.check(lib.ya_mcts_select(grp.ref, grp.states_ptr, env.n, _lib.ptr(grp.players), _lib.ptr(grp.ply), _lib.ptr(grp.episode),
                                       env.seed, env.game_base, sim, None, None, m.cpuct, None, _lib.ptr(grp.features),
-                                      _lib.ptr(grp.need_eval), None, _lib.ptr(m.err_flag), s), "ya_mcts_select")
+                                      _lib.ptr(grp.need_eval), None, m.rows, _lib.ptr(grp.leaf_dst), _lib.ptr(grp.leaf_desc),
+                                      _lib.ptr(m.err_flag), s), "ya_mcts_select")
         a[1].record()
-        pi, v = ev(grp.features, grp.need_eval, None)
+        pi, v = ev(grp.features, grp.need_eval, None, scatter=(grp.leaf_dst, grp.leaf_desc))
         a[2].record()
-        _lib.check(lib.ya_mcts_expand_logits(grp.ref, _lib.ptr(pi), 1 if pi.dtype == torch.float16 else 0, pi.shape[1],
-                                             _lib.ptr(ev.last_row_max), _lib.ptr(v), None, _lib.ptr(m.err_flag), s), "ya_mcts_expand_logits")
+        _lib.check(lib.ya_mcts_expand_logits(grp.ref, None, 1 if m.rows == 2 else 0, 0, _lib.ptr(ev.last_row_max), _lib.ptr(v), None,
+                                             _lib.ptr(m.err_flag), s), "ya_mcts_expand_logits")
         a[3].record()
     torch.cuda.synchronize(dev)
     m.check_errors()

@@ -25,7 +25,7 @@ for t in range(12):
         a0.record()
         _lib.check(lib.ya_mcts_select(grp.ref, grp.states_ptr, env.n, _lib.ptr(grp.players), _lib.ptr(grp.ply), _lib.ptr(grp.episode),
             env.seed, env.game_base, sim, None, None, m.cpuct, None, _lib.ptr(grp.features), _lib.ptr(grp.need_eval),
-            _lib.ptr(m.leaf_states), _lib.ptr(m.err_flag), s), "sel")
+            _lib.ptr(m.leaf_states), m.rows, _lib.ptr(grp.leaf_dst), _lib.ptr(grp.leaf_desc), _lib.ptr(m.err_flag), s), "sel")
         a1.record(); b0.record()
         if not uniform:
             pi, v = ev(grp.features, grp.need_eval, m.leaf_states)

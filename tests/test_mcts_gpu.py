@@ -206,6 +206,25 @@ def test_fused_logits_expand_matches_softmax_mask_renorm(dtype):
     assert 202 in legal_counts and max(legal_counts) >= 2016 and min(legal_counts) <= 12, legal_counts
 
 
+def decode_logit_row(pool, g, node, n_legal):
+    """(priors float64[L], group maxima float32[ceil(L/32)], visited words) of a logit-row node (csrc/ya_mcts.cu ROWS_L16):
+    P[k] = 2^(l[k] * log2(e) + off) from the row's 16-bit logits and the node's exponent offset."""
+    nodes = pool.nodes[g, node].cpu().numpy().view(np.uint32)
+    assert int(nodes[13]) == 2, "not a logit-row node"
+    off = int(nodes[10])
+    lw, nb = (((n_legal + 1) // 2) + 3) & ~3, (n_legal + 31) // 32
+    words = pool.arena[g, off:off + lw + 2 * nb].cpu().numpy().view(np.uint32)
+    halves = words[:lw].view(np.uint16)[:n_legal]
+    if pool.rows == 2:
+        lg = halves.view(np.float16).astype(np.float64)
+    else:
+        lg = (halves.astype(np.uint32) << 16).view(np.float32).astype(np.float64)
+    off_p = float(nodes[14:15].view(np.float32)[0])
+    pri = np.exp2(lg * float(np.float32(1.4426950408889634)) + off_p)
+    gm = words[lw:lw + nb]
+    return pri, lg, gm, words[lw + nb:lw + 2 * nb]
+
+
 def _check_expand_rows(n, plies, LogitEval):
     from nypc_yacht_auction_b200.mcts import BatchedMCTS
     env = _engine(n, 3, 40)
@@ -213,27 +232,27 @@ def _check_expand_rows(n, plies, LogitEval):
         env.play_ply(masks=None, auto_reset=False)
     ev = LogitEval(n)
     mcts = BatchedMCTS(env, 4, 1.5, evaluator=ev)
+    assert mcts.rows in (2, 3) and not mcts.scatter        # dense 16-bit logits in, logit rows in the pool
     mcts.simulate(0)                                       # expands every root (node 0 of every tree)
     mcts.check_errors()
     masks = env.valid_moves(states=env.canonical(), players=torch.ones(n, dtype=torch.int8, device="cuda")).cpu().numpy()
-    arena = mcts.pool.arena.cpu().numpy().view(np.float32)
-    nodes = mcts.pool.nodes.cpu().numpy()
     lg = ev.logits.float().cpu().numpy()[:, :3226]
     counts = set()
     for g in range(n):
         legal = np.flatnonzero(masks[g])
-        off = int(nodes[g, 0, 10])
-        row = arena[g, off:off + len(legal)]
+        row, row_logits, gm, seen = decode_logit_row(mcts.pool, g, 0, len(legal))
+        assert (row_logits == lg[g][legal]).all(), (plies, g)                     # the legal logits, compacted, untouched
         e = np.exp((lg[g] - lg[g].max()).astype(np.float32)).astype(np.float32)
         pi = e / e.sum(dtype=np.float32)
         p = pi * masks[g]
         p = p / np.sum(p)
-        assert np.allclose(row, p[legal], rtol=2e-6, atol=1e-12), (plies, g)
+        assert np.allclose(row, p[legal], rtol=1e-5, atol=1e-12), (plies, g)
         assert abs(float(row.sum()) - 1.0) < 1e-5
         # group maxima: 1 + bits of the largest prior of each 32 (nothing visited yet)
-        gm = mcts.pool.arena.cpu().numpy().view(np.uint32)[g, off + ((len(legal) + 3) & ~3):][: (len(legal) + 31) // 32]
-        want = [int(row[k:k + 32].max().view(np.uint32)) + 1 for k in range(0, len(legal), 32)]
-        assert gm.tolist() == want, (plies, g)
+        got = (gm - 1).view(np.float32).astype(np.float64)
+        want = np.array([row[k:k + 32].max() for k in range(0, len(legal), 32)])
+        assert (gm > 0).all() and np.allclose(got, want, rtol=1e-5), (plies, g)
+        assert not seen.any()
         counts.add(len(legal))
     return counts
 
@@ -279,6 +298,50 @@ def test_fused_evaluator_matches_module_forward(precision, dtype):
     assert verr <= 1.25 * verr_torch + 0.01, (verr, verr_torch)
     tv = 0.5 * (torch.softmax(logits[:, :3226].float(), 1) - torch.softmax(ref_logits, 1)).abs().sum(1).max().item()
     assert tv < (0.005 if precision == "fp16" else 0.02), tv
+
+
+@pytest.mark.parametrize("precision", ["fp16", "bf16"])
+def test_scattered_rows_equal_dense_logit_rows(precision):
+    """the policy-head epilogue writes each leaf's legal logits straight into its row of the tree pool
+    (ya_nn_forward with scatter targets).  Against the same kernel writing the dense [n, 3232] matrix and
+    ya_mcts_expand_logits compacting it: identical rows, visit counts, Q values (bit patterns) and moves, over bid plies,
+    ten-dice score plies (every category pattern the games reach) and -- via late plies -- five-dice rows."""
+    from nypc_yacht_auction_b200.mcts import BatchedMCTS, FusedYachtEvaluator
+    net = _perturbed_net(21)
+
+    class Dense:                                           # same forward kernel, no scatter capability
+        uniform = False
+        returns_logits = True
+
+        def __init__(self, ev):
+            self.ev, self.op_dtype, self.last_row_max = ev, ev.op_dtype, None
+
+        def __call__(self, features, need_eval, leaf_states):
+            out = self.ev(features)
+            self.last_row_max = self.ev.last_row_max
+            return out
+
+    n, sims = 160, 20
+    for start in (0, 40):                                  # from the deal, and from ply 40 (rounds 11-13: few open categories, 5 dice)
+        runs = []
+        for make in (lambda: FusedYachtEvaluator(net, n, precision=precision), lambda: Dense(FusedYachtEvaluator(net, n, precision=precision))):
+            env = _engine(n, 8, 300)
+            for _ in range(start):
+                env.play_ply(masks=None, auto_reset=False)
+            m = BatchedMCTS(env, sims, 1.5, evaluator=make())
+            trace = []
+            for ply in range(8):
+                m.search()
+                c, v, q, k = m.root_counts(with_q=True)
+                trace.append((c.clone(), v.clone(), q.clone(), k.clone(), m.pick_actions().clone()))
+                env.next_state(m.picked)
+            m.check_errors()
+            runs.append((m.scatter, trace, m.pool.meta[:, :2].clone()))
+        assert runs[0][0] and not runs[1][0]
+        for a, b in zip(runs[0][1], runs[1][1]):
+            for x, y in zip(a, b):
+                assert torch.equal(x, y)
+        assert torch.equal(runs[0][2], runs[1][2])         # same node counts and arena tops
 
 
 def test_grouped_streams_give_identical_trees():
@@ -423,11 +486,16 @@ def test_evaluator_abi_rejects_bad_arguments():
     lib = _lib.load()
     ev = FusedYachtEvaluator(YachtPolicyValueNet().cuda().eval(), 256)
     x = torch.zeros((256, 59), device="cuda")
+    ev(x)                                                                            # allocates the dense logit matrix
     s = _lib.current_stream()
-    args = lambda logits_ptr, n: (_lib.ptr(x), logits_ptr, _lib.ptr(ev.values), _lib.ptr(ev.row_max), _lib.ptr(ev.fw_w),
-                                  _lib.ptr(ev.fw_p), ev.fw_off, ev.nblocks, n, ev.eps, 1, s)
+    args = lambda logits_ptr, n, dst=None, desc=None: (
+        _lib.ptr(x), logits_ptr, _lib.ptr(ev.values), _lib.ptr(ev.row_max), _lib.ptr(ev.fw_w), _lib.ptr(ev.fw_p), ev.fw_off,
+        ev.nblocks, n, ev.eps, 1, _lib.ptr(dst), _lib.ptr(desc), s)
     assert lib.ya_nn_forward(*args(_lib.ptr(ev.logits), 0)) == 0                     # nothing to do
     assert lib.ya_nn_forward(*args(ev.logits.data_ptr() + 2, 256)) != 0              # logits not 32-byte aligned
+    assert lib.ya_nn_forward(*args(None, 256)) != 0                                  # neither a dense matrix nor scatter targets
+    dst = torch.zeros(256, dtype=torch.int64, device="cuda")
+    assert lib.ya_nn_forward(*args(None, 256, dst, None)) != 0                       # scatter targets come in pairs
     env = _engine(4, 1, 1)
     from nypc_yacht_auction_b200.mcts import BatchedMCTS
     m = BatchedMCTS(env, 2, 1.5, evaluator=ev.with_private_buffers(4))
@@ -497,11 +565,15 @@ def test_expand_falls_back_to_uniform_when_every_legal_move_underflows():
     mcts = BatchedMCTS(env, 4, 1.5, evaluator=Underflow(n))
     mcts.simulate(0)
     mcts.check_errors()
-    arena = mcts.pool.arena.cpu().numpy().view(np.float32)
-    nodes = mcts.pool.nodes.cpu().numpy()
-    for g in range(n):
-        off = int(nodes[g, 0, 10])
-        assert (arena[g, off:off + 202] == np.float32(1.0) / np.float32(202)).all()
+    nodes = mcts.pool.nodes.cpu().numpy().view(np.uint32)
+    for g in range(n):                                       # the leaf became a constant-prior node: P = 1 / 202 for every bid
+        assert int(nodes[g, 0, 13]) == 1
+        assert nodes[g, 0, 14:15].view(np.float32)[0] == np.float32(1.0) / np.float32(202)
+    for sim in range(1, 4):                                  # and the search walks it like one: lowest unvisited bid first
+        mcts.simulate(sim)
+    mcts.check_errors()
+    counts, visits = mcts.root_counts()
+    assert counts[:, :3].tolist() == [[1, 1, 1]] * n and int(counts.sum()) == 3 * n and visits.tolist() == [3] * n
 
 
 @pytest.mark.parametrize("nblocks,precision", [(1, "fp16"), (3, "bf16")])
