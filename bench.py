@@ -530,16 +530,21 @@ def run_extras(args, torch, env, dev, n, peaks, prof, rank=0, world=1, dist=None
     net = YachtPolicyValueNet().to(dev)
     ev = FusedYachtEvaluator(net, 16384, precision="fp16")
     r = mb.selfplay_block(torch, dev, dist, rank, world, 16384, 100, ev, args.seed + 2, steps=2, warm=1)
-    fwd_us = mb.forward_alone(torch, dev, ev, 16384)
-    fwd_us_148 = mb.forward_alone(torch, dev, FusedYachtEvaluator(net, 148 * 128, precision="fp16"), 148 * 128)
+    wb = mb.wave_breakdown(torch, dev, 16384, 100, ev, args.seed + 2)
+    wb148 = mb.wave_breakdown(torch, dev, 148 * 128, 100, FusedYachtEvaluator(net, 148 * 128, precision="fp16"), args.seed + 2)
+    fwd_us, fwd_us_148 = wb["forward_us"], wb148["forward_us"]
+    dense_us = mb.forward_alone(torch, dev, ev, 16384)
+    ev.logits = None                                       # drop the dense matrix again (106 MB)
     real_flops = 2.0 * YachtPolicyValueNet.num_macs()
     fwd = {"bound": "tensor", "kernel": "ya_k_forward", "achieved": real_flops * 16384 / fwd_us * 1e-6, "peak": peaks["tensor"],
            "unit": "TFLOP/s", "frac": real_flops * 16384 / fwd_us * 1e-6 / peaks["tensor"], "leaves": 16384, "us_per_launch": fwd_us,
            "flops_per_leaf": real_flops, "peak_source": peaks["source"], "operands": "fp16 (tcgen05 kind::f16), float32 accumulation",
+           "how": "CUDA events around the launch inside real simulation waves (ply 6, warm trees): legal logits scattered into the tree "
+                  "rows by the policy-head epilogue, no dense logit matrix",
+           "dense_logits_variant_us": dense_us,
            "full_machine": {"leaves": 148 * 128, "us_per_launch": fwd_us_148, "achieved": real_flops * 148 * 128 / fwd_us_148 * 1e-6,
                             "frac": real_flops * 148 * 128 / fwd_us_148 * 1e-6 / peaks["tensor"],
                             "note": "one CTA of 128 leaves per SM: 16,384 leaves fill 128 of 148 SMs, 18,944 fill all"}}
-    wb = mb.wave_breakdown(torch, dev, 16384, 100, ev, args.seed + 2)
     bf = mb.selfplay_block(torch, dev, dist, rank, world, 16384, 100, FusedYachtEvaluator(net, 16384, precision="bf16"), args.seed + 2,
                            steps=1, warm=1, e2e_steps=0)
     r.update({"workload": "configs[3]: AlphaZero self-play, random-init YachtNNet (hidden 256, 6 blocks), numMCTSSims=100, 16384 games per GPU; "

@@ -101,7 +101,8 @@ int ya_play_ply(uint32_t* states, int64_t stride, int8_t* players, int32_t* ply,
  * The caller (torch) allocates the pool once and passes it as a ya_mcts_tree:
  *   nodes   uint32[n][max_nodes][16]   64-byte node records (key = packed canonical state)
  *   ht      uint16[n][ht_size]         open-addressing table, ht_size = power of two >= 2*max_nodes
- *   arena   uint32[n][arena_words]     legal-only float32 prior rows (+ per-32 group maxima) + visited-edge arrays (index, Nsa, Qsa)
+ *   arena   uint32[n][arena_words]     legal-only prior rows (float32, or 16-bit logits; + per-32 group maxima) + visited-edge
+ *                                      arrays (index, Nsa, Qsa); arena_words a multiple of 8 and the base 32-byte aligned
  *   meta    uint32[n][4]               node count, arena top, round of the last root
  *   cursor  uint32[n][32]              path / leaf of the simulation in flight
  * One simulation of every game = ya_mcts_select -> evaluator -> ya_mcts_expand.  The tree persists

@@ -508,41 +508,48 @@ ya_k_forward(const float* __restrict__ features, uint16_t* __restrict__ logits, 
                         }
                         row_mx[q] = m;
                         if (s_desc) {
-                            // Runs of the action space: r = 0 bids [0, 202), r = c + 1 category c [202 + 252 c, +252).  A 32-column
-                            // chunk meets at most two runs; run starts are even, so a packed pair never straddles one.
-                            const int r0 = ((col0 + 50) * 4162) >> 20;
-                            const int end0 = 202 + 252 * r0;                               // first column of run r0 + 1
-                            const int start0 = r0 ? end0 - 252 : 0;
-                            if (s_desc & 1u) {                                             // bid row: legal index = column
-                                if (r0 == 0) {
+                            // The leaf's logit area keeps every logit at its column's position modulo 16 (csrc/ya_mcts.cu
+                            // "Logit area"): a bid row is columns [0, 208); a ten-dice row has, per OPEN category c, a
+                            // 272-slot copy of the 16-aligned column window around the category's run [202 + 252 c, +252).
+                            // So each of this chunk's two 16-column sectors goes out as ONE aligned 32-byte store per block
+                            // that wants it (a sector holding a run boundary may be wanted by both neighbours).
+                            uint32_t pk[16];
 #pragma unroll
-                                    for (int i = 0; i < 16; ++i)
-                                        if (col0 + 2 * i < 202)
-                                            *reinterpret_cast<uint32_t*>(s_dst + col0 + 2 * i) = pack2<F16>(f[2 * i], f[2 * i + 1]);
-                                }
-                            } else if (s_desc >> 13) {                                     // ten dice: 252 subsets per open category
+                            for (int i = 0; i < 16; ++i) pk[i] = pack2<F16>(f[2 * i], f[2 * i + 1]);
+                            auto store_sector = [&](uint16_t* dst, int h) {
+                                asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst),
+                                             "r"(pk[8 * h]), "r"(pk[8 * h + 1]), "r"(pk[8 * h + 2]), "r"(pk[8 * h + 3]),
+                                             "r"(pk[8 * h + 4]), "r"(pk[8 * h + 5]), "r"(pk[8 * h + 6]), "r"(pk[8 * h + 7]) : "memory");
+                            };
+                            if (s_desc & 1u) {                                             // bid row
+#pragma unroll
+                                for (int h = 0; h < 2; ++h)
+                                    if (col0 + 16 * h < 208) store_sector(s_dst + col0 + 16 * h, h);
+                            } else if (s_desc >> 13) {                                     // ten dice
                                 const uint32_t open = (s_desc >> 1) & 0xFFFu;              // bit c = category c open
-                                const bool ok0 = r0 > 0 && ((open >> (r0 - 1)) & 1u);
-                                const bool ok1 = r0 < 12 && ((open >> r0) & 1u);
-                                const int base0 = r0 > 0 ? 252 * __popc(open & ((1u << (r0 - 1)) - 1u)) : 0;
-                                const int d0 = base0 - start0;                             // legal index = column + d0 inside run r0
-                                const int d1 = base0 + (ok0 ? 252 : 0) - end0;             // ... and inside run r0 + 1
-                                if (ok0 || (ok1 && end0 < col0 + 32)) {
 #pragma unroll
-                                    for (int i = 0; i < 16; ++i) {
-                                        const int c = col0 + 2 * i;
-                                        const bool first = c < end0;
-                                        if (first ? ok0 : ok1)
-                                            *reinterpret_cast<uint32_t*>(s_dst + c + (first ? d0 : d1)) = pack2<F16>(f[2 * i], f[2 * i + 1]);
+                                for (int h = 0; h < 2; ++h) {
+                                    const int cs = col0 + 16 * h;
+                                    const int ra = ((cs + 50) * 4162) >> 20, rb = ((cs + 65) * 4162) >> 20;   // runs of the sector's first / last column
+#pragma unroll
+                                    for (int t = 0; t < 2; ++t) {
+                                        const int r = t ? rb : ra;                         // run r >= 1 = category r - 1
+                                        if ((t == 0 || rb != ra) && r >= 1 && r <= 12 && ((open >> (r - 1)) & 1u)) {
+                                            const int start = 202 + 252 * (r - 1);
+                                            const int rank = __popc(open & ((1u << (r - 1)) - 1u));
+                                            store_sector(s_dst + 272 * rank + (cs - (start & ~15)), h);
+                                        }
                                     }
                                 }
                             } else {                                                       // five dice: subset 0 of every open category
                                 const uint32_t open = (s_desc >> 1) & 0xFFFu;
-                                if (end0 < col0 + 32 && r0 < 12 && ((open >> r0) & 1u)) {    // category r0 starts in this chunk (run starts are
-                                    uint16_t* one = s_dst + __popc(open & ((1u << r0) - 1u));   // never chunk-aligned: 202 + 252 c = 2 mod 4)
+                                const int r0 = ((col0 + 50) * 4162) >> 20;
+                                const int end0 = 202 + 252 * r0;                           // category r0 starts here, if inside this chunk
+                                if (end0 < col0 + 32 && r0 < 12 && ((open >> r0) & 1u)) {
+                                    uint16_t* one = s_dst + __popc(open & ((1u << r0) - 1u));
 #pragma unroll
                                     for (int i = 0; i < 16; ++i)
-                                        if (col0 + 2 * i == end0) *one = (uint16_t)(pack2<F16>(f[2 * i], f[2 * i + 1]) & 0xFFFFu);
+                                        if (col0 + 2 * i == end0) *one = (uint16_t)(pk[i] & 0xFFFFu);
                                 }
                             }
                         }

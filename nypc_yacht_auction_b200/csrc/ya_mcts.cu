@@ -102,12 +102,30 @@ __device__ __forceinline__ Edges edges_at(uint32_t* base, int cap) {
 //               P[a] = 2^(l[a] * log2(e) + off), off = -max * log2(e) - log2(sum over legal of 2^((l - max) * log2(e))),
 //               evaluated where a prior is needed (one FMA + one EX2, the same two instructions that would have produced
 //               a stored float32 prior, so the values are bit-identical to storing them); half the bytes of a float32 row.
-//               Layout from N_PRIOR: ceil(L / 2) words of logits padded to 4 words | ceil(L / 32) group maxima (1 + bits of
-//               the largest unvisited P, 0 = none) | ceil(L / 32) words of visited bits.  A leaf whose legal moves all
-//               underflowed (MCTS.py:97-101) becomes a constant-prior node (N_KIND 1, P = 1 / L) on the same visited bits.
+//               Layout from N_PRIOR: logit area | ceil(L / 32) group maxima (1 + bits of the largest unvisited P, 0 = none) |
+//               ceil(L / 32) words of visited bits.  A leaf whose legal moves all underflowed (MCTS.py:97-101) becomes a
+//               constant-prior node (N_KIND 1, P = 1 / L) on the same visited bits.
+//               Logit area.  The forward kernel's epilogue owns 16 consecutive policy columns per 32-byte store, so the
+//               area keeps every logit at its column's position modulo 16: a bid row is columns [0, 208) as they are; a
+//               ten-dice row has one 272-slot block per OPEN category c, a copy of the 16-aligned column window that
+//               contains the category's 252 columns [202 + 252 c, +252) -- its logits start pad(c) = (10 + 12 c) mod 16
+//               slots into the block, the slots around them hold neighbouring columns and are never read; a five-dice
+//               row (one legal move per open category) is compact.  Every store of the epilogue is a full, aligned sector.
 enum { ROWS_F32 = 0, ROWS_CONST = 1, ROWS_L16F = 2, ROWS_L16B = 3 };
-__device__ __forceinline__ int l16_logit_words(int L) { return (((L + 1) >> 1) + 3) & ~3; }
-__device__ __forceinline__ int l16_words(int L) { return l16_logit_words(L) + 2 * ((L + 31) >> 5); }
+constexpr int kL16Block = 272;                                         // slots per open category of a ten-dice row
+__device__ __forceinline__ int l16_logit_words(uint32_t desc) {
+    if (desc >> 13) return __popc((desc >> 1) & 0xFFFu) * (kL16Block / 2);
+    return (((ya_legal_count(desc) + 1) >> 1) + 3) & ~3;               // bids: 104 words = columns [0, 208)
+}
+__device__ __forceinline__ int l16_words(uint32_t desc) { return l16_logit_words(desc) + 2 * ((ya_legal_count(desc) + 31) >> 5); }
+__device__ __forceinline__ int l16_pad(int cat) { return (10 + 12 * cat) & 15; }       // (202 + 252 cat) mod 16
+// slot of the k-th legal move's logit inside the logit area (16-bit units)
+__device__ __forceinline__ int l16_slot(uint32_t desc, int k) {
+    if (!(desc >> 13)) return k;
+    const int r = k / YA_N_SUBSET, sub = k - r * YA_N_SUBSET;
+    const int cat = __fns((desc >> 1) & 0xFFFu, 0, r + 1);
+    return kL16Block * r + l16_pad(cat) + sub;
+}
 template <int ROWS> __device__ __forceinline__ float l16_value(uint32_t h) {         // one 16-bit logit -> float32
     return ROWS == ROWS_L16F ? __half2float(__ushort_as_half((unsigned short)h)) : __uint_as_float(h << 16);
 }
@@ -238,7 +256,8 @@ __device__ __forceinline__ int ucb_select(const View& v, const uint32_t* node, i
     }
     if (ROWS >= ROWS_L16F) {
         // 16-bit logit row: the same arithmetic on P = 2^(l * log2(e) + off), evaluated on the fly
-        const int lw = l16_logit_words(L), nb = (L + 31) >> 5;
+        const uint32_t desc = node[N_DESC];
+        const int lw = l16_logit_words(desc), nb = (L + 31) >> 5;
         const uint16_t* lg = reinterpret_cast<const uint16_t*>(row);
         const float off = __uint_as_float(node[N_PCONST]);
         if (n_edges > 0) {
@@ -256,7 +275,7 @@ __device__ __forceinline__ int ucb_select(const View& v, const uint32_t* node, i
                     q[t] = ok ? ed.q[e] : 0.0;
                 }
 #pragma unroll
-                for (int t = 0; t < 2; ++t) lb[t] = lg[ai[t]];
+                for (int t = 0; t < 2; ++t) lb[t] = lg[l16_slot(desc, ai[t])];
 #pragma unroll
                 for (int t = 0; t < 2; ++t) {
                     if (e0 + W * t + sub < n_edges) {
@@ -295,13 +314,17 @@ __device__ __forceinline__ int ucb_select(const View& v, const uint32_t* node, i
                 }
             };
             if (kPer == 1) {
-                if (i0 < L) consider(i0, lg[i0]);
-            } else {
+                if (i0 < L) consider(i0, lg[l16_slot(desc, i0)]);
+            } else if (i0 < L) {
+                // kPer (2, 4 or 8) consecutive legal moves starting at a multiple of kPer: 252 is a multiple of 4, so for
+                // kPer <= 4 they lie in one category block at consecutive, even-aligned slots
+                static_assert(kPer == 1 || kPer == 2 || kPer == 4, "a lane's moves must not straddle a category block");
+                const int s0 = l16_slot(desc, i0);
 #pragma unroll
                 for (int t = 0; t < kPer / 2; ++t) {
                     const int i = i0 + 2 * t;
                     if (i < L) {                                        // the pair's word lies inside the logit area
-                        const uint32_t w2 = row[i >> 1];
+                        const uint32_t w2 = row[(s0 >> 1) + t];
                         consider(i, w2 & 0xFFFFu);
                         consider(i + 1, w2 >> 16);
                     }
@@ -447,7 +470,7 @@ __device__ __forceinline__ bool backup_edge(const View& v, uint32_t* node, int a
                 v.arena[node[N_PRIOR] + (ai >> 5)] |= 1u << (ai & 31);      // constant-prior node: visited bitmask
             } else if (ROWS >= ROWS_L16F) {
                 const int Ln = ya_legal_count(node[N_DESC]);
-                v.arena[node[N_PRIOR] + l16_logit_words(Ln) + ((Ln + 31) >> 5) + (ai >> 5)] |= 1u << (ai & 31);
+                v.arena[node[N_PRIOR] + l16_logit_words(node[N_DESC]) + ((Ln + 31) >> 5) + (ai >> 5)] |= 1u << (ai & 31);
                 fresh = 1;
             } else {
                 v.arena[node[N_PRIOR] + ai] |= 0x80000000u;                 // mark the prior entry as visited
@@ -463,14 +486,15 @@ __device__ __forceinline__ bool backup_edge(const View& v, uint32_t* node, int a
         uint32_t* row = v.arena + node[N_PRIOR];
         uint32_t e = 0;
         if (ROWS >= ROWS_L16F) {
-            const int lw = l16_logit_words(L), nb = (L + 31) >> 5;
+            const uint32_t desc = node[N_DESC];
+            const int lw = l16_logit_words(desc), nb = (L + 31) >> 5;
             const uint32_t seen = row[lw + nb + (ai >> 5)];
             const float off = __uint_as_float(node[N_PCONST]);
             const uint16_t* lg = reinterpret_cast<const uint16_t*>(row);
 #pragma unroll
             for (int t = 0; t < 32 / W; ++t) {
                 const int i = (ai & ~31) + t * W + sub;
-                if (i < L && !((seen >> (i & 31)) & 1u)) e = max(e, __float_as_uint(l16_prior<ROWS>(lg[i], off)) + 1u);
+                if (i < L && !((seen >> (i & 31)) & 1u)) e = max(e, __float_as_uint(l16_prior<ROWS>(lg[l16_slot(desc, i)], off)) + 1u);
             }
             e = tm.reduce_max(e);
             if (sub == 0) row[lw + (ai >> 5)] = e;
@@ -563,9 +587,10 @@ __device__ __forceinline__ void descend(const View& v, YaState cur, Walk& w, uin
             if (idx < 0) {                                           // leaf: MCTS.py:84-115 (evaluation happens outside)
                 uint32_t desc = ya_mask_desc(cur, 1);
                 int L = ya_legal_count(desc);
-                uint32_t row_at = (w.arena_top + 3u) & ~3u;         // 16-byte aligned prior rows
+                // 16-byte aligned prior rows; logit rows 32-byte aligned (the forward's epilogue stores whole sectors)
+                uint32_t row_at = ROWS >= ROWS_L16F ? (w.arena_top + 7u) & ~7u : (w.arena_top + 3u) & ~3u;
                 if ((int)w.node_count >= v.max_nodes) { w.err = E_NODES_FULL; w.kind = KIND_ERROR; break; }
-                const uint32_t words = ROWS == ROWS_CONST ? (uint32_t)((L + 31) >> 5) : ROWS >= ROWS_L16F ? (uint32_t)l16_words(L) : (uint32_t)row_words(L);
+                const uint32_t words = ROWS == ROWS_CONST ? (uint32_t)((L + 31) >> 5) : ROWS >= ROWS_L16F ? (uint32_t)l16_words(desc) : (uint32_t)row_words(L);
                 if (row_at + words > v.arena_words) { w.err = E_ARENA_FULL; w.kind = KIND_ERROR; break; }
                 idx = (int)w.node_count;
                 if (lane == 0) {
@@ -850,7 +875,7 @@ ya_k_mcts_expand_rows(ya_mcts_tree tree, const uint16_t* __restrict__ logits_all
     const int L = ya_legal_count(desc);
     if (L > 0) {
         uint32_t* row = v.arena + leaf_row;
-        const int lw = l16_logit_words(L), nb = (L + 31) >> 5, nw_all = (L + 1) >> 1;
+        const int lw = l16_logit_words(desc), nb = (L + 31) >> 5, nw_all = (L + 1) >> 1;
         const uint32_t raw_s = (uint32_t)__cvta_generic_to_shared(raw);
         const uint32_t* lg = FROM_DENSE ? reinterpret_cast<const uint32_t*>(logits_all + g * ld) : nullptr;   // two logits per word
         if (FROM_DENSE) {
@@ -874,7 +899,18 @@ ya_k_mcts_expand_rows(ya_mcts_tree tree, const uint16_t* __restrict__ logits_all
             } else {                                                   // five dice: subset 0 of every open category
                 if (lane < L) reinterpret_cast<uint16_t*>(raw)[lane] = reinterpret_cast<const uint16_t*>(lg)[ya_nth_legal(desc, lane)];
             }
-        } else {                                                       // the row the forward kernel filled: 16-byte chunks
+        } else if (desc >> 13) {                                       // the row the forward kernel filled: 126 words per open
+            int k0 = 0, blk = 0;                                       // category, pad / 2 words into its 136-word block
+            for (uint32_t open = (desc >> 1) & 0xFFFu; open; open &= open - 1, k0 += YA_N_SUBSET / 2, blk += kL16Block / 2) {
+                const uint32_t dst = raw_s + 4u * (uint32_t)(k0 + lane);
+                const uint32_t* src = row + blk + (l16_pad(__ffs(open) - 1) >> 1) + lane;
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n\t"
+                             "cp.async.ca.shared.global [%0 + 128], [%1 + 128], 4;\n\t"
+                             "cp.async.ca.shared.global [%0 + 256], [%1 + 256], 4;" ::"r"(dst), "l"(src) : "memory");
+                if (lane < YA_N_SUBSET / 2 - 96)
+                    asm volatile("cp.async.ca.shared.global [%0 + 384], [%1 + 384], 4;" ::"r"(dst), "l"(src) : "memory");
+            }
+        } else {                                                       // bid / five-dice rows are compact: 16-byte chunks
             for (int j = lane * 4; j < nw_all; j += 128)
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(raw_s + 4u * (uint32_t)j), "l"(row + j) : "memory");
         }
@@ -887,9 +923,8 @@ ya_k_mcts_expand_rows(ya_mcts_tree tree, const uint16_t* __restrict__ logits_all
                 const uint32_t* nd = v.nodes + (int64_t)(pe & 0xFFFFu) * kNodeWords;
                 const int ne = (int)nd[N_NEDGE], ai = (int)(pe >> 16);
                 const uint32_t* prow = v.arena + nd[N_PRIOR];
-                const int Lp = ya_legal_count(nd[N_DESC]);
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(prow + ((ai & ~31) >> 1)));
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(prow + l16_logit_words(Lp) + (ai >> 5)));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(prow + (l16_slot(nd[N_DESC], ai & ~31) >> 1)));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(prow + l16_logit_words(nd[N_DESC]) + (ai >> 5)));
                 if (ne > 0) {
                     const uint32_t* eb = v.arena + nd[N_EDGES];
                     const int cap = edge_cap(ne);
@@ -916,8 +951,17 @@ ya_k_mcts_expand_rows(ya_mcts_tree tree, const uint16_t* __restrict__ logits_all
         }
         asm volatile("cp.async.wait_all;" ::: "memory");
         __syncwarp();
-        if (FROM_DENSE)                                                // the compacted legal logits become the node's row
-            for (int j = lane; j < nw_all; j += 32) row[j] = raw[j];
+        if (FROM_DENSE) {                                              // the compacted legal logits become the node's row
+            if (desc >> 13) {
+                int k0 = 0, blk = 0;
+                for (uint32_t open = (desc >> 1) & 0xFFFu; open; open &= open - 1, k0 += YA_N_SUBSET / 2, blk += kL16Block / 2) {
+                    uint32_t* dst = row + blk + (l16_pad(__ffs(open) - 1) >> 1);
+                    for (int j = lane; j < YA_N_SUBSET / 2; j += 32) dst[j] = raw[k0 + j];
+                }
+            } else {
+                for (int j = lane; j < nw_all; j += 32) row[j] = raw[j];
+            }
+        }
         // exp(l - max) = 2^(l * log2(e) - max * log2(e)): one FMA + one EX2 per logit; the normalisation is folded into
         // the exponent as well (P = 2^(.. - log2(total))).
         const float off_sum = -mx * kLog2e;
@@ -1217,6 +1261,8 @@ int ya_mcts_select(const ya_mcts_tree* tree, const uint32_t* states, int64_t str
                    uint32_t* leaf_desc, int32_t* err_flag, void* stream) {
     if (!tree_ok(tree) || !(cpuct >= 0.0f)) return (int)cudaErrorInvalidValue;   // group maxima rely on u monotone in P
     if (rows != YA_ROWS_F32 && rows != YA_ROWS_FP16 && rows != YA_ROWS_BF16) return (int)cudaErrorInvalidValue;
+    if (rows != YA_ROWS_F32 && ((tree->arena_words % 8) != 0 || (reinterpret_cast<uintptr_t>(tree->arena) & 31u)))
+        return (int)cudaErrorMisalignedAddress;                                   // logit rows are 32-byte aligned
     if ((leaf_dst == nullptr) != (leaf_desc == nullptr)) return (int)cudaErrorInvalidValue;
     const dim3 grid(select_blocks(tree->n)), block(kWarpsPerBlock * 32);
     const cudaStream_t st = (cudaStream_t)stream;

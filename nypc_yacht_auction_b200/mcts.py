@@ -45,7 +45,7 @@ class TreePool:
             per_sim_kb = 48.0 if self.rows == 0 else 28.0
             arena_mb_per_game = max(num_sims * per_sim_kb / 1024.0, 0.25)
         words = int(arena_mb_per_game * 2 ** 20) // 4
-        self.arena_words = words - (words % 4)
+        self.arena_words = words - (words % 8)          # every game's arena starts 32-byte aligned (logit rows)
         d = self.device
         self.nodes = torch.zeros((self.n, self.max_nodes, lib.ya_mcts_node_words()), dtype=torch.int32, device=d)
         self.ht = torch.zeros((self.n, self.ht_size), dtype=torch.int16, device=d)

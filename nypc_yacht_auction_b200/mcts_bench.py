@@ -13,11 +13,12 @@ import time
 
 PLIES = 48
 # SURVEY.md section 8(d), algorithmic bytes per simulation: ~7.5 KB (uniform prior: prior rows + edges on a depth-2 path),
-# ~33 KB with the network (+ features + float32 logits written and read once).  The 16-bit figure is what THIS engine moves
-# by design: 236 B features + 3232 x 2 B logits written + 2 x L legal logits read (L ~ 910 on average) + 4 x L row write.
+# ~33 KB with the network (+ features + float32 logits written and read once).  The "engine" figure is what THIS engine moves
+# by design: 236 B features + the L legal logits written once by the forward's epilogue and read once by expand as 16-bit
+# values (L ~ 910 on average) + L / 4 B of group maxima and visited bits + ~3.6 KB of node / edge traffic on the path + value.
 ALGO_BYTES_UNIFORM = 7500
 ALGO_BYTES_NN_F32 = 33000
-ALGO_BYTES_NN_16 = 236 + 3232 * 2 + 2 * 910 + 4 * 910 + 3600 + 200
+ALGO_BYTES_NN_16 = 236 + 2 * 910 + 2 * 910 + 910 // 4 + 3600 + 200
 
 
 def _fence(torch, dev, dist, world):

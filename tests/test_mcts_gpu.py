@@ -206,15 +206,28 @@ def test_fused_logits_expand_matches_softmax_mask_renorm(dtype):
     assert 202 in legal_counts and max(legal_counts) >= 2016 and min(legal_counts) <= 12, legal_counts
 
 
+def logit_row_slots(desc, n_legal):
+    """Slot of every legal move's logit inside a logit-row node's logit area (csrc/ya_mcts.cu "Logit area"), and the
+    area's size in words: ten-dice rows keep one 272-slot block per open category, the category's 252 logits starting
+    (10 + 12 c) mod 16 slots into it; bid and five-dice rows are compact."""
+    if desc >> 13:
+        cats = [c for c in range(12) if (desc >> (1 + c)) & 1]
+        slots = np.concatenate([272 * r + ((10 + 12 * c) & 15) + np.arange(252) for r, c in enumerate(cats)])
+        assert len(slots) == n_legal
+        return slots, 136 * len(cats)
+    return np.arange(n_legal), (((n_legal + 1) // 2) + 3) & ~3
+
+
 def decode_logit_row(pool, g, node, n_legal):
-    """(priors float64[L], group maxima float32[ceil(L/32)], visited words) of a logit-row node (csrc/ya_mcts.cu ROWS_L16):
-    P[k] = 2^(l[k] * log2(e) + off) from the row's 16-bit logits and the node's exponent offset."""
+    """(priors float64[L], legal logits float64[L], group-maximum words, visited words) of a logit-row node (csrc/ya_mcts.cu
+    ROWS_L16): P[k] = 2^(l[k] * log2(e) + off) from the row's 16-bit logits and the node's exponent offset."""
     nodes = pool.nodes[g, node].cpu().numpy().view(np.uint32)
     assert int(nodes[13]) == 2, "not a logit-row node"
     off = int(nodes[10])
-    lw, nb = (((n_legal + 1) // 2) + 3) & ~3, (n_legal + 31) // 32
+    slots, lw = logit_row_slots(int(nodes[8]), n_legal)
+    nb = (n_legal + 31) // 32
     words = pool.arena[g, off:off + lw + 2 * nb].cpu().numpy().view(np.uint32)
-    halves = words[:lw].view(np.uint16)[:n_legal]
+    halves = words[:lw].view(np.uint16)[slots]
     if pool.rows == 2:
         lg = halves.view(np.float16).astype(np.float64)
     else:
