@@ -46,6 +46,7 @@ def parse_args():
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary kernels and every MCTS block")
     ap.add_argument("--no-1m", action="store_true", help="skip the configs[4] block (1,048,576 games, ~1 min on one GPU)")
     ap.add_argument("--games-1m", type=int, default=1 << 20, help="total games of the configs[4] block (all ranks together)")
+    ap.add_argument("--wave-1m", type=int, default=2 * 148 * 128, help="games per wave and tree pool of the configs[4] block")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     return ap.parse_args()
 
@@ -564,7 +565,7 @@ def run_extras(args, torch, env, dev, n, peaks, prof, rank=0, world=1, dist=None
     if not args.no_1m:
         total = args.games_1m
         r = mb.selfplay_1m(torch, dev, dist, rank, world, lambda m: FusedYachtEvaluator(net, m, precision="fp16"), total, 100,
-                           min(16384, total // world), args.seed + 3)
+                           args.wave_1m, args.seed + 3)
         r.update({"workload": "configs[4]: %d concurrent games sharded over %d GPU(s) by global game id, numMCTSSims=100, random-init "
                               "YachtNNet, waves of %d games on one tree pool per GPU" % (total, world, r["wave_games"]),
                   "metric": "mcts_sims_per_sec", "unit": "sims/s", "dtype": "fp16 operands / f32 accumulate",

@@ -225,29 +225,38 @@ class BatchedArena:
 
 def self_play_in_waves(total_games, wave_games, num_sims, evaluator, first_game=0, on_wave=None, use_graph=True, **kwargs):
     """BASELINE.json configs[4]: more concurrent games than one tree pool fits in HBM (1,048,576 games over
-    8 GPUs = 131,072 per GPU at ~4 MB of tree per game) are played as consecutive waves of `wave_games`
+    8 GPUs = 131,072 per GPU at ~2.8 MB of tree per game) are played as consecutive waves of `wave_games`
     games on ONE pool; wave w owns global games [first_game + w*wave_games, ...), so the result is the same
-    as one huge batch (Philox streams are keyed by the global game id).  `on_wave(w, examples)` receives
-    each wave's example tensors (copy or reduce them there: the buffers are reused).  Returns the total
-    (p1_wins, p2_wins, draws)."""
-    assert total_games % wave_games == 0, "total_games must be a multiple of wave_games"
-    sp = BatchedSelfPlay(wave_games, num_sims, evaluator=evaluator, game_base=first_game, **kwargs)
-    if use_graph and not getattr(sp.mcts.evaluator, "uniform", False):
-        sp.mcts.capture_graph()                                  # one simulation wave, replayed numMCTSSims times per move
+    as one huge batch (Philox streams are keyed by the global game id).  A remainder that does not fill a wave is
+    played last on a pool of its own size (e.g. waves of 148 x 128 x 2 games keep every SM busy in the forward kernel
+    and never divide a power of two).  `on_wave(w, examples)` receives each wave's example tensors (copy or reduce them
+    there: the buffers are reused).  Returns the total (p1_wins, p2_wins, draws)."""
+    full, rest = divmod(int(total_games), int(wave_games))
     p1 = p2 = dr = 0
-    for w in range(total_games // wave_games):
-        if w:
-            base = first_game + w * wave_games
-            sp.env.game_base = base                              # same pool, next slice of global game ids (the captured
-                                                                 # graph reads them from device memory: mcts.sync_game_base)
-            sp.mcts.pool.reset()
-            sp.env.episode.zero_()
-            sp.env.reset()
-        ex = sp.execute_episodes()
-        r = (ex["result_p1"] if ex is not None else sp.env.game_ended(players=torch.ones_like(sp.env.players)))
-        p1 += int((r > 0.5).sum().item())
-        p2 += int((r < -0.5).sum().item())
-        dr += int((r.abs() < 0.5).sum().item())
-        if on_wave is not None:
-            on_wave(w, ex)
+    w = 0
+    for n, count, base0 in ((int(wave_games), full, first_game), (rest, 1 if rest else 0, first_game + full * int(wave_games))):
+        if count == 0:
+            continue
+        ev = evaluator
+        if n != wave_games and hasattr(ev, "with_private_buffers"):
+            ev = ev.with_private_buffers(n)
+        sp = BatchedSelfPlay(n, num_sims, evaluator=ev, game_base=base0, **kwargs)
+        if use_graph and not getattr(sp.mcts.evaluator, "uniform", False):
+            sp.mcts.capture_graph()                              # one simulation wave, replayed numMCTSSims times per move
+        for i in range(count):
+            if i:
+                sp.env.game_base = base0 + i * n                 # same pool, next slice of global game ids (the captured
+                sp.mcts.pool.reset()                             # graph reads them from device memory: mcts.sync_game_base)
+                sp.env.episode.zero_()
+                sp.env.reset()
+            ex = sp.execute_episodes()
+            r = (ex["result_p1"] if ex is not None else sp.env.game_ended(players=torch.ones_like(sp.env.players)))
+            p1 += int((r > 0.5).sum().item())
+            p2 += int((r < -0.5).sum().item())
+            dr += int((r.abs() < 0.5).sum().item())
+            if on_wave is not None:
+                on_wave(w, ex)
+            w += 1
+        del sp                                                   # the pool goes back before the remainder's pool is made
+        torch.cuda.empty_cache()
     return p1, p2, dr

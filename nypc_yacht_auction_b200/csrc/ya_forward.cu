@@ -59,6 +59,9 @@ __device__ __forceinline__ uint32_t a_tile_offset(int r, int c8) {
 }
 
 template <bool F16>
+#ifdef YA_EXP_TRUNK_NO_TANH                            // profiling experiment: the trunk epilogue without its MUFU op
+#define silu_from_half(x) ((x) * 1.0009765625f)
+#endif
 __device__ __forceinline__ void pack_store_a(uint8_t* a_tile, int row, int c8_first, const uint32_t (&r)[32]) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -485,15 +488,24 @@ ya_k_forward(const float* __restrict__ features, uint16_t* __restrict__ logits, 
                 for (int q = 0; q < n_my; ++q) {
                     const int pp = part + q;
                     uint32_t r[32];
+#ifdef YA_EXP_POLICY_NO_LD                                 // profiling experiment: the MMA / bulk-copy pipeline alone
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) r[i] = 0u;
+#else
                     tmem_ld32(t_lane + kPolicyTile + (j % 3) * kPolicyTile + pp * 32, r);
                     tmem_ld_wait();
+#endif
                     if (q == n_my - 1) {
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&bars[9 + j % 3]); // this warp's share of the accumulator is in registers
                     }
                     const int col0 = j * kPolicyTile + pp * 32;
+#if defined(YA_EXP_POLICY_NO_LD) || defined(YA_EXP_POLICY_NO_ST)
+                    if (col0 < kPolicyCols && r[0] == 0x7FC12345u) {   // profiling experiment: epilogue without its stores
+#else
                     if (col0 < kPolicyCols) {
+#endif
                         const float* bias = bias_all + col0;
                         float f[32];
 #pragma unroll

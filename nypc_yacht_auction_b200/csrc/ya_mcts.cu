@@ -260,6 +260,9 @@ __device__ __forceinline__ int ucb_select(const View& v, const uint32_t* node, i
         const int lw = l16_logit_words(desc), nb = (L + 31) >> 5;
         const uint16_t* lg = reinterpret_cast<const uint16_t*>(row);
         const float off = __uint_as_float(node[N_PCONST]);
+        // the group maxima (<= 95 words) and visited bits are needed after the visited-edge loop, whose loads depend on one
+        // another (edge -> logit): start pulling their lines now (one 128-byte line per lane that has one)
+        if (sub * 32 < 2 * nb) asm volatile("prefetch.global.L1 [%0];" ::"l"(row + lw + sub * 32));
         if (n_edges > 0) {
             const Edges ed = edges_at(v.arena + node[N_EDGES], edge_cap(n_edges));
             for (int e0 = 0; e0 < n_edges; e0 += 2 * W) {
@@ -491,12 +494,15 @@ __device__ __forceinline__ bool backup_edge(const View& v, uint32_t* node, int a
             const uint32_t seen = row[lw + nb + (ai >> 5)];
             const float off = __uint_as_float(node[N_PCONST]);
             const uint16_t* lg = reinterpret_cast<const uint16_t*>(row);
+            float m = -CUDART_INF_F;                                 // the group's largest unvisited logit; its maximum is P(that)
 #pragma unroll
             for (int t = 0; t < 32 / W; ++t) {
                 const int i = (ai & ~31) + t * W + sub;
-                if (i < L && !((seen >> (i & 31)) & 1u)) e = max(e, __float_as_uint(l16_prior<ROWS>(lg[l16_slot(desc, i)], off)) + 1u);
+                if (i < L && !((seen >> (i & 31)) & 1u)) m = fmaxf(m, l16_value<ROWS>(lg[l16_slot(desc, i)]));
             }
-            e = tm.reduce_max(e);
+#pragma unroll
+            for (int o = W / 2; o; o >>= 1) m = fmaxf(m, tm.xor_(m, o));
+            e = m == -CUDART_INF_F ? 0u : __float_as_uint(ex2_approx(fmaf(m, kLog2e, off))) + 1u;
             if (sub == 0) row[lw + (ai >> 5)] = e;
         } else {
 #pragma unroll
@@ -863,6 +869,7 @@ ya_k_mcts_expand_rows(ya_mcts_tree tree, const uint16_t* __restrict__ logits_all
                       uint32_t* __restrict__ sim_counter, int32_t* __restrict__ err_flag) {
     constexpr int ROWS = F16 ? ROWS_L16F : ROWS_L16B;
     __shared__ __align__(16) uint32_t raw_all[kLogitWarps][kLogitCols / 2];
+    __shared__ float group_logit[kLogitWarps][96];                     // largest logit of every group of 32 legal moves
     const int lane = threadIdx.x & 31;
     uint32_t* raw = raw_all[threadIdx.x >> 5];
     const int64_t g = (int64_t)blockIdx.x * kLogitWarps + (threadIdx.x >> 5);
@@ -968,28 +975,62 @@ ya_k_mcts_expand_rows(ya_mcts_tree tree, const uint16_t* __restrict__ logits_all
         const uint16_t* rc = reinterpret_cast<const uint16_t*>(raw);
         const bool pairs = !(L & 1), quads = !(L & 3);                 // ten-dice rows: L = 252 * open categories
         const int nw = L >> 1;
+        // ONE pass over the legal logits: the softmax denominator and, per group of 32 legal moves, the largest logit
+        // (the group maximum of the priors is P(largest logit): P is a monotone function of the logit)
+        float* gl = group_logit[threadIdx.x >> 5];
         float total = 0.0f;
         if (quads) {
             float t1 = 0.0f, t2 = 0.0f, t3 = 0.0f;
             const uint2* raw2 = reinterpret_cast<const uint2*>(raw);
-            for (int j = lane; j < (L >> 2); j += 32) {
-                const uint2 w = raw2[j];
-                total += l16_prior<ROWS>(w.x & 0xFFFFu, off_sum);
-                t1 += l16_prior<ROWS>(w.x >> 16, off_sum);
-                t2 += l16_prior<ROWS>(w.y & 0xFFFFu, off_sum);
-                t3 += l16_prior<ROWS>(w.y >> 16, off_sum);
+            const int nq = L >> 2;
+            for (int j0 = 0; j0 < nq; j0 += 32) {                      // a lane owns four consecutive logits, eight lanes a group
+                const int j = j0 + lane;
+                float m = -CUDART_INF_F;
+                if (j < nq) {
+                    const uint2 w = raw2[j];
+                    const float a0 = l16_value<ROWS>(w.x & 0xFFFFu), a1 = l16_value<ROWS>(w.x >> 16);
+                    const float a2 = l16_value<ROWS>(w.y & 0xFFFFu), a3 = l16_value<ROWS>(w.y >> 16);
+                    total += ex2_approx(fmaf(a0, kLog2e, off_sum));
+                    t1 += ex2_approx(fmaf(a1, kLog2e, off_sum));
+                    t2 += ex2_approx(fmaf(a2, kLog2e, off_sum));
+                    t3 += ex2_approx(fmaf(a3, kLog2e, off_sum));
+                    m = fmaxf(fmaxf(a0, a1), fmaxf(a2, a3));
+                }
+                m = fmaxf(m, __shfl_xor_sync(0xFFFFFFFFu, m, 1));
+                m = fmaxf(m, __shfl_xor_sync(0xFFFFFFFFu, m, 2));
+                m = fmaxf(m, __shfl_xor_sync(0xFFFFFFFFu, m, 4));
+                if ((lane & 7) == 0 && j < nq) gl[j >> 3] = m;         // group of legal moves 4j .. 4j + 31
             }
             total = (total + t1) + (t2 + t3);
         } else if (pairs) {
             float t1 = 0.0f;
-            for (int j = lane; j < nw; j += 32) {
-                const uint32_t w = raw[j];
-                total += l16_prior<ROWS>(w & 0xFFFFu, off_sum);
-                t1 += l16_prior<ROWS>(w >> 16, off_sum);
+            for (int j0 = 0; j0 < nw; j0 += 32) {                      // two logits per lane, sixteen lanes a group
+                const int j = j0 + lane;
+                float m = -CUDART_INF_F;
+                if (j < nw) {
+                    const uint32_t w = raw[j];
+                    const float a0 = l16_value<ROWS>(w & 0xFFFFu), a1 = l16_value<ROWS>(w >> 16);
+                    total += ex2_approx(fmaf(a0, kLog2e, off_sum));
+                    t1 += ex2_approx(fmaf(a1, kLog2e, off_sum));
+                    m = fmaxf(a0, a1);
+                }
+#pragma unroll
+                for (int o = 1; o < 16; o <<= 1) m = fmaxf(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
+                if ((lane & 15) == 0 && j < nw) gl[j >> 4] = m;
             }
             total += t1;
         } else {
-            for (int k = lane; k < L; k += 32) total += l16_prior<ROWS>(rc[k], off_sum);
+            for (int k0 = 0; k0 < L; k0 += 32) {
+                const int k = k0 + lane;
+                float m = -CUDART_INF_F;
+                if (k < L) {
+                    m = l16_value<ROWS>(rc[k]);
+                    total += ex2_approx(fmaf(m, kLog2e, off_sum));
+                }
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) m = fmaxf(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
+                if (lane == 0) gl[k0 >> 5] = m;
+            }
         }
 #pragma unroll
         for (int o = 16; o; o >>= 1) total += __shfl_xor_sync(0xFFFFFFFFu, total, o);
@@ -997,36 +1038,11 @@ ya_k_mcts_expand_rows(ya_mcts_tree tree, const uint16_t* __restrict__ logits_all
         uint32_t* seen = row + lw + nb;
         uint32_t* node = v.nodes + (int64_t)v.cur[C_NODE] * kNodeWords;
         for (int b = lane; b < nb; b += 32) seen[b] = 0u;
+        __syncwarp();
         if (total > 0.0f) {
             const float off_p = off_sum - __log2f(total);
             if (lane == 0) node[N_PCONST] = __float_as_uint(off_p);
-            if (quads) {
-                // 128 priors = four groups per iteration: a lane owns four consecutive priors, eight lanes own a group
-                // and reduce its maximum with three shuffles
-                const uint2* raw2 = reinterpret_cast<const uint2*>(raw);
-                const int nq = L >> 2;
-                for (int j0 = 0; j0 < nq; j0 += 32) {
-                    const int j = j0 + lane;
-                    uint32_t e = 0;
-                    if (j < nq) {
-                        const uint2 w = raw2[j];
-                        const float pa = l16_prior<ROWS>(w.x & 0xFFFFu, off_p), pb = l16_prior<ROWS>(w.x >> 16, off_p);
-                        const float pc = l16_prior<ROWS>(w.y & 0xFFFFu, off_p), pd = l16_prior<ROWS>(w.y >> 16, off_p);
-                        e = __float_as_uint(fmaxf(fmaxf(pa, pb), fmaxf(pc, pd))) + 1u;
-                    }
-                    e = max(e, __shfl_xor_sync(0xFFFFFFFFu, e, 1));
-                    e = max(e, __shfl_xor_sync(0xFFFFFFFFu, e, 2));
-                    e = max(e, __shfl_xor_sync(0xFFFFFFFFu, e, 4));
-                    if ((lane & 7) == 0 && j < nq) gm[j >> 3] = e;     // group of priors 4j .. 4j + 31
-                }
-            } else {
-                for (int k0 = 0; k0 < L; k0 += 32) {
-                    const int k = k0 + lane;
-                    uint32_t e = k < L ? __float_as_uint(l16_prior<ROWS>(rc[k], off_p)) + 1u : 0u;
-                    e = __reduce_max_sync(0xFFFFFFFFu, e);
-                    if (lane == 0) gm[k0 >> 5] = e;
-                }
-            }
+            for (int b = lane; b < nb; b += 32) gm[b] = __float_as_uint(ex2_approx(fmaf(gl[b], kLog2e, off_p))) + 1u;
         } else if (lane == 0) {                                        // every legal move underflowed (MCTS.py:97-101): Ps = 1 / L,
             node[N_KIND] = 1u;                                         // a constant-prior node on the row's visited bits
             node[N_PRIOR] = leaf_row + (uint32_t)(lw + nb);

@@ -161,7 +161,7 @@ def selfplay_1m(torch, dev, dist, rank, world, evaluator_factory, total, sims, w
     from .dist import shard_range
     first, last = shard_range(total, rank, world)
     mine = last - first
-    assert mine % wave == 0, "games per rank must be a multiple of the wave size"
+    wave = min(wave, mine)
     ev = evaluator_factory(wave)
     host = {}
     tally = {"d2h": 0, "waves": 0}
@@ -170,8 +170,10 @@ def selfplay_1m(torch, dev, dist, rank, world, evaluator_factory, total, sims, w
         for name in ("features", "actions", "counts", "value", "result_p1"):
             if name not in host:
                 host[name] = torch.empty(ex[name].shape, dtype=ex[name].dtype, pin_memory=True)
-            host[name].copy_(ex[name], non_blocking=True)
-            tally["d2h"] += host[name].numel() * host[name].element_size()
+            gd = 0 if ex[name].dim() == 1 else 1                 # a ragged last wave fills only its share of the buffer
+            dst = host[name].narrow(gd, 0, ex[name].shape[gd])
+            dst.copy_(ex[name], non_blocking=True)
+            tally["d2h"] += dst.numel() * dst.element_size()
         tally["waves"] += 1
 
     _fence(torch, dev, dist, world)
@@ -188,11 +190,15 @@ def selfplay_1m(torch, dev, dist, rank, world, evaluator_factory, total, sims, w
         dist.all_reduce(res)
     res = [int(x) for x in res.tolist()]
     assert sum(res) == total, "every game must finish"
-    out = {"games": total, "games_per_gpu": mine, "wave_games": wave, "waves_per_gpu": tally["waves"], "num_mcts_sims": sims,
+    full, rest = divmod(mine, wave)
+    out = {"games": total, "games_per_gpu": mine, "wave_games": wave, "waves_per_gpu": tally["waves"], "last_wave_games": rest or wave,
+           "num_mcts_sims": sims,
            "seconds": ms * 1e-3, "wall_seconds": wall, "sims_per_sec": total * PLIES * sims / (ms * 1e-3),
            "game_steps_per_sec": total * PLIES / (ms * 1e-3), "scaling": "strong",
            "outcomes_p1_p2_draw": res, "d2h_bytes_per_gpu": tally["d2h"],
            "gpu_launches_per_gpu": tally["waves"] * _launches_per_episode(3, sims),
+           "wave_choice": "148 SMs x 128 leaves x 2 = 37,888 games per wave: every SM runs a forward CTA pair of tiles, the ragged "
+                          "remainder is played last on a pool of its own size" if wave % (148 * 128) == 0 else "as configured",
            "includes": "pool reset + re-deal per wave, example recording, device->host copy of every wave's examples (pinned)"}
     del host
     torch.cuda.empty_cache()

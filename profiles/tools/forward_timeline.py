@@ -21,10 +21,11 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
 ev = FusedYachtEvaluator(YachtPolicyValueNet().to(dev).eval(), n)
 x = torch.rand((n, 59), device=dev)
 vp = ctypes.c_void_p
-lib.ya_nn_forward.argtypes = [vp, vp, vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int64, ctypes.c_float, vp]
+lib.ya_nn_forward.argtypes = [vp, vp, vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_int, vp, vp, vp]
+logits = torch.empty((n, 3232), dtype=torch.float16, device=dev)
 for _ in range(5):
-    rc = lib.ya_nn_forward(x.data_ptr(), ev.logits.data_ptr(), ev.values.data_ptr(), ev.row_max.data_ptr(), ev.fw_w.data_ptr(),
-                           ev.fw_p.data_ptr(), ev.fw_off, ev.nblocks, n, ev.eps, torch.cuda.current_stream().cuda_stream)
+    rc = lib.ya_nn_forward(x.data_ptr(), logits.data_ptr(), ev.values.data_ptr(), ev.row_max.data_ptr(), ev.fw_w.data_ptr(),
+                           ev.fw_p.data_ptr(), ev.fw_off, ev.nblocks, n, ev.eps, 1, None, None, torch.cuda.current_stream().cuda_stream)
     assert rc == 0, rc
     torch.cuda.synchronize()
 buf = (ctypes.c_ulonglong * 1024)()
@@ -42,3 +43,11 @@ base = 3 * nst
 pol = t[base:base + 27]
 print("policy: first accumulator ready at %.2f us; per tile (us):" % ((pol[0] - t0) / 1e3), " ".join("%.2f" % ((pol[i + 1] - pol[i]) / 1e3) for i in range(26)))
 print("total %.2f us" % ((pol[26] - t0) / 1e3))
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(20):
+    lib.ya_nn_forward(x.data_ptr(), logits.data_ptr(), ev.values.data_ptr(), ev.row_max.data_ptr(), ev.fw_w.data_ptr(),
+                      ev.fw_p.data_ptr(), ev.fw_off, ev.nblocks, n, ev.eps, 1, None, None, torch.cuda.current_stream().cuda_stream)
+e1.record()
+torch.cuda.synchronize()
+print("variant %s: %.1f us per forward (CUDA events, %d leaves, dense logits)" % ("".join(extra) or "production", e0.elapsed_time(e1) * 50.0, n))

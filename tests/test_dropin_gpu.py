@@ -147,19 +147,20 @@ def _wave_examples(total, wave, sims, evaluator, use_graph, seed, first):
 
 def _assert_waves_equal(got, ref, wave):
     for w in sorted(got):
-        sl = slice(wave * w, wave * w + wave)
+        sl = slice(wave * w, wave * w + got[w]["result_p1"].shape[0])
         assert torch.equal(got[w]["result_p1"], ref["result_p1"][sl]), w
         assert torch.equal(got[w]["counts"], ref["counts"][:, sl]) and torch.equal(got[w]["actions"], ref["actions"][:, sl]), w
         assert torch.equal(got[w]["features"], ref["features"][:, sl]), w
 
 
 def test_waves_equal_one_big_batch():
-    """configs[4] driver: playing 3 waves of 4 games on one tree pool gives exactly the games of one batch of
-    12 (global game ids key the Philox streams), so sharding over waves / GPUs never changes results."""
+    """configs[4] driver: playing 3 waves of 4 games on one tree pool and a ragged last wave of 2 gives exactly the games of
+    one batch of 14 (global game ids key the Philox streams), so sharding over waves / GPUs never changes results."""
     from nypc_yacht_auction_b200.coach import BatchedSelfPlay
-    big = BatchedSelfPlay(12, 6, seed=9, game_base=200)
+    big = BatchedSelfPlay(14, 6, seed=9, game_base=200)
     ref = big.execute_episodes()
-    got, totals = _wave_examples(12, 4, 6, None, True, 9, 200)
+    got, totals = _wave_examples(14, 4, 6, None, True, 9, 200)
+    assert sorted(got) == [0, 1, 2, 3] and got[3]["result_p1"].shape[0] == 2
     _assert_waves_equal(got, ref, 4)
     r = ref["result_p1"]
     assert totals == (int((r > 0.5).sum()), int((r < -0.5).sum()), int((r.abs() < 0.5).sum()))
