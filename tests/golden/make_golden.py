@@ -22,6 +22,10 @@ import sys
 
 import numpy as np
 
+# The fixtures pin numpy >= 2 semantics (NEP 50: a Python float times an np.float32 stays float32), which decide the
+# bits of the reference's UCB / Q arithmetic (MCTS.py:125-129,155-156); under numpy 1.x the reference itself behaves differently.
+assert int(np.__version__.split(".")[0]) >= 2, "regenerate the golden files with numpy >= 2 (NEP 50), got %s" % np.__version__
+
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 REF = os.environ.get("YACHT_REFERENCE", "/root/reference")
