@@ -219,7 +219,7 @@ class BatchedMCTS:
     slice overlap the tensor-core forward of the other (games never interact, so this is exact)."""
 
     def __init__(self, env: BatchedYacht, num_sims, cpuct=1.5, evaluator=None, temp_threshold=15,
-                 arena_mb_per_game=None, max_nodes=None, want_leaf_states=False, groups=None):
+                 arena_mb_per_game=None, max_nodes=None, want_leaf_states=False, groups=None, forward_priority=True):
         self.env = env
         self.lib = env.lib
         self.num_sims = int(num_sims)
@@ -268,6 +268,10 @@ class BatchedMCTS:
                 ev = ev.with_private_buffers(g1 - g0)
             stream = torch.cuda.Stream(device=d) if groups > 1 else None
             self.groups.append(_Group(self, g0, g1, ev, stream))
+            if groups > 1 and forward_priority:
+                # a forward CTA needs a whole SM; at high priority its pending CTAs are placed before any further small
+                # block of the other groups' tree kernels, so the SMs drain for it instead of starving it
+                self.groups[-1].fwd_stream = torch.cuda.Stream(device=d, priority=-1)
         self.sim_counter = self.groups[0].sim_counter
         self._base_on_device = env.game_base
 
@@ -322,10 +326,18 @@ class BatchedMCTS:
             _lib.check(self.lib.ya_mcts_expand(grp.ref, None, None, 1, ev.p, ev.v, counter, _lib.ptr(self.err_flag), s),
                        "ya_mcts_expand")
             return
+        fwd = getattr(grp, "fwd_stream", None)                        # multi-group mode: the forward on its own high-priority stream
+        if fwd is not None:
+            fwd.wait_stream(torch.cuda.current_stream())
+            ctx = torch.cuda.stream(fwd)
+            ctx.__enter__()
         if self.scatter:                                              # legal logits go from the tensor core into the tree rows
             pi, v = ev(grp.features, grp.need_eval, leaf, scatter=(grp.leaf_dst, grp.leaf_desc))
         else:
             pi, v = ev(grp.features, grp.need_eval, leaf)
+        if fwd is not None:
+            ctx.__exit__(None, None, None)
+            torch.cuda.current_stream().wait_stream(fwd)
         assert v.dtype == torch.float32 and v.is_contiguous() and v.shape == (grp.n,)
         if self.rows:
             assert self.scatter or (pi.dtype == (torch.float16 if self.rows == 2 else torch.bfloat16) and pi.is_contiguous()
