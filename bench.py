@@ -531,7 +531,8 @@ def run_extras(args, torch, env, dev, n, peaks, prof, rank=0, world=1, dist=None
     net = YachtPolicyValueNet().to(dev)
     ev = FusedYachtEvaluator(net, 16384, precision="fp16")
     r = mb.selfplay_block(torch, dev, dist, rank, world, 16384, 100, ev, args.seed + 2, steps=2, warm=1)
-    wb = mb.wave_breakdown(torch, dev, 16384, 100, ev, args.seed + 2)
+    wb = mb.wave_breakdown(torch, dev, 16384, 100, ev, args.seed + 2)                       # ply 6: ten-dice score ply, ~3,000 legal moves per leaf
+    wb_bid = mb.wave_breakdown(torch, dev, 16384, 100, ev, args.seed + 2, plies_before=8)   # ply 8: first bid of round 3 (202-move rows)
     wb148 = mb.wave_breakdown(torch, dev, 148 * 128, 100, FusedYachtEvaluator(net, 148 * 128, precision="fp16"), args.seed + 2)
     fwd_us, fwd_us_148 = wb["forward_us"], wb148["forward_us"]
     dense_us = mb.forward_alone(torch, dev, ev, 16384)
@@ -552,7 +553,8 @@ def run_extras(args, torch, env, dev, n, peaks, prof, rank=0, world=1, dist=None
                           "one step = one full 48-ply episode of every game with example recording; per simulation wave 3 launches "
                           "(select, whole-network tcgen05 forward, expand with fused softmax + mask), replayed as one CUDA graph",
               "metric": "mcts_sims_per_sec", "unit": "sims/s", "dtype": "fp16 operands / f32 accumulate (the reference's CUDA autocast precision)",
-              "scaling": "weak", "nn_flops_per_leaf": real_flops, "wave_breakdown": wb, "nn_share_of_time": wb["nn_share_of_wave"],
+              "scaling": "weak", "nn_flops_per_leaf": real_flops, "wave_breakdown": wb, "wave_breakdown_bid_ply": wb_bid,
+              "nn_share_of_time": 0.5 * (wb["nn_share_of_wave"] + wb_bid["nn_share_of_wave"]),
               "bf16_operands": {"sims_per_sec": bf["sims_per_sec"], "ms_per_step": bf["ms_per_step"]},
               "roofline": hbm_roofline(r["sims_per_sec"], mb.ALGO_BYTES_NN_F32, "ya_mcts_wave",
                                        {"algorithmic_bytes_per_sim_16bit": mb.ALGO_BYTES_NN_16,

@@ -76,7 +76,7 @@ def selfplay_block(torch, dev, dist, rank, world, n, sims, evaluator, seed, step
            "sims_per_sec": world * n * sims * PLIES * steps / (ms * 1e-3),
            "game_steps_per_sec": world * n * PLIES * steps / (ms * 1e-3),
            "gpu_launches": steps * _launches_per_episode(0 if (uniform and fuse_uniform) else (2 if uniform else 3), sims),
-           "pool_gb": sp.mcts.pool.bytes() / 1e9, "max_nodes_in_use": nodes}
+           "pool_gb": sp.mcts.pool.bytes() / 1e9, "nodes_live_at_episode_end": nodes}
     if e2e_steps:
         host = sp.host_buffers()
         host["boards"].copy_(sp.env.states)                         # getInitBoard positions of the next episode, kept on the host
