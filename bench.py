@@ -571,7 +571,8 @@ def run_extras(args, torch, env, dev, n, peaks, prof, rank=0, world=1, dist=None
         r.update({"workload": "configs[4]: %d concurrent games sharded over %d GPU(s) by global game id, numMCTSSims=100, random-init "
                               "YachtNNet, waves of %d games on one tree pool per GPU" % (total, world, r["wave_games"]),
                   "metric": "mcts_sims_per_sec", "unit": "sims/s", "dtype": "fp16 operands / f32 accumulate",
-                  "roofline": hbm_roofline(r["sims_per_sec"], mb.ALGO_BYTES_NN_F32, "ya_mcts_wave"),
+                  "roofline": hbm_roofline(r["sims_per_sec"], mb.ALGO_BYTES_NN_F32, "ya_mcts_wave",
+                                           {"frac_16bit": r["sims_per_sec"] / world * mb.ALGO_BYTES_NN_16 / 1e9 / peak}),
                   "e2e": {"value": r["sims_per_sec"], "unit": "sims/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": r["d2h_bytes_per_gpu"],
                           "note": "the block itself is end to end: games are dealt on device from the seed (no input but the seed), every "
                                   "wave's examples are copied to pinned host memory inside the timed region"}})

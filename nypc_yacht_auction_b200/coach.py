@@ -223,40 +223,50 @@ class BatchedArena:
         return a_wins, b_wins, draws
 
 
-def self_play_in_waves(total_games, wave_games, num_sims, evaluator, first_game=0, on_wave=None, use_graph=True, **kwargs):
+def make_wave_player(total_games, wave_games, num_sims, evaluator, first_game=0, use_graph=True, **kwargs):
+    """The reusable part of self_play_in_waves: ONE BatchedSelfPlay of min(wave_games, total_games) games (tree pool,
+    example buffers) with the simulation wave captured as a CUDA graph.  Build it once, outside any timed region."""
+    n = min(int(wave_games), int(total_games))
+    ev = evaluator
+    if n != wave_games and hasattr(ev, "with_private_buffers") and getattr(ev, "max_batch", n) < n:
+        ev = ev.with_private_buffers(n)
+    sp = BatchedSelfPlay(n, num_sims, evaluator=ev, game_base=first_game, **kwargs)
+    if use_graph and not getattr(sp.mcts.evaluator, "uniform", False):
+        sp.mcts.capture_graph()                                  # one simulation wave, replayed numMCTSSims times per move
+    return sp
+
+
+def self_play_in_waves(total_games, wave_games, num_sims, evaluator, first_game=0, on_wave=None, use_graph=True, sp=None,
+                       **kwargs):
     """BASELINE.json configs[4]: more concurrent games than one tree pool fits in HBM (1,048,576 games over
     8 GPUs = 131,072 per GPU at ~2.8 MB of tree per game) are played as consecutive waves of `wave_games`
     games on ONE pool; wave w owns global games [first_game + w*wave_games, ...), so the result is the same
-    as one huge batch (Philox streams are keyed by the global game id).  A remainder that does not fill a wave is
-    played last on a pool of its own size (e.g. waves of 148 x 128 x 2 games keep every SM busy in the forward kernel
-    and never divide a power of two).  `on_wave(w, examples)` receives each wave's example tensors (copy or reduce them
-    there: the buffers are reused).  Returns the total (p1_wins, p2_wins, draws)."""
-    full, rest = divmod(int(total_games), int(wave_games))
+    as one huge batch (Philox streams are keyed by the global game id).  When the last wave is not full, its surplus
+    slots play the games that follow the range (same pool, same captured graph) and are dropped from the tallies and from
+    the examples handed out.  `on_wave(w, examples)` receives each wave's example tensors (copy or reduce them there: the
+    buffers are reused).  `sp`: a player from make_wave_player (pool + graph built beforehand); otherwise one is built
+    here.  Returns the total (p1_wins, p2_wins, draws)."""
+    total_games = int(total_games)
+    if sp is None:
+        sp = make_wave_player(total_games, wave_games, num_sims, evaluator, first_game, use_graph, **kwargs)
+    n = sp.n
     p1 = p2 = dr = 0
-    w = 0
-    for n, count, base0 in ((int(wave_games), full, first_game), (rest, 1 if rest else 0, first_game + full * int(wave_games))):
-        if count == 0:
-            continue
-        ev = evaluator
-        if n != wave_games and hasattr(ev, "with_private_buffers"):
-            ev = ev.with_private_buffers(n)
-        sp = BatchedSelfPlay(n, num_sims, evaluator=ev, game_base=base0, **kwargs)
-        if use_graph and not getattr(sp.mcts.evaluator, "uniform", False):
-            sp.mcts.capture_graph()                              # one simulation wave, replayed numMCTSSims times per move
-        for i in range(count):
-            if i:
-                sp.env.game_base = base0 + i * n                 # same pool, next slice of global game ids (the captured
-                sp.mcts.pool.reset()                             # graph reads them from device memory: mcts.sync_game_base)
-                sp.env.episode.zero_()
-                sp.env.reset()
-            ex = sp.execute_episodes()
-            r = (ex["result_p1"] if ex is not None else sp.env.game_ended(players=torch.ones_like(sp.env.players)))
-            p1 += int((r > 0.5).sum().item())
-            p2 += int((r < -0.5).sum().item())
-            dr += int((r.abs() < 0.5).sum().item())
-            if on_wave is not None:
-                on_wave(w, ex)
-            w += 1
-        del sp                                                   # the pool goes back before the remainder's pool is made
-        torch.cuda.empty_cache()
+    waves = (total_games + n - 1) // n
+    for w in range(waves):
+        base = first_game + w * n
+        live = min(n, total_games - w * n)                       # games of this wave that belong to the range
+        if w or sp.env.game_base != base or int(sp.env.ply.max().item()) != 0:
+            sp.env.game_base = base                              # same pool, next slice of global game ids (the captured
+            sp.mcts.pool.reset()                                 # graph reads them from device memory: mcts.sync_game_base)
+            sp.env.episode.zero_()
+            sp.env.reset()
+        ex = sp.execute_episodes()
+        r = (ex["result_p1"] if ex is not None else sp.env.game_ended(players=torch.ones_like(sp.env.players)))[:live]
+        p1 += int((r > 0.5).sum().item())
+        p2 += int((r < -0.5).sum().item())
+        dr += int((r.abs() < 0.5).sum().item())
+        if on_wave is not None:
+            if ex is not None and live < n:
+                ex = {k: v.narrow(0 if v.dim() == 1 else (2 if k == "states" else 1), 0, live) for k, v in ex.items()}
+            on_wave(w, ex)
     return p1, p2, dr

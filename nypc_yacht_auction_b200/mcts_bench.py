@@ -153,23 +153,29 @@ def forward_alone(torch, dev, evaluator, leaves, reps=50):
     return f0.elapsed_time(f1) * 1000.0 / reps
 
 
-def selfplay_1m(torch, dev, dist, rank, world, evaluator_factory, total, sims, wave, seed):
+def selfplay_1m(torch, dev, dist, rank, world, evaluator_factory, total, sims, wave_cap, seed):
     """configs[4]: `total` games split over the ranks by global game id (dist.shard_range), every rank plays its shard as
-    consecutive waves of `wave` games on ONE tree pool (coach.self_play_in_waves; simulation wave replayed as a CUDA graph),
-    and copies every wave's examples to pinned host memory.  STRONG scaling: total work is fixed."""
-    from .coach import self_play_in_waves
+    consecutive waves on ONE tree pool (coach.self_play_in_waves; simulation wave replayed as a CUDA graph) and copies every
+    wave's examples to pinned host memory.  STRONG scaling: total work is fixed.  The pool, the graph and the pinned buffers
+    are built before the timed region (one-time setup, like loading the weights); every wave's pool reset, re-deal, search,
+    example recording and device->host copy are inside it."""
+    from .coach import make_wave_player, self_play_in_waves
     from .dist import shard_range
     first, last = shard_range(total, rank, world)
     mine = last - first
-    wave = min(wave, mine)
-    ev = evaluator_factory(wave)
-    host = {}
+    waves = (mine + wave_cap - 1) // wave_cap                    # as few waves as fit the pool, all (but the last) full,
+    wave = min(mine, ((mine + waves - 1) // waves + 127) // 128 * 128)   # sized in whole 128-leaf forward tiles
+    sp = make_wave_player(mine, wave, sims, evaluator_factory(wave), first_game=first, use_graph=True, seed=seed, device=dev)
+    names = ("features", "actions", "counts", "value", "result_p1")
+    host = {"features": torch.empty((sp.PLIES, sp.n, 59), dtype=torch.float32, pin_memory=True),
+            "actions": torch.empty((sp.PLIES, sp.n, sp.k), dtype=torch.int16, pin_memory=True),
+            "counts": torch.empty((sp.PLIES, sp.n, sp.k), dtype=torch.int32, pin_memory=True),
+            "value": torch.empty((sp.PLIES, sp.n), dtype=torch.float32, pin_memory=True),
+            "result_p1": torch.empty(sp.n, dtype=torch.float32, pin_memory=True)}
     tally = {"d2h": 0, "waves": 0}
 
     def on_wave(w, ex):
-        for name in ("features", "actions", "counts", "value", "result_p1"):
-            if name not in host:
-                host[name] = torch.empty(ex[name].shape, dtype=ex[name].dtype, pin_memory=True)
+        for name in names:
             gd = 0 if ex[name].dim() == 1 else 1                 # a ragged last wave fills only its share of the buffer
             dst = host[name].narrow(gd, 0, ex[name].shape[gd])
             dst.copy_(ex[name], non_blocking=True)
@@ -180,7 +186,7 @@ def selfplay_1m(torch, dev, dist, rank, world, evaluator_factory, total, sims, w
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
     e0.record()
-    p1, p2, dr = self_play_in_waves(mine, wave, sims, ev, first_game=first, on_wave=on_wave, use_graph=True, seed=seed, device=dev)
+    p1, p2, dr = self_play_in_waves(mine, wave, sims, None, first_game=first, on_wave=on_wave, sp=sp)
     e1.record()
     _fence(torch, dev, dist, world)
     wall = _max_ranks(torch, dev, dist, world, time.perf_counter() - t0)
@@ -190,17 +196,17 @@ def selfplay_1m(torch, dev, dist, rank, world, evaluator_factory, total, sims, w
         dist.all_reduce(res)
     res = [int(x) for x in res.tolist()]
     assert sum(res) == total, "every game must finish"
-    full, rest = divmod(mine, wave)
-    out = {"games": total, "games_per_gpu": mine, "wave_games": wave, "waves_per_gpu": tally["waves"], "last_wave_games": rest or wave,
-           "num_mcts_sims": sims,
+    out = {"games": total, "games_per_gpu": mine, "wave_games": wave, "waves_per_gpu": tally["waves"],
+           "last_wave_live_games": mine - (tally["waves"] - 1) * wave, "num_mcts_sims": sims,
            "seconds": ms * 1e-3, "wall_seconds": wall, "sims_per_sec": total * PLIES * sims / (ms * 1e-3),
            "game_steps_per_sec": total * PLIES / (ms * 1e-3), "scaling": "strong",
-           "outcomes_p1_p2_draw": res, "d2h_bytes_per_gpu": tally["d2h"],
+           "outcomes_p1_p2_draw": res, "d2h_bytes_per_gpu": tally["d2h"], "pool_gb": sp.mcts.pool.bytes() / 1e9,
            "gpu_launches_per_gpu": tally["waves"] * _launches_per_episode(3, sims),
-           "wave_choice": "148 SMs x 128 leaves x 2 = 37,888 games per wave: every SM runs a forward CTA pair of tiles, the ragged "
-                          "remainder is played last on a pool of its own size" if wave % (148 * 128) == 0 else "as configured",
-           "includes": "pool reset + re-deal per wave, example recording, device->host copy of every wave's examples (pinned)"}
-    del host
+           "wave_choice": "the fewest waves of <= %d games (2 x 148 SMs x 128 leaves) that cover the shard, equal sizes in whole 128-leaf tiles; "
+                          "a last wave that is not full plays surplus games that are dropped" % wave_cap,
+           "includes": "per wave: pool reset + re-deal, 48 plies x numMCTSSims simulations, example recording, device->host copy of the "
+                       "examples into pinned memory; excludes the one-time setup (pool allocation, CUDA-graph capture, pinned buffers)"}
+    del host, sp
     torch.cuda.empty_cache()
     return out
 
