@@ -76,21 +76,27 @@ __device__ __forceinline__ int row_words(int L) { return ((L + 3) & ~3) + ((L + 
 __device__ __forceinline__ int group_max_at(int L) { return (L + 3) & ~3; }
 
 // A node's visited edges: ONE contiguous array in the arena, capacity C = 32, 64, 128, ... (it doubles when full; the
-// old copy is abandoned in the bump arena): C x u16 legal index | C x u32 Nsa (bit 31: Q is a Python float, else a
-// numpy float32) | C x f64 Q.  Every lane can address any edge directly, so a node with 100 edges costs one
-// round of independent loads, not a walk over a chunk list.
+// old copy is abandoned in the bump arena): C x u16 legal index | C x u16 child | C x u32 Nsa (bit 31: Q is a Python
+// float, else a numpy float32) | C x f64 Q = 16 bytes per edge.  Every lane can address any edge directly, so a node with
+// 100 edges costs one round of independent loads, not a walk over a chunk list.
+// child = 1 + the node the edge leads to, when getNextState is deterministic for it (no dice, no tie-break: everything
+// except second bids that tie or close round 1, and the score move that ends a round -- which the search never makes,
+// quirk Q3); 0 = not known / stochastic.  The child's record holds its canonical state (it IS the node key), so a descent
+// through a known child skips the transition, the hash and the table probe: one dependent load instead of three.
 __device__ __forceinline__ int edge_cap(int n) { return n <= kMinEdgeCap ? kMinEdgeCap : 1 << (32 - __clz(n - 1)); }
-__device__ __forceinline__ int edge_words(int cap) { return cap / 2 + cap + 2 * cap; }
+__device__ __forceinline__ int edge_words(int cap) { return 4 * cap; }
 struct Edges {
     uint16_t* idx;
+    uint16_t* child;
     uint32_t* nsa;
     double* q;
 };
 __device__ __forceinline__ Edges edges_at(uint32_t* base, int cap) {
     Edges e;
     e.idx = reinterpret_cast<uint16_t*>(base);
-    e.nsa = base + cap / 2;
-    e.q = reinterpret_cast<double*>(base + cap / 2 + cap);
+    e.child = reinterpret_cast<uint16_t*>(base + cap / 2);
+    e.nsa = base + cap;
+    e.q = reinterpret_cast<double*>(base + 2 * cap);
     return e;
 }
 
@@ -171,6 +177,11 @@ struct Team {
     __device__ __forceinline__ uint32_t reduce_max(uint32_t v) const { return __reduce_max_sync(mask, v); }
 };
 
+// path word of one level of a descent: node index | legal index of the chosen move << 16 | deterministic transition << 31
+__device__ __forceinline__ int path_node(uint32_t pe) { return (int)(pe & 0xFFFFu); }
+__device__ __forceinline__ int path_move(uint32_t pe) { return (int)((pe >> 16) & 0xFFFu); }
+__device__ __forceinline__ bool path_deterministic(uint32_t pe) { return (pe >> 31) != 0u; }
+
 // A value travelling up the tree with the numeric type Python would give it.
 struct Val {
     double d;        // value (exact float32 value when is_f32)
@@ -209,6 +220,8 @@ __device__ __forceinline__ double es_as_double(float es) {       // getGameEnded
 // ---------------------------------------------------------------- UCB argmax (MCTS.py:117-133)
 // ROWS: the row storage of this pool (constant-prior nodes: only ya_k_mcts_search_uniform creates them, and a tree pool is
 // driven either by that kernel or by select / expand -- mcts.BatchedMCTS fixes the choice at construction).
+// Returns (legal index << 16) | child of the arg-max edge (child = 0 for an unvisited move): ordering packed keys is
+// ordering legal indices, so the lowest-index tie-break of MCTS.py:131 is untouched.
 template <int ROWS, int W>
 __device__ __forceinline__ int ucb_select(const View& v, const uint32_t* node, int L, float cpuct, const Team<W>& tm) {
     const int sub = tm.sub;
@@ -233,7 +246,7 @@ __device__ __forceinline__ int ucb_select(const View& v, const uint32_t* node, i
         if (n_edges > 0) {
             const Edges ed = edges_at(v.arena + node[N_EDGES], edge_cap(n_edges));
             for (int e = sub; e < n_edges; e += W) {
-                const int ai = (int)ed.idx[e];
+                const int ai = ((int)ed.idx[e] << 16) | (int)ed.child[e];
                 float x = __fdiv_rn(__fmul_rn(cp, sq_old), (float)(1u + (ed.nsa[e] & 0x7FFFFFFFu)));
                 float u = __fadd_rn((float)ed.q[e], x);
                 if (u > best || (u == best && ai < besti)) { best = u; besti = ai; }
@@ -249,7 +262,7 @@ __device__ __forceinline__ int ucb_select(const View& v, const uint32_t* node, i
         for (int o = W / 2; o; o >>= 1) first = min(first, tm.xor_(first, o));
         if (first != 0x7FFFFFFF) {
             const float u = __fmul_rn(cp, sq_new);
-            if (u > best || (u == best && first < besti)) { best = u; besti = first; }
+            if (u > best || (u == best && (first << 16) < besti)) { best = u; besti = first << 16; }
         }
         team_argmax();
         return besti;
@@ -273,12 +286,12 @@ __device__ __forceinline__ int ucb_select(const View& v, const uint32_t* node, i
                 for (int t = 0; t < 2; ++t) {
                     const int e = e0 + W * t + sub;
                     const bool ok = e < n_edges;
-                    ai[t] = ok ? (int)ed.idx[e] : 0;
+                    ai[t] = ok ? ((int)ed.idx[e] << 16) | (int)ed.child[e] : 0;
                     nsa[t] = ok ? ed.nsa[e] & 0x7FFFFFFFu : 0u;
                     q[t] = ok ? ed.q[e] : 0.0;
                 }
 #pragma unroll
-                for (int t = 0; t < 2; ++t) lb[t] = lg[l16_slot(desc, ai[t])];
+                for (int t = 0; t < 2; ++t) lb[t] = lg[l16_slot(desc, ai[t] >> 16)];
 #pragma unroll
                 for (int t = 0; t < 2; ++t) {
                     if (e0 + W * t + sub < n_edges) {
@@ -313,7 +326,7 @@ __device__ __forceinline__ int ucb_select(const View& v, const uint32_t* node, i
             auto consider = [&](int i, uint32_t h) {
                 if (i < L && !((seen >> (i & 31)) & 1u)) {
                     float u = __fmul_rn(__fmul_rn(cpuct, l16_prior<ROWS>(h, off)), sq_new);
-                    if (u > best || (u == best && i < besti)) { best = u; besti = i; }
+                    if (u > best || (u == best && (i << 16) < besti)) { best = u; besti = i << 16; }
                 }
             };
             if (kPer == 1) {
@@ -348,12 +361,12 @@ __device__ __forceinline__ int ucb_select(const View& v, const uint32_t* node, i
             for (int t = 0; t < 2; ++t) {
                 const int e = e0 + W * t + sub;
                 const bool ok = e < n_edges;
-                ai[t] = ok ? (int)ed.idx[e] : 0;
+                ai[t] = ok ? ((int)ed.idx[e] << 16) | (int)ed.child[e] : 0;
                 nsa[t] = ok ? ed.nsa[e] & 0x7FFFFFFFu : 0u;
                 q[t] = ok ? ed.q[e] : 0.0;
             }
 #pragma unroll
-            for (int t = 0; t < 2; ++t) pb[t] = row[ai[t]];
+            for (int t = 0; t < 2; ++t) pb[t] = row[ai[t] >> 16];
 #pragma unroll
             for (int t = 0; t < 2; ++t) {
                 if (e0 + W * t + sub < n_edges) {
@@ -394,7 +407,7 @@ __device__ __forceinline__ int ucb_select(const View& v, const uint32_t* node, i
                     uint32_t bits = row[i];
                     if (!(bits >> 31)) {
                         float u = __fmul_rn(__fmul_rn(cpuct, __uint_as_float(bits)), sq_new);
-                        if (u > best || (u == best && i < besti)) { best = u; besti = i; }
+                        if (u > best || (u == best && (i << 16) < besti)) { best = u; besti = i << 16; }
                     }
                 }
             }
@@ -408,7 +421,7 @@ __device__ __forceinline__ int ucb_select(const View& v, const uint32_t* node, i
 // Returns false if the arena overflowed.
 template <int ROWS, int W>
 __device__ __forceinline__ bool backup_edge(const View& v, uint32_t* node, int ai, const Val& val, uint32_t& arena_top,
-                                            const Team<W>& tm) {
+                                            const Team<W>& tm, uint32_t child) {
     const int sub = tm.sub;
     int failed = 0, fresh = 0;
     // locate the edge
@@ -436,7 +449,9 @@ __device__ __forceinline__ bool backup_edge(const View& v, uint32_t* node, int a
             uint32_t* nb = v.arena + top;
             if (n_edges > 0) {
                 const Edges from = edges_at(base, cap), to = edges_at(nb, new_cap);
-                for (int e = sub; e < n_edges; e += W) { to.idx[e] = from.idx[e]; to.nsa[e] = from.nsa[e]; to.q[e] = from.q[e]; }
+                for (int e = sub; e < n_edges; e += W) {
+                    to.idx[e] = from.idx[e]; to.child[e] = from.child[e]; to.nsa[e] = from.nsa[e]; to.q[e] = from.q[e];
+                }
             }
             tm.sync();
             if (sub == 0) node[N_EDGES] = top;
@@ -463,9 +478,11 @@ __device__ __forceinline__ bool backup_edge(const View& v, uint32_t* node, int a
             }
             ed.q[found] = q;
             ed.nsa[found] = (nsa + 1u) | (q_f32 ? 0u : 0x80000000u);
+            if (child && ed.child[found] == 0) ed.child[found] = (uint16_t)child;
         } else if (!failed) {
             const Edges ed = edges_at(base, edge_cap(n_edges + 1));
             ed.idx[n_edges] = (uint16_t)ai;
+            ed.child[n_edges] = (uint16_t)child;
             ed.nsa[n_edges] = 1u | (val.is_f32 ? 0u : 0x80000000u);        // Qsa = v, Nsa = 1
             ed.q[n_edges] = val.d;
             node[N_NEDGE] = (uint32_t)(n_edges + 1);
@@ -518,12 +535,18 @@ __device__ __forceinline__ bool backup_edge(const View& v, uint32_t* node, int a
     return !failed;
 }
 
+// last_node: the node the deepest edge of the path leads to (the new leaf, or a dead-end node), -1 if it ended in a
+// terminal state (terminal states have no node).
 template <int ROWS, int W>
-__device__ __forceinline__ bool backup_path(const View& v, int depth, Val ret, uint32_t& arena_top, const Team<W>& tm) {
+__device__ __forceinline__ bool backup_path(const View& v, int depth, Val ret, uint32_t& arena_top, const Team<W>& tm,
+                                            int last_node) {
+    int below = last_node;                                           // node one level further down the path
     for (int d = depth - 1; d >= 0; --d) {
         uint32_t pe = v.cur[C_PATH + d];
-        uint32_t* node = v.nodes + (int64_t)(pe & 0xFFFFu) * kNodeWords;
-        if (!backup_edge<ROWS>(v, node, (int)(pe >> 16), ret, arena_top, tm)) return false;
+        uint32_t* node = v.nodes + (int64_t)path_node(pe) * kNodeWords;
+        const uint32_t child = (path_deterministic(pe) && below >= 0) ? (uint32_t)below + 1u : 0u;
+        if (!backup_edge<ROWS>(v, node, path_move(pe), ret, arena_top, tm, child)) return false;
+        below = path_node(pe);
         ret.d = -ret.d;                                              // return -v
     }
     return true;
@@ -576,6 +599,7 @@ __device__ __forceinline__ void descend(const View& v, YaState cur, Walk& w, uin
     w.ret.d = 0.0; w.ret.is_f32 = false;
     bool pending = false;
     int a = 0;
+    int known = -1;                                                  // node index of `cur` when it was reached through a cached child
     int have = (INJECT && src.inj && src.resume) ? src.inj[11] : 0;  // draws supplied for the paused transition
     if (INJECT && src.resume) {                                     // pick the paused transition up again
 #pragma unroll
@@ -586,10 +610,13 @@ __device__ __forceinline__ void descend(const View& v, YaState cur, Walk& w, uin
     }
     for (;;) {
         if (!pending) {
-            float es = ya_game_ended(cur, 1);                       // Es[s], MCTS.py:79-83
-            if (es != 0.0f) { w.ret.d = -es_as_double(es); w.ret.is_f32 = false; break; }
-            int free_slot;
-            int idx = ht_find(v, cur, &free_slot);
+            int idx = known, free_slot = 0;
+            known = -1;
+            if (idx < 0) {                                           // not reached through a cached child: look the state up
+                float es = ya_game_ended(cur, 1);                   // Es[s], MCTS.py:79-83
+                if (es != 0.0f) { w.ret.d = -es_as_double(es); w.ret.is_f32 = false; break; }
+                idx = ht_find(v, cur, &free_slot);
+            }
             if (idx < 0) {                                           // leaf: MCTS.py:84-115 (evaluation happens outside)
                 uint32_t desc = ya_mask_desc(cur, 1);
                 int L = ya_legal_count(desc);
@@ -621,11 +648,23 @@ __device__ __forceinline__ void descend(const View& v, YaState cur, Walk& w, uin
             uint32_t* node = v.nodes + (int64_t)idx * kNodeWords;
             uint32_t desc = node[N_DESC];
             int L = ya_legal_count(desc);
-            if (L == 0) { w.ret.d = 0.0; w.ret.is_f32 = false; break; }    // MCTS.py:138-147: `return 0`, not negated
+            if (L == 0) { w.leaf_node = idx; w.ret.d = 0.0; w.ret.is_f32 = false; break; }   // MCTS.py:138-147: `return 0`, not negated
             if (w.depth >= kMaxDepth) { w.err = E_DEPTH; w.kind = KIND_ERROR; break; }
-            int ai = ucb_select<ROWS>(v, node, L, cpuct, tm);
+            const int key = ucb_select<ROWS>(v, node, L, cpuct, tm);
+            const int ai = key >> 16, child = key & 0xFFFF;
             a = ya_nth_legal(desc, ai);
-            if (lane == 0) v.cur[C_PATH + w.depth] = (uint32_t)idx | ((uint32_t)ai << 16);
+            // getNextState(s, 1, a) without dice or tie-break is a function of (s, a): its result can be cached on the edge
+            const bool det = !INJECT && ya_draw_needs(cur, 1, a) == 0;
+            if (lane == 0) v.cur[C_PATH + w.depth] = (uint32_t)idx | ((uint32_t)ai << 16) | (det ? 0x80000000u : 0u);
+            if (det && child) {                                      // known child: its record holds the next canonical state
+                const uint4* ck = reinterpret_cast<const uint4*>(v.nodes + (int64_t)(child - 1) * kNodeWords);
+                const uint4 k0 = ck[0], k1 = ck[1];
+                cur.w[0] = k0.x; cur.w[1] = k0.y; cur.w[2] = k0.z; cur.w[3] = k0.w;
+                cur.w[4] = k1.x; cur.w[5] = k1.y; cur.w[6] = k1.z; cur.w[7] = k1.w;
+                known = child - 1;
+                ++w.depth;
+                continue;
+            }
         }
         pending = false;
         YaDraw d;
@@ -684,7 +723,7 @@ ya_k_mcts_select(ya_mcts_tree tree, const uint4* __restrict__ states, int64_t st
     DrawSource src{INJECT ? injected + g * 12 : nullptr, INJECT ? resume : 0};
     descend<true, INJECT, ROWS>(v, root, w, seed, gid, ep, pl, sim, cpuct, features + g * YA_N_FEATURE, tm, src);
     if (w.kind == KIND_DONE) {
-        if (!backup_path<ROWS>(v, w.depth, w.ret, w.arena_top, tm)) { w.err = E_ARENA_FULL; w.kind = KIND_ERROR; }
+        if (!backup_path<ROWS>(v, w.depth, w.ret, w.arena_top, tm, w.leaf_node)) { w.err = E_ARENA_FULL; w.kind = KIND_ERROR; }
     }
     if (lane == 0) {
         v.meta[M_NODES] = w.node_count;
@@ -841,7 +880,7 @@ ya_k_mcts_expand(ya_mcts_tree tree, const float* __restrict__ pi_all, const floa
     ret.d = -(double)(MODE == 1 ? uniform_v : value[g]);             // return -v (numpy float32)
     ret.is_f32 = true;
     uint32_t arena_top = v.meta[M_TOP];
-    bool ok = backup_path<ROWS_F32>(v, (int)v.cur[C_DEPTH], ret, arena_top, Team<32>::make());
+    bool ok = backup_path<ROWS_F32>(v, (int)v.cur[C_DEPTH], ret, arena_top, Team<32>::make(), (int)v.cur[C_NODE]);
     if (lane == 0) {
         v.meta[M_TOP] = arena_top;
         v.cur[C_KIND] = KIND_DONE;
@@ -928,7 +967,7 @@ ya_k_mcts_expand_rows(ya_mcts_tree tree, const uint16_t* __restrict__ logits_all
             if (lane < depth) {
                 const uint32_t pe = v.cur[C_PATH + lane];
                 const uint32_t* nd = v.nodes + (int64_t)(pe & 0xFFFFu) * kNodeWords;
-                const int ne = (int)nd[N_NEDGE], ai = (int)(pe >> 16);
+                const int ne = (int)nd[N_NEDGE], ai = path_move(pe);
                 const uint32_t* prow = v.arena + nd[N_PRIOR];
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(prow + (l16_slot(nd[N_DESC], ai & ~31) >> 1)));
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(prow + l16_logit_words(nd[N_DESC]) + (ai >> 5)));
@@ -936,8 +975,8 @@ ya_k_mcts_expand_rows(ya_mcts_tree tree, const uint16_t* __restrict__ logits_all
                     const uint32_t* eb = v.arena + nd[N_EDGES];
                     const int cap = edge_cap(ne);
                     for (int b = 0; b < ne * 2; b += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(eb) + b));
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(eb + cap / 2));            // Nsa / Q of a one-chunk node
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(eb + cap / 2 + cap));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(eb + cap));                // Nsa / Q of a one-chunk node
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(eb + 2 * cap));
                 }
             }
             __syncwarp();
@@ -1054,7 +1093,7 @@ ya_k_mcts_expand_rows(ya_mcts_tree tree, const uint16_t* __restrict__ logits_all
     ret.d = -(double)value[g];
     ret.is_f32 = true;
     uint32_t arena_top = v.meta[M_TOP];
-    bool ok = backup_path<ROWS>(v, (int)v.cur[C_DEPTH], ret, arena_top, Team<32>::make());
+    bool ok = backup_path<ROWS>(v, (int)v.cur[C_DEPTH], ret, arena_top, Team<32>::make(), (int)v.cur[C_NODE]);
     if (lane == 0) {
         v.meta[M_TOP] = arena_top;
         v.cur[C_KIND] = KIND_DONE;
@@ -1107,7 +1146,7 @@ ya_k_mcts_search_uniform(ya_mcts_tree tree, const uint4* __restrict__ states, in
             ret.d = -(double)uniform_v;
             ret.is_f32 = true;
         }
-        if (!backup_path<ROWS_CONST>(v, w.depth, ret, w.arena_top, tm)) { err = E_ARENA_FULL; break; }
+        if (!backup_path<ROWS_CONST>(v, w.depth, ret, w.arena_top, tm, w.leaf_node)) { err = E_ARENA_FULL; break; }
     }
     if (lane == 0) {
         v.meta[M_NODES] = w.node_count;

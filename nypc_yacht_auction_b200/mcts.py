@@ -40,8 +40,8 @@ class TreePool:
             # measured peak (random-init net, 100 sims, profiles/tools/arena_peak.py): 39 KB per simulation of the
             # longest-lived tree (rounds 1+2: six plies without pruning); 48 KB/sim leaves ~20 % head-room,
             # overflow is detected and raised.
-            # 16-bit logit rows (ROWS_FP16 / ROWS_BF16) take 2.25 instead of 4.1 bytes per legal move: measured peak 21.6 KB
-            # per simulation, 28 KB/sim allocated.
+            # 16-bit logit rows (ROWS_FP16 / ROWS_BF16) take 2.4 instead of 4.1 bytes per legal move: measured peak 22.4 KB
+            # per simulation (2.24 MB per game at 100 sims), 28 KB/sim allocated.
             per_sim_kb = 48.0 if self.rows == 0 else 28.0
             arena_mb_per_game = max(num_sims * per_sim_kb / 1024.0, 0.25)
         words = int(arena_mb_per_game * 2 ** 20) // 4
