@@ -58,9 +58,10 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
 // descriptor of the same tile `bytes` further on (same swizzle atom row: K steps of 32 bytes, K-blocks, halves)
 __device__ __forceinline__ uint64_t umma_desc_advance(uint64_t desc, uint32_t bytes) { return desc + (uint64_t)(bytes >> 4); }
 
-// instruction descriptor (kind::f16): D=f32, A=B=bf16 (format 1) or fp16 (format 0), both K-major, M=128, N=n_cols
-__host__ __device__ constexpr uint32_t umma_idesc(int n_cols, bool fp16 = false) {
-    return (1u << 4) | (fp16 ? 0u : ((1u << 7) | (1u << 10))) | ((uint32_t)(n_cols >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+// instruction descriptor (kind::f16): D=f32, A=B=bf16 (format 1) or fp16 (format 0), both K-major, M=m_rows (128 for one
+// CTA, 256 for a CTA pair: 128 rows in each CTA's tensor memory), N=n_cols
+__host__ __device__ constexpr uint32_t umma_idesc(int n_cols, bool fp16 = false, int m_rows = 128) {
+    return (1u << 4) | (fp16 ? 0u : ((1u << 7) | (1u << 10))) | ((uint32_t)(n_cols >> 3) << 17) | ((uint32_t)(m_rows >> 4) << 24);
 }
 
 // two float32 -> one packed 16-bit pair (low half = first element), round to nearest even
@@ -94,6 +95,46 @@ __device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// ---- CTA pair (cta_group::2): the leader CTA's elected thread issues one M = 256 instruction for both SMs.  Each CTA
+// supplies its own 128 rows of A (shared memory at the same offset, or its own tensor memory) and HALF of B's N rows
+// (rank 0: N [0, N/2), rank 1: N [N/2, N)); each CTA's tensor memory receives its 128 rows x N columns.
+__device__ __forceinline__ void umma2(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate, uint32_t idesc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma2_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t accumulate, uint32_t idesc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+// completion of every MMA issued so far arrives on the mbarrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma2_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// Arrive on the mbarrier at the same offset in CTA `cta` of the cluster.  Default semantics (release at CTA scope), as in
+// CUTLASS's ClusterBarrier::arrive(cta_id): what the hand-off publishes is this CTA's OWN shared / tensor memory, made
+// visible CTA-wide by the bar.sync (+ fence.proxy.async / tcgen05.fence) that precedes the arrive, and read by the tensor
+// core of this SM.  A cluster-scope release would cost a MEMBAR.ALL.GPU per hand-off, a cluster-scope acquire a CCTL.IVALL
+// (measured: +0.5 us per network layer).
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
+        ::"r"(smem_u32(bar)), "r"(cta) : "memory");
 }
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
@@ -131,6 +172,36 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void proxy_fence() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---- packed float32 pairs (Blackwell FFMA2 / FADD2 / FMUL2: one issue slot for two IEEE operations; results are bit
+// for bit those of the scalar instructions).  The epilogues are issue-bound next to the MUFU and LSU work they carry, so
+// every float32 step that exists for two neighbouring columns is issued once.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ f32x2 pk2u(uint32_t lo, uint32_t hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi)); return r; }
+__device__ __forceinline__ void upk2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ void upk2u(f32x2 v, uint32_t& lo, uint32_t& hi) { asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+template <bool F16>
+__device__ __forceinline__ uint32_t pack2(f32x2 v) { float lo, hi; upk2(v, lo, hi); return pack2<F16>(lo, hi); }
+// element-wise maximum of two packed 16-bit pairs / the larger element of one pair as float32
+template <bool F16>
+__device__ __forceinline__ uint32_t max16x2(uint32_t a, uint32_t b) {
+    uint32_t r;
+    if (F16) asm("max.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    else asm("max.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
+}
+template <bool F16>
+__device__ __forceinline__ float hmax16x2(uint32_t a) {
+    if (F16) {
+        __half2 h = *reinterpret_cast<__half2*>(&a);
+        return fmaxf(__low2float(h), __high2float(h));
+    }
+    return fmaxf(__uint_as_float(a << 16), __uint_as_float(a & 0xFFFF0000u));
+}
 
 // SiLU with ONE special-function op and two FMAs: with t = x / 2, x * sigmoid(x) = t * (1 + tanh(t)) = fma(t, tanh(t), t)
 // (tanh.approx: 2^-11 relative error, far below the bf16 activations' 2^-8).  The epilogue is bound by the

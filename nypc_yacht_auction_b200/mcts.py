@@ -112,7 +112,7 @@ class FusedYachtEvaluator:
         for i in range(self.nblocks):
             p = "blocks.%d." % i
             for fc, ln in (("fc1", "ln1"), ("fc2", "ln2")):
-                images.append(self.swizzled_image(sd[p + fc + ".weight"].to(dev)))
+                images.append(self.pair_image(sd[p + fc + ".weight"].to(dev), 128))
                 params.append(torch.stack([0.5 * sd[p + fc + ".bias"], sd[p + ln + ".weight"], sd[p + ln + ".bias"]]).float())
         # params[layer] = bias / 2 | gamma | beta: the kernel's SiLU works on (z + b) / 2
         trunk_w = torch.cat(images) if images else torch.zeros(0, dtype=torch.uint8, device=dev)
@@ -121,10 +121,12 @@ class FusedYachtEvaluator:
         w_in[:, :sd["inp.0.weight"].shape[1]].copy_(sd["inp.0.weight"])
         w_pi = torch.zeros((26 * 128, 256), dtype=torch.float32, device=dev)
         w_pi[:a].copy_(sd["pi_head.2.weight"])
-        b_pi = torch.zeros(26 * 128, dtype=torch.float32, device=dev)
+        # the padding columns (>= the action count; their weights are zero) get a bias of -inf: their logits can never be a
+        # row maximum, and nobody reads them (they are not legal moves)
+        b_pi = torch.full((26 * 128,), float("-inf"), dtype=torch.float32, device=dev)
         b_pi[:a].copy_(sd["pi_head.2.bias"])
-        wparts = [self.swizzled_image(w_in), trunk_w, self.swizzled_image(sd["v_head.2.weight"].to(dev))] + \
-                 [self.swizzled_image(w_pi[128 * j:128 * (j + 1)]) for j in range(26)]
+        wparts = [self.pair_image(w_in, 256), trunk_w, self.pair_image(sd["v_head.2.weight"].to(dev), 128),
+                  self.pair_image(w_pi, 128, tile_major=True)]
         pparts = [f32(sd["inp.0.bias"]), f32(sd["inp.1.weight"]), f32(sd["inp.1.bias"]), trunk_p,
                   f32(sd["v_head.0.weight"]), f32(sd["v_head.0.bias"]), f32(sd["v_head.2.bias"]), f32(sd["v_head.4.weight"]),
                   torch.cat([f32(sd["v_head.4.bias"]), torch.zeros(3, device=dev)]),
@@ -151,6 +153,20 @@ class FusedYachtEvaluator:
         src_chunk = (torch.arange(8, device=w.device).view(1, 1, 8) ^ (r & 7)).expand(rows, k // 64, 8)
         img = torch.gather(w, 2, src_chunk.unsqueeze(-1).expand(rows, k // 64, 8, 8))
         return img.permute(1, 0, 2, 3).contiguous().view(torch.uint8).reshape(-1)
+
+    def pair_image(self, w, n_tile, tile_major=False):
+        """Weight [rows][K] for the CTA-pair kernel: the rows are consumed in blocks of n_tile output columns (one
+        tcgen05.mma.cta_group::2 N extent), and of each block rank 0 of the pair holds the first n_tile / 2 rows, rank 1 the
+        rest.  Layout: trunk / value / input = [rank][block][image of n_tile / 2 rows] (each CTA's share of a whole layer is
+        contiguous); policy head (many blocks streamed one at a time) the same with rows = one tile, i.e. [tile][rank][image]."""
+        rows, k = w.shape
+        half = n_tile // 2
+        blocks = w.reshape(rows // n_tile, 2, half, k)                  # [block][rank][half rows][K]
+        if tile_major:                                                  # policy head
+            order = blocks.reshape(-1, half, k)
+        else:
+            order = blocks.permute(1, 0, 2, 3).reshape(-1, half, k)    # rank-major
+        return torch.cat([self.swizzled_image(b) for b in order])
 
     def _alloc(self, n, dev):
         self.max_batch = n

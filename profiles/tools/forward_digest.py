@@ -1,0 +1,28 @@
+"""Digest of the forward kernel's outputs (dense logits, values, row maxima) on seeded weights and inputs, fp16 and bf16
+operands: a change of the kernel that is meant to keep the arithmetic must keep these digests."""
+import hashlib, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+import torch
+from nypc_yacht_auction_b200.mcts import FusedYachtEvaluator
+from nypc_yacht_auction_b200.nnet import YachtPolicyValueNet
+dev = torch.device("cuda", 0)
+torch.manual_seed(1234)
+net = YachtPolicyValueNet().to(dev).eval()
+with torch.no_grad():
+    for name, p in net.named_parameters():          # non-trivial biases and LayerNorm parameters
+        if name.endswith("bias") or "ln" in name or name in ("inp.1.weight", "pi_head.0.weight", "v_head.0.weight"):
+            p.add_(0.1 * torch.randn_like(p))
+for n in (1000, 16384):
+    x = torch.rand((n, 59), device=dev, generator=torch.Generator(device=dev).manual_seed(7))
+    for fp16 in (True, False):
+        ev = FusedYachtEvaluator(net, n, precision="fp16" if fp16 else "bf16")
+        logits, values = ev(x)
+        torch.cuda.synchronize()
+        h = hashlib.sha256()
+        for t in (logits[:, :3226].contiguous(), values, ev.last_row_max):
+            h.update(t.contiguous().view(torch.uint8).cpu().numpy().tobytes())
+        with torch.no_grad():
+            pi, v = net(x)
+        err = (logits[:, :3226].float() - pi).abs().max().item()
+        print("n=%d %s digest %s  max|logit - fp32| %.4f  max|v - fp32| %.5f" % (n, "fp16" if fp16 else "bf16", h.hexdigest()[:16], err,
+              (values - v.reshape(-1)).abs().max().item()))

@@ -17,15 +17,36 @@ if not torch.cuda.is_available():
     sys.exit(0)
 lib = ctypes.CDLL(dbg)
 dev = torch.device("cuda", 0)
-n = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
+pos = [a for a in sys.argv[1:] if not a.startswith("--")]
+n = int(pos[0]) if pos else 16384
 ev = FusedYachtEvaluator(YachtPolicyValueNet().to(dev).eval(), n)
 x = torch.rand((n, 59), device=dev)
 vp = ctypes.c_void_p
 lib.ya_nn_forward.argtypes = [vp, vp, vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_int, vp, vp, vp]
 logits = torch.empty((n, 3232), dtype=torch.float16, device=dev)
+# --scatter=bid|score|mix: the MCTS mode (legal logits into per-leaf rows, no dense matrix) with synthetic leaves: bid rows
+# (208 slots) and / or ten-dice rows with every category open (12 x 272 slots)
+mode = next((a.split("=")[1] for a in sys.argv if a.startswith("--scatter=")), None)
+sc_dst = sc_desc = None
+if mode:
+    # --stride-mb=S: rows S MB apart, like the leaf rows of a per-game tree pool (one 2 MB page per leaf)
+    stride_mb = next((float(a.split("=")[1]) for a in sys.argv if a.startswith("--stride-mb=")), None)
+    row_elems = 12 * 272 + 16 if stride_mb is None else int(stride_mb * (1 << 20)) // 2
+    area = torch.zeros((n, row_elems), dtype=torch.float16, device=dev)
+    sc_dst = (area.data_ptr() + torch.arange(n, device=dev, dtype=torch.int64) * area.stride(0) * 2).contiguous()
+    bid = torch.ones(n, dtype=torch.int32, device=dev)
+    score = torch.full((n,), (1 << 13) | (0xFFF << 1), dtype=torch.int32, device=dev)
+    mode = mode.split(",")[0]
+    if mode == "score-hot":          # every 256-leaf cluster writes the same 256 rows: the stores stay in L2 (no HBM write-back)
+        sc_dst = (area.data_ptr() + (torch.arange(n, device=dev, dtype=torch.int64) % 256) * area.stride(0) * 2).contiguous()
+    sc_desc = {"bid": bid, "score": score, "score-hot": score, "mix": torch.where(torch.arange(n, device=dev) % 2 == 0, bid, score)}[mode].contiguous()
+    logits = None
+def run():
+    return lib.ya_nn_forward(x.data_ptr(), logits.data_ptr() if logits is not None else None, ev.values.data_ptr(), ev.row_max.data_ptr(), ev.fw_w.data_ptr(),
+                             ev.fw_p.data_ptr(), ev.fw_off, ev.nblocks, n, ev.eps, 1, sc_dst.data_ptr() if mode else None,
+                             sc_desc.data_ptr() if mode else None, torch.cuda.current_stream().cuda_stream)
 for _ in range(5):
-    rc = lib.ya_nn_forward(x.data_ptr(), logits.data_ptr(), ev.values.data_ptr(), ev.row_max.data_ptr(), ev.fw_w.data_ptr(),
-                           ev.fw_p.data_ptr(), ev.fw_off, ev.nblocks, n, ev.eps, 1, None, None, torch.cuda.current_stream().cuda_stream)
+    rc = run()
     assert rc == 0, rc
     torch.cuda.synchronize()
 buf = (ctypes.c_ulonglong * 1024)()
@@ -43,11 +64,24 @@ base = 3 * nst
 pol = t[base:base + 27]
 print("policy: first accumulator ready at %.2f us; per tile (us):" % ((pol[0] - t0) / 1e3), " ".join("%.2f" % ((pol[i + 1] - pol[i]) / 1e3) for i in range(26)))
 print("total %.2f us" % ((pol[26] - t0) / 1e3))
+if hasattr(lib, "ya_debug_forward_timeline2"):
+    buf2 = (ctypes.c_ulonglong * 1024)()
+    assert lib.ya_debug_forward_timeline2(buf2) == 0
+    t2 = list(buf2)
+    if t2[1002] > t2[1000]:
+        print("SM clock inside the kernel: %.0f MHz (%d cycles in %.2f us)" % ((t2[1003] - t2[1001]) * 1e3 / (t2[1002] - t2[1000]),
+              t2[1003] - t2[1001], (t2[1002] - t2[1000]) / 1e3))
+    if t2[0]:
+        print("trunk layer detail (us, thread 0): issue->h0_ready  pass1_h0  wait_h1  pass1_h1  stats  pass2 | total")
+        for l in range(2 * ev.nblocks):
+            q = t2[8 * l:8 * l + 8]
+            d = [(q[i + 1] - q[i]) / 1e3 for i in range(6)]
+            print("  L%-2d  %s | %.2f" % (l, "  ".join("%5.2f" % x for x in d), (q[6] - q[0]) / 1e3))
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
 for _ in range(20):
-    lib.ya_nn_forward(x.data_ptr(), logits.data_ptr(), ev.values.data_ptr(), ev.row_max.data_ptr(), ev.fw_w.data_ptr(),
-                      ev.fw_p.data_ptr(), ev.fw_off, ev.nblocks, n, ev.eps, 1, None, None, torch.cuda.current_stream().cuda_stream)
+    run()
 e1.record()
 torch.cuda.synchronize()
-print("variant %s: %.1f us per forward (CUDA events, %d leaves, dense logits)" % ("".join(extra) or "production", e0.elapsed_time(e1) * 50.0, n))
+print("variant %s: %.1f us per forward (CUDA events, %d leaves, %s)" % ("".join(extra) or "production", e0.elapsed_time(e1) * 50.0, n,
+      "scatter " + mode if mode else "dense logits"))
