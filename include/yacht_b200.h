@@ -215,7 +215,8 @@ int ya_mcts_pick_action(const int32_t* counts, const int32_t* ply, const uint32_
  * tcgen05 kernel: features float32 [n][59] (state_to_vec rows) -> 16-bit logits [n][3232] (columns >= 3226 are
  * padding) and values float32 [n] (tanh).  fp16 != 0: operands (activations, weight images) and logits are IEEE half,
  * the precision of the reference's CUDA predict (fp16 autocast, yacht/NNet.py:186-193); fp16 == 0: bfloat16.
- * Accumulation, LayerNorm statistics and the skip connection are float32 in both modes.  weight_blob / param_blob are built once on the host
+ * Accumulation, bias, SiLU, LayerNorm and the residual sum are float32 in both modes; the residual stream is stored
+ * between blocks as IEEE half (with half operands: exactly the next block's operand).  weight_blob / param_blob are built once on the host
  * (mcts.FusedYachtEvaluator): 128-byte-swizzled K-major images of W_in (K padded to 64), the 2*nblocks trunk
  * weights, the value head's first Linear and 26 policy-head tiles of 128 columns; biases and LayerNorm
  * parameters as float32.  offsets (HOST pointer, int64[9]) = byte offsets {w_in, w_trunk, w_v, w_pi} and float
@@ -229,6 +230,13 @@ int ya_mcts_pick_action(const int32_t* counts, const int32_t* ply, const uint32_
 int ya_nn_forward(const float* features, void* logits16, float* values, float* row_max, const void* weight_blob,
                   const float* param_blob, const int64_t* offsets, int nblocks, int64_t n, float eps, int fp16,
                   const uint64_t* scatter_dst, const uint32_t* scatter_desc, void* stream);
+/* The same with the scheduling chosen by the caller.  tiles_per_cta = 1: one 128-leaf tile per CTA (a CTA pair = 256
+ * leaves); 2: two tiles per CTA (512 leaves per pair): the tensor core works on one tile while the 16 warps run the other
+ * tile's epilogue -- for waves of more than one tile per SM; 0: by size (ya_nn_forward).  Both schedules compute every
+ * row with the same arithmetic in the same order: outputs are bit-identical. */
+int ya_nn_forward_tiles(const float* features, void* logits16, float* values, float* row_max, const void* weight_blob,
+                        const float* param_blob, const int64_t* offsets, int nblocks, int64_t n, float eps, int fp16,
+                        const uint64_t* scatter_dst, const uint32_t* scatter_desc, int tiles_per_cta, void* stream);
 
 /* ---- host-buffer variants (end-to-end path for callers that keep boards in host memory) ----
  * ya_host_create allocates the device mirror for n games once (no allocation per call);

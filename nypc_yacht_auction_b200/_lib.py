@@ -46,6 +46,7 @@ SIGNATURES = {
     "ya_mcts_root_sparse": [_vp, _vp, _i64, _vp, _int, _vp, _vp, _vp, _vp],
     "ya_mcts_pick_action": [_vp, _vp, _vp, _i64, _u64, _u64, _int, _vp, _vp],
     "ya_nn_forward": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _int, _i64, ctypes.c_float, _int, _vp, _vp, _vp],
+    "ya_nn_forward_tiles": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _int, _i64, ctypes.c_float, _int, _vp, _vp, _int, _vp],
     "ya_host_create": [_i64, _int, ctypes.POINTER(ctypes.c_void_p)],
     "ya_host_destroy": [_vp],
     "ya_host_play_ply": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _u64, _u64, _int],

@@ -90,9 +90,12 @@ class FusedYachtEvaluator:
     supports_scatter = True
     PADDED = 3232
 
-    def __init__(self, net, max_batch, precision="fp16"):
+    def __init__(self, net, max_batch, precision="fp16", tiles_per_cta=0):
         if precision not in ("fp16", "bf16"):
             raise ValueError("precision must be 'fp16' or 'bf16', got %r" % (precision,))
+        if tiles_per_cta not in (0, 1, 2):
+            raise ValueError("tiles_per_cta must be 0 (by wave size), 1 or 2")
+        self.tiles_per_cta = tiles_per_cta          # scheduling only: both kernels give bit-identical rows
         self.precision = precision
         self.fp16 = precision == "fp16"
         self.op_dtype = torch.float16 if self.fp16 else torch.bfloat16
@@ -195,11 +198,12 @@ class FusedYachtEvaluator:
                 self.logits = torch.empty((self.max_batch, self.PADDED), dtype=self.op_dtype, device=self.device)
             logits = self.logits[:n]
         dst, desc = scatter if scatter is not None else (None, None)
-        _lib.check(self.lib.ya_nn_forward(_lib.ptr(features), _lib.ptr(logits), _lib.ptr(values),
-                                          _lib.ptr(self.last_row_max), _lib.ptr(self.fw_w),
-                                          _lib.ptr(self.fw_p), self.fw_off, self.nblocks, n, self.eps,
-                                          1 if self.fp16 else 0, _lib.ptr(dst), _lib.ptr(desc), _lib.current_stream()),
-                   "ya_nn_forward")
+        _lib.check(self.lib.ya_nn_forward_tiles(_lib.ptr(features), _lib.ptr(logits), _lib.ptr(values),
+                                                _lib.ptr(self.last_row_max), _lib.ptr(self.fw_w),
+                                                _lib.ptr(self.fw_p), self.fw_off, self.nblocks, n, self.eps,
+                                                1 if self.fp16 else 0, _lib.ptr(dst), _lib.ptr(desc), self.tiles_per_cta,
+                                                _lib.current_stream()),
+                   "ya_nn_forward_tiles")
         return logits, values
 
 

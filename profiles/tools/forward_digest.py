@@ -12,10 +12,10 @@ with torch.no_grad():
     for name, p in net.named_parameters():          # non-trivial biases and LayerNorm parameters
         if name.endswith("bias") or "ln" in name or name in ("inp.1.weight", "pi_head.0.weight", "v_head.0.weight"):
             p.add_(0.1 * torch.randn_like(p))
-for n in (1000, 16384):
+for n in (1000, 16384, 37888):
     x = torch.rand((n, 59), device=dev, generator=torch.Generator(device=dev).manual_seed(7))
-    for fp16 in (True, False):
-        ev = FusedYachtEvaluator(net, n, precision="fp16" if fp16 else "bf16")
+    for fp16, tiles in ((True, 1), (True, 2), (False, 1), (False, 2)):
+        ev = FusedYachtEvaluator(net, n, precision="fp16" if fp16 else "bf16", tiles_per_cta=tiles)
         logits, values = ev(x)
         torch.cuda.synchronize()
         h = hashlib.sha256()
@@ -24,5 +24,5 @@ for n in (1000, 16384):
         with torch.no_grad():
             pi, v = net(x)
         err = (logits[:, :3226].float() - pi).abs().max().item()
-        print("n=%d %s digest %s  max|logit - fp32| %.4f  max|v - fp32| %.5f" % (n, "fp16" if fp16 else "bf16", h.hexdigest()[:16], err,
+        print("n=%d tiles/CTA %d %s digest %s  max|logit - fp32| %.4f  max|v - fp32| %.5f" % (n, tiles, "fp16" if fp16 else "bf16", h.hexdigest()[:16], err,
               (values - v.reshape(-1)).abs().max().item()))

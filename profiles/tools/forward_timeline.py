@@ -22,7 +22,8 @@ n = int(pos[0]) if pos else 16384
 ev = FusedYachtEvaluator(YachtPolicyValueNet().to(dev).eval(), n)
 x = torch.rand((n, 59), device=dev)
 vp = ctypes.c_void_p
-lib.ya_nn_forward.argtypes = [vp, vp, vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_int, vp, vp, vp]
+lib.ya_nn_forward_tiles.argtypes = [vp, vp, vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_int, vp, vp, ctypes.c_int, vp]
+tiles = next((int(a.split("=")[1]) for a in sys.argv if a.startswith("--tiles=")), 0)
 logits = torch.empty((n, 3232), dtype=torch.float16, device=dev)
 # --scatter=bid|score|mix: the MCTS mode (legal logits into per-leaf rows, no dense matrix) with synthetic leaves: bid rows
 # (208 slots) and / or ten-dice rows with every category open (12 x 272 slots)
@@ -42,41 +43,64 @@ if mode:
     sc_desc = {"bid": bid, "score": score, "score-hot": score, "mix": torch.where(torch.arange(n, device=dev) % 2 == 0, bid, score)}[mode].contiguous()
     logits = None
 def run():
-    return lib.ya_nn_forward(x.data_ptr(), logits.data_ptr() if logits is not None else None, ev.values.data_ptr(), ev.row_max.data_ptr(), ev.fw_w.data_ptr(),
-                             ev.fw_p.data_ptr(), ev.fw_off, ev.nblocks, n, ev.eps, 1, sc_dst.data_ptr() if mode else None,
-                             sc_desc.data_ptr() if mode else None, torch.cuda.current_stream().cuda_stream)
+    return lib.ya_nn_forward_tiles(x.data_ptr(), logits.data_ptr() if logits is not None else None, ev.values.data_ptr(), ev.row_max.data_ptr(), ev.fw_w.data_ptr(),
+                                   ev.fw_p.data_ptr(), ev.fw_off, ev.nblocks, n, ev.eps, 1, sc_dst.data_ptr() if mode else None,
+                                   sc_desc.data_ptr() if mode else None, tiles, torch.cuda.current_stream().cuda_stream)
 for _ in range(5):
     rc = run()
     assert rc == 0, rc
     torch.cuda.synchronize()
+two = tiles == 2 or (tiles == 0 and n > 148 * 128)
 buf = (ctypes.c_ulonglong * 1024)()
 assert lib.ya_debug_forward_timeline(buf) == 0
 t = list(buf)
-nst = 2 + 2 * ev.nblocks                    # run_mma stages: input, trunk layers, value head
-names = ["input"] + ["trunk%d" % i for i in range(2 * ev.nblocks)] + ["value"]
-t0 = t[0]
-print("stage        start_us  wait_weights  mma   epilogue(until next stage's sync)")
-for k in range(nst):
-    a, b, c = t[3 * k], t[3 * k + 1], t[3 * k + 2]
-    nxt = t[3 * k + 3]
-    print("%-10s %9.2f %9.2f %9.2f %9.2f" % (names[k], (a - t0) / 1e3, (b - a) / 1e3, (c - b) / 1e3, (nxt - c) / 1e3))
-base = 3 * nst
-pol = t[base:base + 27]
-print("policy: first accumulator ready at %.2f us; per tile (us):" % ((pol[0] - t0) / 1e3), " ".join("%.2f" % ((pol[i + 1] - pol[i]) / 1e3) for i in range(26)))
-print("total %.2f us" % ((pol[26] - t0) / 1e3))
-if hasattr(lib, "ya_debug_forward_timeline2"):
-    buf2 = (ctypes.c_ulonglong * 1024)()
-    assert lib.ya_debug_forward_timeline2(buf2) == 0
-    t2 = list(buf2)
-    if t2[1002] > t2[1000]:
-        print("SM clock inside the kernel: %.0f MHz (%d cycles in %.2f us)" % ((t2[1003] - t2[1001]) * 1e3 / (t2[1002] - t2[1000]),
-              t2[1003] - t2[1001], (t2[1002] - t2[1000]) / 1e3))
+buf2 = (ctypes.c_ulonglong * 1024)()
+assert lib.ya_debug_forward_timeline2(buf2) == 0
+t2 = list(buf2)
+if not two:
+    nst = 2 + 2 * ev.nblocks                    # stages: input, trunk layers, value head
+    names = ["input"] + ["trunk%d" % i for i in range(2 * ev.nblocks)] + ["value"]
+    t0 = t[0]
+    print("stage        start_us  wait_weights  mma   epilogue(until next stage's sync)")
+    for k in range(nst):
+        a, b, c = t[3 * k], t[3 * k + 1], t[3 * k + 2]
+        nxt = t[3 * k + 3]
+        print("%-10s %9.2f %9.2f %9.2f %9.2f" % (names[k], (a - t0) / 1e3, (b - a) / 1e3, (c - b) / 1e3, (nxt - c) / 1e3))
+    base = 3 * nst
+    pol = t[base:base + 27]
+    print("policy: first accumulator ready at %.2f us; per tile (us):" % ((pol[0] - t0) / 1e3), " ".join("%.2f" % ((pol[i + 1] - pol[i]) / 1e3) for i in range(26)))
+    print("total %.2f us" % ((pol[26] - t0) / 1e3))
     if t2[0]:
         print("trunk layer detail (us, thread 0): issue->h0_ready  pass1_h0  wait_h1  pass1_h1  stats  pass2 | total")
         for l in range(2 * ev.nblocks):
             q = t2[8 * l:8 * l + 8]
             d = [(q[i + 1] - q[i]) / 1e3 for i in range(6)]
             print("  L%-2d  %s | %.2f" % (l, "  ".join("%5.2f" % x for x in d), (q[6] - q[0]) / 1e3))
+else:
+    t0 = t2[1000]
+    print("two tiles per CTA; epilogues of CTA 0 (us, thread 0): start | wait_h0  pass1_h0  wait_h1  pass1_h1  stats  pass2  close | total")
+    for e in range(4 * ev.nblocks):
+        q = t2[8 * e:8 * e + 8]
+        d = [(q[i + 1] - q[i]) / 1e3 for i in range(7)]
+        print("  L%-2d %s  %7.2f | %s | %.2f" % (e // 2, "XY"[e % 2], (q[0] - t0) / 1e3, "  ".join("%5.2f" % x for x in d), (q[7] - q[0]) / 1e3))
+    names = ["features", "input weights", "X input MMA", "X input epilogue", "Y input MMA", "Y input epilogue", "(trunk) head parameters", "X heads", "Y heads", "X value", "Y value"]
+    print("other stages (us since start, duration): " + "; ".join("%s %.2f (+%.2f)" % (names[i], (t[i + 1] - t0) / 1e3, (t[i + 1] - t[i]) / 1e3) for i in range(11)))
+    t = t[12:]
+    pol = t[0:53]
+    print("policy: first accumulator ready at %.2f us; per (tile, X / Y) (us):" % ((pol[0] - t0) / 1e3), " ".join("%.2f" % ((pol[i + 1] - pol[i]) / 1e3) for i in range(52)))
+    print("total %.2f us" % ((pol[52] - t0) / 1e3))
+if t2[1002] > t2[1000]:
+    print("SM clock inside the kernel: %.0f MHz (%d cycles in %.2f us)" % ((t2[1003] - t2[1001]) * 1e3 / (t2[1002] - t2[1000]),
+          t2[1003] - t2[1001], (t2[1002] - t2[1000]) / 1e3))
+cb = (ctypes.c_ulonglong * 4096)()
+assert lib.ya_debug_forward_cta_times(cb) == 0
+c = list(cb)
+nb = 2 * ((n + (512 if two else 256) - 1) // (512 if two else 256))
+tc0 = min(c[4 * i] for i in range(nb))
+du = sorted((c[4 * i + 2] - c[4 * i]) / 1e3 for i in range(nb))
+tr = sorted((c[4 * i + 1] - c[4 * i]) / 1e3 for i in range(nb))
+print("per CTA (us): trunk done after min %.1f median %.1f max %.1f | duration min %.1f median %.1f max %.1f | last end %.1f | %d CTAs on %d SMs" % (
+    tr[0], tr[len(tr) // 2], tr[-1], du[0], du[len(du) // 2], du[-1], max(c[4 * i + 2] - tc0 for i in range(nb)) / 1e3, nb, len({c[4 * i + 3] for i in range(nb)})))
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
 for _ in range(20):

@@ -13,7 +13,8 @@ n = int(pos[0]) if pos else 16384
 episode = "--episode" in sys.argv
 torch.manual_seed(0)
 net = YachtPolicyValueNet().to(dev).eval()
-ev0 = FusedYachtEvaluator(net, n)
+tiles = next((int(a.split('=')[1]) for a in sys.argv if a.startswith('--tiles=')), 0)
+ev0 = FusedYachtEvaluator(net, n, tiles_per_cta=tiles)
 def ev_pair():
     return torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 plies = next(([int(x) for x in a.split('=')[1].split(',')] for a in sys.argv if a.startswith('--plies=')), [6, 8])
@@ -64,10 +65,10 @@ for ply in plies:
         import ctypes
         dbg = ctypes.CDLL(os.path.join(os.path.dirname(os.path.abspath(__file__)), "_dbg", "libfwd_tl.so"))
         vp = ctypes.c_void_p
-        dbg.ya_nn_forward.argtypes = [vp, vp, vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_int, vp, vp, vp]
+        dbg.ya_nn_forward_tiles.argtypes = [vp, vp, vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_int, vp, vp, ctypes.c_int, vp]
         for _ in range(3):
-            assert dbg.ya_nn_forward(grp.features.data_ptr(), None, ev.values.data_ptr(), ev.row_max.data_ptr(), ev.fw_w.data_ptr(), ev.fw_p.data_ptr(),
-                                     ev.fw_off, ev.nblocks, n, ev.eps, 1, grp.leaf_dst.data_ptr(), grp.leaf_desc.data_ptr(), s) == 0
+            assert dbg.ya_nn_forward_tiles(grp.features.data_ptr(), None, ev.values.data_ptr(), ev.row_max.data_ptr(), ev.fw_w.data_ptr(), ev.fw_p.data_ptr(),
+                                           ev.fw_off, ev.nblocks, n, ev.eps, 1, grp.leaf_dst.data_ptr(), grp.leaf_desc.data_ptr(), 1, s) == 0
             torch.cuda.synchronize(dev)
         buf = (ctypes.c_ulonglong * 1024)()
         assert dbg.ya_debug_forward_timeline(buf) == 0
