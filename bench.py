@@ -535,6 +535,9 @@ def run_extras(args, torch, env, dev, n, peaks, prof, rank=0, world=1, dist=None
     wb_bid = mb.wave_breakdown(torch, dev, 16384, 100, ev, args.seed + 2, plies_before=8)   # ply 8: first bid of round 3 (202-move rows)
     wb148 = mb.wave_breakdown(torch, dev, 148 * 128, 100, FusedYachtEvaluator(net, 148 * 128, precision="fp16"), args.seed + 2)
     fwd_us, fwd_us_148 = wb["forward_us"], wb148["forward_us"]
+    n2 = 2 * 148 * 128                                     # the configs[4] wave: two tiles per CTA on every SM
+    wb2 = mb.wave_breakdown(torch, dev, n2, 100, FusedYachtEvaluator(net, n2, precision="fp16"), args.seed + 2)
+    wb2_one = mb.wave_breakdown(torch, dev, n2, 100, FusedYachtEvaluator(net, n2, precision="fp16", tiles_per_cta=1), args.seed + 2)
     dense_us = mb.forward_alone(torch, dev, ev, 16384)
     ev.logits = None                                       # drop the dense matrix again (106 MB)
     real_flops = 2.0 * YachtPolicyValueNet.num_macs()
@@ -546,7 +549,13 @@ def run_extras(args, torch, env, dev, n, peaks, prof, rank=0, world=1, dist=None
            "dense_logits_variant_us": dense_us,
            "full_machine": {"leaves": 148 * 128, "us_per_launch": fwd_us_148, "achieved": real_flops * 148 * 128 / fwd_us_148 * 1e-6,
                             "frac": real_flops * 148 * 128 / fwd_us_148 * 1e-6 / peaks["tensor"],
-                            "note": "one CTA of 128 leaves per SM: 16,384 leaves fill 128 of 148 SMs, 18,944 fill all"}}
+                            "note": "one CTA of 128 leaves per SM: 16,384 leaves fill 128 of 148 SMs, 18,944 fill all"},
+           "two_tiles_per_cta": {"leaves": n2, "us_per_launch": wb2["forward_us"], "achieved": real_flops * n2 / wb2["forward_us"] * 1e-6,
+                                 "frac": real_flops * n2 / wb2["forward_us"] * 1e-6 / peaks["tensor"],
+                                 "one_tile_schedule_us": wb2_one["forward_us"], "wave": wb2,
+                                 "note": "ya_k_forward2 (waves above one tile per SM, e.g. the configs[4] waves of 37,888 games): each CTA "
+                                         "owns two 128-leaf tiles, the tensor core runs one tile's MMAs under the other tile's epilogue; "
+                                         "bit-identical to the one-tile schedule (two launch rounds), whose time is given beside it"}}
     bf = mb.selfplay_block(torch, dev, dist, rank, world, 16384, 100, FusedYachtEvaluator(net, 16384, precision="bf16"), args.seed + 2,
                            steps=1, warm=1, e2e_steps=0)
     r.update({"workload": "configs[3]: AlphaZero self-play, random-init YachtNNet (hidden 256, 6 blocks), numMCTSSims=100, 16384 games per GPU; "

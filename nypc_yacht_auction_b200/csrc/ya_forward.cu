@@ -141,21 +141,23 @@ struct Lane {
     }
 };
 
-// features (float32 [n][59]) -> 16-bit, K padded to 64: this thread fills chunks 2 * part, 2 * part + 1 of K-block 0
-template <bool F16>
-__device__ __forceinline__ void load_features(const Lane& L, const float* __restrict__ features, int64_t grow, int64_t n, uint8_t* a_tile) {
-    uint32_t f[16];
+// features (float32 [n][59]) -> 16-bit, K padded to 64: this thread fills chunks 2 * part, 2 * part + 1 of K-block 0.
+// The global loads are issued at the very top of the kernel (they are in flight during barrier and TMEM set-up).
+__device__ __forceinline__ void fetch_features(float (&f)[16], int part, const float* __restrict__ features, int64_t grow, int64_t n) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
-        int c = L.part * 16 + i;
-        f[i] = (grow < n && c < kFeat) ? __float_as_uint(features[grow * kFeat + c]) : 0u;
+        int c = part * 16 + i;
+        f[i] = (grow < n && c < kFeat) ? features[grow * kFeat + c] : 0.0f;
     }
+}
+template <bool F16>
+__device__ __forceinline__ void store_features(const float (&f)[16], int row, int part, uint8_t* a_tile) {
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
         uint32_t p[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) p[i] = pack2<F16>(__uint_as_float(f[q * 8 + 2 * i]), __uint_as_float(f[q * 8 + 2 * i + 1]));
-        *reinterpret_cast<uint4*>(a_tile + a_tile_offset(L.row, L.part * 2 + q)) = make_uint4(p[0], p[1], p[2], p[3]);
+        for (int i = 0; i < 4; ++i) p[i] = pack2<F16>(f[q * 8 + 2 * i], f[q * 8 + 2 * i + 1]);
+        *reinterpret_cast<uint4*>(a_tile + a_tile_offset(row, part * 2 + q)) = make_uint4(p[0], p[1], p[2], p[3]);
     }
 }
 
@@ -444,6 +446,8 @@ ya_k_forward(const float* __restrict__ features, uint16_t* __restrict__ logits, 
     const bool producer = warp == kIssuerWarp;                        // also an epilogue warp, except in the policy head
     const uint32_t rank = cluster_ctarank();
     const bool leader = rank == 0;
+    float feat[16];
+    fetch_features(feat, part, features, grow, n);
 
     if (tid == 0) {
         for (int i = 0; i < B_DRAIN; ++i) mbar_init(&bars[i], 1);
@@ -567,7 +571,7 @@ ya_k_forward(const float* __restrict__ features, uint16_t* __restrict__ logits, 
         load_stage(0);
         load_stage(1);                                                // first trunk layer (or the value head) streams in
     }
-    load_features<F16>(L, features, grow, n, a_tile);
+    store_features<F16>(feat, row, part, a_tile);
     begin_stage(0);
     wait_mma(0, 0);
     wait_mma(0, 1);
@@ -786,6 +790,9 @@ ya_k_forward2(const float* __restrict__ features, uint16_t* __restrict__ logits,
     const bool leader = rank == 0;
     auto a_tile = [&](int t) { return base + t * kABytes; };
     auto grow_of = [&](int t) { return ((int64_t)blockIdx.x * 2 + t) * kRows + row; };
+    float feat0[16], feat1[16];
+    fetch_features(feat0, part, features, grow_of(0), n);
+    fetch_features(feat1, part, features, grow_of(1), n);
 
     if (tid == 0) {
         for (int i = 0; i < kBars; ++i) mbar_init(&bars[i], (i == C_FREE || i == C_FREE + 1) ? 16 : (i == C_DRAIN || i == C_DRAIN + 1) ? 30 : 1);
@@ -910,8 +917,8 @@ ya_k_forward2(const float* __restrict__ features, uint16_t* __restrict__ logits,
         load_piece(1);
     }
     YA_STAMP();                                                        // [0] start
-    load_features<F16>(L, features, grow_of(0), n, a_tile(0));
-    load_features<F16>(L, features, grow_of(1), n, a_tile(1));
+    store_features<F16>(feat0, row, part, a_tile(0));
+    store_features<F16>(feat1, row, part, a_tile(1));
     close_epilogue();
     YA_STAMP();                                                        // [1] features in shared memory
     if (producer) issue_group(0, 0, 0, true, -1);

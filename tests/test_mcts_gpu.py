@@ -314,7 +314,29 @@ def test_fused_evaluator_matches_module_forward(precision, dtype):
 
 
 @pytest.mark.parametrize("precision", ["fp16", "bf16"])
-def test_scattered_rows_equal_dense_logit_rows(precision):
+def test_two_tile_schedule_is_bit_identical(precision):
+    """ya_nn_forward_tiles: the two-tiles-per-CTA kernel (tensor core on one tile under the other tile's epilogue) computes
+    every row with the same arithmetic as the one-tile kernel -- dense logits, values and row maxima are bit-identical, for
+    full and ragged waves (rows beyond n, a last CTA pair with one to four tiles), so the choice of schedule (by wave size)
+    cannot break batch / shard invariance."""
+    from nypc_yacht_auction_b200.mcts import FusedYachtEvaluator
+    net = _perturbed_net(5)
+    g = torch.Generator(device="cuda").manual_seed(11)
+    for n in (1, 129, 300, 513, 1100):
+        x = torch.rand((n, 59), device="cuda", generator=g)
+        outs = []
+        for tiles in (1, 2):
+            ev = FusedYachtEvaluator(net, n, precision=precision, tiles_per_cta=tiles)
+            logits, v = ev(x)
+            outs.append((logits[:, :3226].clone(), v.clone(), ev.last_row_max.clone()))
+        for a, b in zip(*outs):
+            assert torch.equal(a.view(torch.uint8) if a.dtype == torch.bfloat16 else a, b.view(torch.uint8) if b.dtype == torch.bfloat16 else b), n
+    with pytest.raises(ValueError):
+        FusedYachtEvaluator(net, 8, tiles_per_cta=3)
+
+
+@pytest.mark.parametrize("precision,tiles", [("fp16", 1), ("bf16", 1), ("fp16", 2)])
+def test_scattered_rows_equal_dense_logit_rows(precision, tiles):
     """the policy-head epilogue writes each leaf's legal logits straight into its row of the tree pool
     (ya_nn_forward with scatter targets).  Against the same kernel writing the dense [n, 3232] matrix and
     ya_mcts_expand_logits compacting it: identical rows, visit counts, Q values (bit patterns) and moves, over bid plies,
@@ -337,7 +359,8 @@ def test_scattered_rows_equal_dense_logit_rows(precision):
     n, sims = 160, 20
     for start in (0, 40):                                  # from the deal, and from ply 40 (rounds 11-13: few open categories, 5 dice)
         runs = []
-        for make in (lambda: FusedYachtEvaluator(net, n, precision=precision), lambda: Dense(FusedYachtEvaluator(net, n, precision=precision))):
+        for make in (lambda: FusedYachtEvaluator(net, n, precision=precision, tiles_per_cta=tiles),
+                     lambda: Dense(FusedYachtEvaluator(net, n, precision=precision, tiles_per_cta=tiles))):
             env = _engine(n, 8, 300)
             for _ in range(start):
                 env.play_ply(masks=None, auto_reset=False)
