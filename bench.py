@@ -632,6 +632,10 @@ def dropin_mcts_rate(torch, dev, sims=25, plies=12):
 
 def main():
     args = parse_args()
+    wd = float(os.environ.get("YA_BENCH_WATCHDOG", "0") or 0)   # seconds; > 0: dump every thread's stack to stderr and exit if still running
+    if wd > 0:
+        import faulthandler
+        faulthandler.dump_traceback_later(wd, exit=True)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -766,7 +766,13 @@ enum { C_WL = 0,        // [2] weight piece (+ parameters) landed in slot p & 1
        C_SLOT = 10,     // [6] policy head: this CTA's half of a weight tile landed in the slot
        C_PSLOT = 16,    // [6] leader only: the other CTA's half landed
        C_ACC = 22,      // [2] policy head: accumulator of tile t ready (commit multicast)
-       C_DRAIN = 24 };  // [2] leader only: accumulator of tile t read out by the 15 epilogue warps of BOTH CTAs (count 30)
+       C_DRAIN = 24,    // [2] leader only: accumulator of tile t read out by the 15 epilogue warps of BOTH CTAs (count 30)
+       C_VPEER = 29,    // [2] leader only: rank 1 is ready for tile t's value-head MMAs.  Own barriers: the two value hand-offs follow
+                        //     each other with no MMA completion in between, so on a shared barrier rank 1 could report twice before
+                        //     a slower leader has looked once -- and the leader would wait for the parity of a phase long gone
+       C_RET = 26 };    // [3] policy head: both tiles' MMAs on weight tile j retired (slot j % 3; commit multicast).  A barrier of its
+                        //     own, three tiles deep: a producer that tests "tile j - 1 retired" on C_ACC a moment after tile j has
+                        //     ALSO retired would see the parity of two phases ago as pending and wait for a tile it has to load first
 
 template <bool F16>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
@@ -863,14 +869,21 @@ ya_k_forward2(const float* __restrict__ features, uint16_t* __restrict__ logits,
             if (whole) mbar_wait(&bars[C_FREE + 1], (uint32_t)(free_phase & 1));
         }
         mbar_wait(piece_bar(piece), piece_par(piece));
+        const bool value_head = s > layers;
         if (!leader) {
             if (elect_one()) {
-                mbar_arrive_remote(&bars[C_PEER + h], 0);
-                if (whole) mbar_arrive_remote(&bars[C_PEER + 1], 0);
+                if (value_head) mbar_arrive_remote(&bars[C_VPEER + t], 0);
+                else {
+                    mbar_arrive_remote(&bars[C_PEER + h], 0);
+                    if (whole) mbar_arrive_remote(&bars[C_PEER + 1], 0);
+                }
             }
         } else {
-            mbar_wait(&bars[C_PEER + h], (uint32_t)(g & 1));
-            if (whole) mbar_wait(&bars[C_PEER + 1], (uint32_t)(g & 1));
+            if (value_head) mbar_wait(&bars[C_VPEER + t], 0u);
+            else {
+                mbar_wait(&bars[C_PEER + h], (uint32_t)(g & 1));
+                if (whole) mbar_wait(&bars[C_PEER + 1], (uint32_t)(g & 1));
+            }
             tc_fence_after();
             if (elect_one()) {
                 const uint64_t da = umma_desc(smem_u32(a_tile(t))), db = umma_desc(smem_u32(w_slots + (piece & 1) * kSlotBytes));
@@ -1081,12 +1094,13 @@ ya_k_forward2(const float* __restrict__ features, uint16_t* __restrict__ logits,
                                     umma2_ts(tmem + kSkipCol + 128 * t, tmem + 128 * t + kb * 32 + k * 8,
                                              umma_desc_advance(db, kb * 8192 + k * 32), (uint32_t)((kb | k) != 0), idesc);
                             umma2_commit(&bars[C_ACC + t]);
+                            if (t == 1) umma2_commit(&bars[C_RET + j % 3]);
                         }
                         __syncwarp();
                     }
                 }
                 if (j >= 1 && j + kSlots - 1 < kPolicyTiles) {        // tile j - 1 has retired in both accumulators: refill its slot
-                    mbar_wait(&bars[C_ACC + 1], (uint32_t)((j - 1) & 1));
+                    mbar_wait(&bars[C_RET + (j - 1) % 3], (uint32_t)(((j - 1) / 3) & 1));
                     if (elect_one()) load_tile(j + kSlots - 1);
                     __syncwarp();
                 }

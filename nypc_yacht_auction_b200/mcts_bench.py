@@ -9,6 +9,8 @@ barrier + synchronize on both sides, max over ranks.  The e2e figures go through
 """
 from __future__ import annotations
 
+import os
+import sys
 import time
 
 PLIES = 48
@@ -186,6 +188,8 @@ def selfplay_1m(torch, dev, dist, rank, world, evaluator_factory, total, sims, w
             dst.copy_(ex[name], non_blocking=True)
             tally["d2h"] += dst.numel() * dst.element_size()
         tally["waves"] += 1
+        if os.environ.get("YA_BENCH_PROGRESS"):
+            print("[selfplay_1m] rank %d wave %d done after %.1f s" % (rank, w, time.perf_counter() - t0), file=sys.stderr, flush=True)
 
     _fence(torch, dev, dist, world)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
