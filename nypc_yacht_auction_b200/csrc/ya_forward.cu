@@ -150,6 +150,20 @@ __device__ __forceinline__ void fetch_features(float (&f)[16], int part, const f
         f[i] = (grow < n && c < kFeat) ? features[grow * kFeat + c] : 0.0f;
     }
 }
+// A full tile's 128 feature rows are contiguous in global memory (30,208 bytes): ONE bulk copy, issued before the TMEM /
+// cluster set-up, parks them in the part of the A tile the input stage does not read (K-blocks 1..3); from there every
+// thread picks its 16 columns (row stride 59 words: odd, conflict-free).  Ragged tiles and unaligned feature buffers use
+// the per-thread global loads above.
+constexpr int kFeatTileBytes = kRows * kFeat * 4;
+constexpr int kFeatStage = 16384;                     // offset of the parking area inside an A tile
+__device__ __forceinline__ void unpark_features(float (&f)[16], int row, int part, const uint8_t* a_tile) {
+    const float* raw = reinterpret_cast<const float*>(a_tile + kFeatStage) + row * kFeat;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        int c = part * 16 + i;
+        f[i] = c < kFeat ? raw[c] : 0.0f;
+    }
+}
 template <bool F16>
 __device__ __forceinline__ void store_features(const float (&f)[16], int row, int part, uint8_t* a_tile) {
 #pragma unroll
@@ -422,13 +436,14 @@ enum { B_W = 0,         // [2] weights + parameters of a stage landed in buffer 
        B_SLOT = 5,      // [6] policy head: this CTA's half of a weight tile landed in the slot
        B_PSLOT = 11,    // [6] leader only: the other CTA's half landed
        B_ACC = 17,      // [3] policy head: accumulator ready (commit multicast)
-       B_DRAIN = 20 };  // [3] leader only: accumulator read out by the 15 epilogue warps of BOTH CTAs
+       B_DRAIN = 20,    // [3] leader only: accumulator read out by the 15 epilogue warps of BOTH CTAs
+       B_FEAT = 23 };   // the tile's feature rows landed in the parking area
 
 template <bool F16>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 ya_k_forward(const float* __restrict__ features, uint16_t* __restrict__ logits, float* __restrict__ values,
              float* __restrict__ row_max, const uint8_t* __restrict__ wblob, const float* __restrict__ pblob, Blob off, int nblocks, int64_t n, float eps,
-             const uint64_t* __restrict__ scatter_dst, const uint32_t* __restrict__ scatter_desc) {
+             const uint64_t* __restrict__ scatter_dst, const uint32_t* __restrict__ scatter_desc, bool feat_aligned) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* a_tile = base;
@@ -446,13 +461,20 @@ ya_k_forward(const float* __restrict__ features, uint16_t* __restrict__ logits, 
     const bool producer = warp == kIssuerWarp;                        // also an epilogue warp, except in the policy head
     const uint32_t rank = cluster_ctarank();
     const bool leader = rank == 0;
+    const bool feat_bulk = feat_aligned && (int64_t)(blockIdx.x + 1) * kRows <= n;   // a full tile of an aligned feature matrix
     float feat[16];
-    fetch_features(feat, part, features, grow, n);
+    if (!feat_bulk) fetch_features(feat, part, features, grow, n);
 
     if (tid == 0) {
         for (int i = 0; i < B_DRAIN; ++i) mbar_init(&bars[i], 1);
         for (int i = B_DRAIN; i < B_DRAIN + 3; ++i) mbar_init(&bars[i], 30);
+        mbar_init(&bars[B_FEAT], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (feat_bulk) {
+            proxy_fence();
+            mbar_expect_tx(&bars[B_FEAT], kFeatTileBytes);
+            bulk_g2s(a_tile + kFeatStage, features + (int64_t)blockIdx.x * kRows * kFeat, kFeatTileBytes, &bars[B_FEAT]);
+        }
     }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
@@ -570,6 +592,10 @@ ya_k_forward(const float* __restrict__ features, uint16_t* __restrict__ logits, 
     if (producer && elect_one()) {
         load_stage(0);
         load_stage(1);                                                // first trunk layer (or the value head) streams in
+    }
+    if (feat_bulk) {
+        mbar_wait(&bars[B_FEAT], 0u);
+        unpark_features(feat, row, part, a_tile);
     }
     store_features<F16>(feat, row, part, a_tile);
     begin_stage(0);
@@ -770,6 +796,7 @@ enum { C_WL = 0,        // [2] weight piece (+ parameters) landed in slot p & 1
        C_VPEER = 29,    // [2] leader only: rank 1 is ready for tile t's value-head MMAs.  Own barriers: the two value hand-offs follow
                         //     each other with no MMA completion in between, so on a shared barrier rank 1 could report twice before
                         //     a slower leader has looked once -- and the leader would wait for the parity of a phase long gone
+       C_FEAT = 31,     // both tiles' feature rows landed in their parking areas
        C_RET = 26 };    // [3] policy head: both tiles' MMAs on weight tile j retired (slot j % 3; commit multicast).  A barrier of its
                         //     own, three tiles deep: a producer that tests "tile j - 1 retired" on C_ACC a moment after tile j has
                         //     ALSO retired would see the parity of two phases ago as pending and wait for a tile it has to load first
@@ -778,7 +805,7 @@ template <bool F16>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 ya_k_forward2(const float* __restrict__ features, uint16_t* __restrict__ logits, float* __restrict__ values,
               float* __restrict__ row_max, const uint8_t* __restrict__ wblob, const float* __restrict__ pblob, Blob off, int nblocks, int64_t n, float eps,
-              const uint64_t* __restrict__ scatter_dst, const uint32_t* __restrict__ scatter_desc) {
+              const uint64_t* __restrict__ scatter_dst, const uint32_t* __restrict__ scatter_desc, bool feat_aligned) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* w_slots = base + 2 * kABytes;                            // A tiles of X and Y, then two 32 KB weight slots
@@ -796,13 +823,23 @@ ya_k_forward2(const float* __restrict__ features, uint16_t* __restrict__ logits,
     const bool leader = rank == 0;
     auto a_tile = [&](int t) { return base + t * kABytes; };
     auto grow_of = [&](int t) { return ((int64_t)blockIdx.x * 2 + t) * kRows + row; };
+    const bool feat_bulk = feat_aligned && ((int64_t)blockIdx.x * 2 + 2) * kRows <= n;   // two full tiles of an aligned feature matrix
     float feat0[16], feat1[16];
-    fetch_features(feat0, part, features, grow_of(0), n);
-    fetch_features(feat1, part, features, grow_of(1), n);
+    if (!feat_bulk) {
+        fetch_features(feat0, part, features, grow_of(0), n);
+        fetch_features(feat1, part, features, grow_of(1), n);
+    }
 
     if (tid == 0) {
         for (int i = 0; i < kBars; ++i) mbar_init(&bars[i], (i == C_FREE || i == C_FREE + 1) ? 16 : (i == C_DRAIN || i == C_DRAIN + 1) ? 30 : 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (feat_bulk) {
+            proxy_fence();
+            mbar_expect_tx(&bars[C_FEAT], 2 * kFeatTileBytes);
+            const float* src = features + (int64_t)blockIdx.x * 2 * kRows * kFeat;
+            bulk_g2s(base + kFeatStage, src, kFeatTileBytes, &bars[C_FEAT]);
+            bulk_g2s(base + kABytes + kFeatStage, src + kRows * kFeat, kFeatTileBytes, &bars[C_FEAT]);
+        }
     }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
@@ -930,6 +967,11 @@ ya_k_forward2(const float* __restrict__ features, uint16_t* __restrict__ logits,
         load_piece(1);
     }
     YA_STAMP();                                                        // [0] start
+    if (feat_bulk) {
+        mbar_wait(&bars[C_FEAT], 0u);
+        unpark_features(feat0, row, part, a_tile(0));
+        unpark_features(feat1, row, part, a_tile(1));
+    }
     store_features<F16>(feat0, row, part, a_tile(0));
     store_features<F16>(feat1, row, part, a_tile(1));
     close_epilogue();
@@ -1204,7 +1246,7 @@ extern "C" int ya_nn_forward_tiles(const float* features, void* logits16, float*
     auto launch = [&](auto kernel) {
         kernel<<<blocks, kThreads, kSmemBytes, (cudaStream_t)stream>>>(
             features, static_cast<uint16_t*>(logits16), values, row_max, static_cast<const uint8_t*>(weight_blob), param_blob, off,
-            nblocks, n, eps, scatter_dst, scatter_desc);
+            nblocks, n, eps, scatter_dst, scatter_desc, (reinterpret_cast<uintptr_t>(features) & 15u) == 0);
     };
     if (tiles_per_cta == 2) { if (fp16) launch(ya_k_forward2<true>); else launch(ya_k_forward2<false>); }
     else { if (fp16) launch(ya_k_forward<true>); else launch(ya_k_forward<false>); }
