@@ -165,13 +165,12 @@ def selfplay_1m(torch, dev, dist, rank, world, evaluator_factory, total, sims, w
     from .dist import shard_range
     first, last = shard_range(total, rank, world)
     mine = last - first
-    # wave size: whole rounds of the forward kernel (one 128-leaf CTA per SM: 148 x 128 = 18,944 games per round).  The pool
-    # holds `wave_cap` games (two rounds); if the shard is an odd number of rounds, single-round waves waste less padding.
-    unit = 148 * 128
-    units, cap_units = (mine + unit - 1) // unit, max(1, wave_cap // unit)
-    wave = cap_units * unit if units % cap_units == 0 else unit
-    if mine < wave:
-        wave = (mine + 127) // 128 * 128
+    # Wave size.  A forward launch costs about the same for anything up to two 128-leaf tiles per SM (2 x 148 x 128 = 37,888
+    # leaves = `wave_cap`: the two-tiles-per-CTA kernel), and the tree kernels scale with the games, so: as few waves as the
+    # pool allows, all of the same size (one pool, one captured graph), padded to whole 128-leaf tiles.
+    tile = 128
+    n_waves = max(1, (mine + wave_cap - 1) // wave_cap)
+    wave = ((mine + n_waves - 1) // n_waves + tile - 1) // tile * tile
     sp = make_wave_player(mine, wave, sims, evaluator_factory(wave), first_game=first, use_graph=True, seed=seed, device=dev)
     names = ("features", "actions", "counts", "value", "result_p1")
     host = {"features": torch.empty((sp.PLIES, sp.n, 59), dtype=torch.float32, pin_memory=True),
@@ -211,8 +210,8 @@ def selfplay_1m(torch, dev, dist, rank, world, evaluator_factory, total, sims, w
            "game_steps_per_sec": total * PLIES / (ms * 1e-3), "scaling": "strong",
            "outcomes_p1_p2_draw": res, "d2h_bytes_per_gpu": tally["d2h"], "pool_gb": sp.mcts.pool.bytes() / 1e9,
            "gpu_launches_per_gpu": tally["waves"] * _launches_per_episode(3, sims),
-           "wave_choice": "whole rounds of the forward kernel (148 SMs x 128 leaves = 18,944 games): two rounds per wave (the pool's "
-                          "capacity) when the shard is an even number of rounds, else one; the last wave's surplus slots play games that are dropped",
+           "wave_choice": "as few equal waves as the tree pool (capacity %d games = two 128-leaf tiles per SM, one launch of the two-tiles-per-CTA "
+                          "forward) allows, padded to whole tiles; the last wave's surplus slots play games that are dropped" % wave_cap,
            "includes": "per wave: pool reset + re-deal, 48 plies x numMCTSSims simulations, example recording, device->host copy of the "
                        "examples into pinned memory; excludes the one-time setup (pool allocation, CUDA-graph capture, pinned buffers)"}
     del host, sp
