@@ -212,8 +212,9 @@ int ya_mcts_pick_action(const int32_t* counts, const int32_t* ply, const uint32_
 
 /* ---- leaf evaluator (YachtNNet.forward, yacht/pytorch/YachtNNet.py:62-70) ---- */
 /* The whole YachtNNet.forward (yacht/pytorch/YachtNNet.py:62-70) for a wave of leaves as one persistent
- * tcgen05 kernel: features float32 [n][59] (state_to_vec rows) -> 16-bit logits [n][3232] (columns >= 3226 are
- * padding) and values float32 [n] (tanh).  fp16 != 0: operands (activations, weight images) and logits are IEEE half,
+ * tcgen05 kernel: features float32 [n][59] (state_to_vec rows; contiguous -- a 16-byte aligned matrix lets whole 128-row tiles
+ * arrive by bulk copy, any other alignment works too) -> 16-bit logits [n][3232] (columns >= 3226 are padding: the dense
+ * matrix holds -inf there) and values float32 [n] (tanh).  fp16 != 0: operands (activations, weight images) and logits are IEEE half,
  * the precision of the reference's CUDA predict (fp16 autocast, yacht/NNet.py:186-193); fp16 == 0: bfloat16.
  * Accumulation, bias, SiLU, LayerNorm and the residual sum are float32 in both modes; the residual stream is stored
  * between blocks as IEEE half (with half operands: exactly the next block's operand).  weight_blob / param_blob are built once on the host

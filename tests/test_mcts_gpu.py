@@ -329,8 +329,16 @@ def test_two_tile_schedule_is_bit_identical(precision):
             ev = FusedYachtEvaluator(net, n, precision=precision, tiles_per_cta=tiles)
             logits, v = ev(x)
             outs.append((logits[:, :3226].clone(), v.clone(), ev.last_row_max.clone()))
-        for a, b in zip(*outs):
-            assert torch.equal(a.view(torch.uint8) if a.dtype == torch.bfloat16 else a, b.view(torch.uint8) if b.dtype == torch.bfloat16 else b), n
+        # a feature matrix that is only 4-byte aligned takes the per-thread loads instead of the bulk copy of whole tiles
+        x4 = torch.empty(n * 59 + 1, device="cuda")[1:].view(n, 59)
+        x4.copy_(x)
+        assert x4.data_ptr() % 16 != 0
+        ev = FusedYachtEvaluator(net, n, precision=precision, tiles_per_cta=1)
+        logits, v = ev(x4)
+        outs.append((logits[:, :3226].clone(), v.clone(), ev.last_row_max.clone()))
+        for other in outs[1:]:
+            for a, b in zip(outs[0], other):
+                assert torch.equal(a.view(torch.uint8) if a.dtype == torch.bfloat16 else a, b.view(torch.uint8) if b.dtype == torch.bfloat16 else b), n
     with pytest.raises(ValueError):
         FusedYachtEvaluator(net, 8, tiles_per_cta=3)
 
