@@ -155,6 +155,14 @@ def forward_alone(torch, dev, evaluator, leaves, reps=50):
     return f0.elapsed_time(f1) * 1000.0 / reps
 
 
+def wave_plan(games, wave_cap, tile=128):
+    """(number of waves, games per wave) for a shard of `games` games on a tree pool of `wave_cap` games: as few waves as the
+    pool allows, all of the same size, padded to whole forward tiles."""
+    n_waves = max(1, (games + wave_cap - 1) // wave_cap)
+    wave = ((games + n_waves - 1) // n_waves + tile - 1) // tile * tile
+    return n_waves, wave
+
+
 def selfplay_1m(torch, dev, dist, rank, world, evaluator_factory, total, sims, wave_cap, seed):
     """configs[4]: `total` games split over the ranks by global game id (dist.shard_range), every rank plays its shard as
     consecutive waves on ONE tree pool (coach.self_play_in_waves; simulation wave replayed as a CUDA graph) and copies every
@@ -168,9 +176,7 @@ def selfplay_1m(torch, dev, dist, rank, world, evaluator_factory, total, sims, w
     # Wave size.  A forward launch costs about the same for anything up to two 128-leaf tiles per SM (2 x 148 x 128 = 37,888
     # leaves = `wave_cap`: the two-tiles-per-CTA kernel), and the tree kernels scale with the games, so: as few waves as the
     # pool allows, all of the same size (one pool, one captured graph), padded to whole 128-leaf tiles.
-    tile = 128
-    n_waves = max(1, (mine + wave_cap - 1) // wave_cap)
-    wave = ((mine + n_waves - 1) // n_waves + tile - 1) // tile * tile
+    wave = wave_plan(mine, wave_cap)[1]
     sp = make_wave_player(mine, wave, sims, evaluator_factory(wave), first_game=first, use_graph=True, seed=seed, device=dev)
     names = ("features", "actions", "counts", "value", "result_p1")
     host = {"features": torch.empty((sp.PLIES, sp.n, 59), dtype=torch.float32, pin_memory=True),
