@@ -78,12 +78,16 @@ class UniformEvaluator:
 
 class FusedYachtEvaluator:
     """The yacht NNet forward (yacht/pytorch/YachtNNet.py:62-70) for a whole wave of leaves as ONE hand-written
-    tcgen05 kernel (csrc/ya_forward.cu): features in, 16-bit logits padded to 3232 columns + tanh value + per-row
-    max logit out, consumed by ya_mcts_expand_logits; rows do not depend on the batch they sit in.
+    tcgen05 kernel on CTA pairs (csrc/ya_forward.cu): features in; tanh value, per-row max logit and the 16-bit policy
+    logits out -- scattered straight into the leaves' rows of the tree pool (scatter=...), or as a dense matrix padded to
+    3232 columns -- consumed by ya_mcts_expand_logits; rows do not depend on the batch they sit in.
 
-    precision="fp16" (default): activations, weights and logits in IEEE half with float32 accumulation, LayerNorm
-    and skip connection -- the arithmetic of the reference's CUDA predict (fp16 autocast, yacht/NNet.py:186-193).
+    precision="fp16" (default): activations, weights and logits in IEEE half; accumulation, bias, SiLU, LayerNorm and the
+    residual sum in float32 (the residual stream is stored as half between blocks) -- inside the error of the reference's
+    CUDA predict (fp16 autocast, yacht/NNet.py:186-193).
     precision="bf16": the same kernel with bfloat16 operands (same tensor-core rate, 8-bit mantissa).
+    tiles_per_cta: 1 = one 128-leaf tile per CTA, 2 = two (the tensor core works on one tile under the other tile's
+    epilogue: for waves above one tile per SM), 0 = by wave size.  Scheduling only: the rows are bit-identical.
     Weights come from any module with YachtNNet's state dict (:25-52), hidden width 256 (main.py:40)."""
     uniform = False
     returns_logits = True
