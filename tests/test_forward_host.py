@@ -65,3 +65,21 @@ def test_wave_plan():
     for games in (1, 127, 128, 129, 37888, 37889, 75776, 1000003):
         n, wave = wave_plan(games, cap)
         assert wave % 128 == 0 and wave <= cap and n * wave >= games and (n - 1) * wave < games
+
+
+def test_wave_plans_of_the_shards_cover_every_game_once():
+    """configs[4] strong scaling: for every GPU count the shards (dist.shard_range) and their waves (wave_plan) tile the
+    global game ids 0 .. total - 1 exactly once -- the games a wave plays are first_game + w * wave + slot for the live
+    slots, which is what keys the Philox streams, so the set of games does not depend on the GPU count."""
+    from nypc_yacht_auction_b200.dist import shard_range
+    total, cap = 1 << 20, 2 * 148 * 128
+    for world in (1, 2, 4, 8):
+        covered = 0
+        for rank in range(world):
+            first, last = shard_range(total, rank, world)
+            assert first == covered
+            n_waves, wave = wave_plan(last - first, cap)
+            live = [min(wave, last - first - w * wave) for w in range(n_waves)]
+            assert all(x > 0 for x in live) and sum(live) == last - first
+            covered = last
+        assert covered == total
