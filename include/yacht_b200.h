@@ -219,7 +219,8 @@ int ya_mcts_pick_action(const int32_t* counts, const int32_t* ply, const uint32_
  * Accumulation, bias, SiLU, LayerNorm and the residual sum are float32 in both modes; the residual stream is stored
  * between blocks as IEEE half (with half operands: exactly the next block's operand).  weight_blob / param_blob are built once on the host
  * (mcts.FusedYachtEvaluator): 128-byte-swizzled K-major images of W_in (K padded to 64), the 2*nblocks trunk
- * weights, the value head's first Linear and 26 policy-head tiles of 128 columns; biases and LayerNorm
+ * weights, the value head's first Linear and 26 policy-head tiles of 128 columns, every matrix split by output columns
+ * into the halves the two CTAs of a pair hold (layout: mcts.FusedYachtEvaluator.pair_image; tests/test_forward_host.py); biases and LayerNorm
  * parameters as float32.  offsets (HOST pointer, int64[9]) = byte offsets {w_in, w_trunk, w_v, w_pi} and float
  * offsets {p_in, p_trunk, p_v, p_pi_ln, p_pi_bias}.  hidden width 256 only.  Rows are independent of the
  * batch they sit in (batch-invariant evaluator).  row_max float32[n] (may be NULL) receives each row's largest
